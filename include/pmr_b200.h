@@ -1,0 +1,213 @@
+/*
+ * pmr_b200.h -- C ABI of libpmr_b200.so, the B200 (sm_100a) implementation of
+ * pymolresponse's linear-response hot path.
+ *
+ * The reference (berquist/pymolresponse) is pure Python/NumPy: there is no FFI in it.  The
+ * seam this library sits behind is the reference's Python function/class API; each entry
+ * point below names the reference call site (file:line under /root/reference/pymolresponse/)
+ * whose arithmetic it replaces.  INTEGRATION.md shows the ctypes binding a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to FP64 data unless the name ends in _host;
+ *   - all matrices are C-order (row-major) with explicit element strides;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it;
+ *   - return value: 0 on success, negative pmr_status on error (pmr_last_error() has text);
+ *   - factorisation failure (non-SPD / singular) is reported through a device int `info`
+ *     (0 = ok, k>0 = first bad pivot, 1-based), never through the return value.
+ *   - no global state except a per-thread error string; thread-safe per stream.
+ */
+#ifndef PMR_B200_H
+#define PMR_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  PMR_OK = 0,
+  PMR_ERR_ARG = -1,      /* bad argument (shape / stride / null pointer) */
+  PMR_ERR_CUDA = -2,     /* CUDA runtime error (launch, attribute, ...)   */
+  PMR_ERR_WORKSPACE = -3 /* workspace too small                           */
+} pmr_status;
+
+int pmr_version(void);
+const char* pmr_last_error(void);
+/* Number of kernels this library launched from the calling thread since the last reset. */
+long long pmr_launch_count(void);
+void pmr_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * FP64 DMMA GEMM:  C(m,n) = alpha * sum_k A(m,k) B(k,n) + beta * C(m,n), batched two levels.
+ * A(m,k) = A[m*a_sm + k*a_sk], B(k,n) = B[k*b_sk + n*b_sn], C(m,n) = C[m*c_sm + n*c_sn];
+ * for A and for B one of the two strides must be 1.  This is the building block behind
+ *   ao2mo.py:45-49 (np.dot + three einsum quarter transforms),
+ *   solvers.py:505,527-530 (inverse / Cholesky trailing updates),
+ *   operators.py:85-87 (C_v^T O C_o), utils.py:26 (P R^T).
+ * ---------------------------------------------------------------------------------------- */
+#define PMR_GEMM_LOWER 1      /* write only C(m,n) with n <= m; tiles above the diagonal skipped */
+#define PMR_GEMM_KSTART_M 2   /* operands vanish for k < m-tile origin: start the k loop there  */
+#define PMR_GEMM_KEND_M 4     /* operands vanish for k >= m-tile end: stop the k loop there     */
+
+typedef struct {
+  int M, N, K;
+  double alpha, beta;
+  const double* A;
+  long long a_sm, a_sk;
+  const double* B;
+  long long b_sk, b_sn;
+  double* C;
+  long long c_sm, c_sn;
+  int batch1, batch2;                           /* >= 1 each */
+  long long a_b1, a_b2, b_b1, b_b2, c_b1, c_b2; /* element strides per batch index */
+  int flags;
+} pmr_gemm_t;
+
+int pmr_dgemm(const pmr_gemm_t* g, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * AO -> MO two-electron integral transformation.
+ * pmr_ao2mo_transform: AO2MO.transform (ao2mo.py:35-50), quarters in index order 1,2,3,4.
+ *   I is (n,n,n,n); Ck is (n x dk) with row stride ldck; out is (d1,d2,d3,d4) C-order.
+ * pmr_ao2mo_partial: the occupied-first chain that produces the blocks of
+ *   AO2MO.perform_rhf_partial (ao2mo.py:58-70) / AO2MOpyscf.perform_uhf_partial
+ *   (interfaces/pyscf/ao2mo.py:71-109) from ONE shared first quarter per bra spin:
+ *     ovov_k[i,a,j,b] = (i a | j_k b_k)  for k < n_ket   (ket spin k has its own Co2/Cv2)
+ *     oovv  [i,j,a,b] = (i j | a b)      if oovv != NULL (bra spin only)
+ *   I_slab holds I[:, nu_lo:nu_hi, :, :] as (n, nu_cnt, n, n) C-order: the AO ERI tensor sharded
+ *   over the second index of the first AO pair; partial sums over the local nu are ACCUMULATED
+ *   into ovov/oovv when `accumulate` != 0 (ranks then sum with one reduce per block).
+ * Workspace sizes in doubles come from the *_workspace functions.
+ * ---------------------------------------------------------------------------------------- */
+long long pmr_ao2mo_transform_workspace(int n, int d1, int d2, int d3, int d4);
+int pmr_ao2mo_transform(const double* I, int n, const double* C1, int ldc1, int d1,
+                        const double* C2, int ldc2, int d2, const double* C3, int ldc3, int d3,
+                        const double* C4, int ldc4, int d4, double* out, double* workspace,
+                        long long workspace_doubles, void* stream);
+
+typedef struct {
+  const double* Co2; /* (n x o2) ket occupied coefficients, row stride ldc2 */
+  const double* Cv2; /* (n x v2) ket virtual coefficients, row stride ldc2  */
+  int ldc2, o2, v2;
+  double* ovov; /* (o1, v1, o2, v2) C-order output */
+} pmr_ao2mo_ket_t;
+
+long long pmr_ao2mo_partial_workspace(int n, int nu_cnt, int o1, int v1, int n_ket,
+                                      const pmr_ao2mo_ket_t* kets, int want_oovv, int nu_block);
+int pmr_ao2mo_partial(const double* I_slab, int n, int nu_lo, int nu_cnt, const double* Co1,
+                      const double* Cv1, int ldc1, int o1, int v1, int n_ket,
+                      const pmr_ao2mo_ket_t* kets, double* oovv, int accumulate, int nu_block,
+                      double* workspace, long long workspace_doubles, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Orbital-Hessian block assembly (explicit_equations_partial.py:8-214,
+ * explicit_equations_full.py:8-238).  One bandwidth-bound gather kernel:
+ *   P[ia,jb] = c1 * T1[(i,a,j,b)] - c2 * T2[(i,a,j,b)] + delta(ia,jb) * (ev[a] - eo[i])
+ *   Q[ia,jb] = -(c1q * U1[(i,a,j,b)] - c2q * U2[(i,a,j,b)])
+ * with each operand addressed by four element strides (partial AND full layouts are both
+ * expressible).  Outputs: out_mode 0 -> (A = P, B = Q) ; out_mode 1 -> (M = P - Q, K = P + Q),
+ * the A-B / A+B matrices the half-size solver consumes.  Either output pointer may be NULL.
+ * ia = i*nv_x + a (a fast), jb = j*nv_y + b.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  const double* ptr; /* NULL => term absent */
+  long long s_i, s_a, s_j, s_b;
+  double coef;
+} pmr_gather_term_t;
+
+typedef struct {
+  int no_x, nv_x, no_y, nv_y; /* row space (i,a), column space (j,b) */
+  pmr_gather_term_t p1, p2;   /* P = p1.coef*p1 - p2.coef*p2 (+ diagonal) */
+  pmr_gather_term_t q1, q2;   /* Q = -(q1.coef*q1 - q2.coef*q2) */
+  const double* eps_occ;      /* NULL => no diagonal */
+  const double* eps_virt;
+  int out_mode;               /* 0: (P,Q)  1: (P-Q, P+Q) */
+  int i_lo, i_hi;             /* only rows with i in [i_lo, i_hi) are produced (row-block shard) */
+  double* out0;
+  double* out1;
+  long long ld0, ld1;         /* row strides of the outputs (row index is global ia) */
+} pmr_assemble_t;
+
+int pmr_assemble(const pmr_assemble_t* a, void* stream);
+/* ediff[i*nv + a] = eps_virt[a] - eps_occ[i]  (utils.py:326-347) */
+int pmr_energy_differences(const double* eps_occ, int no, const double* eps_virt, int nv,
+                           double* ediff, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense factorisations and solves (replacing np.linalg.inv / scipy cholesky+inv,
+ * solvers.py:499-555, and the G^-1 . rhs products, solvers.py:401-466).
+ * All matrices row-major; `batch` independent problems at element stride `stride_*`.
+ * Cholesky: lower factor L (A = L L^T) overwrites the lower triangle; the strictly upper
+ * triangle is neither read nor written.  `dinv` receives the inverses of the 128x128
+ * diagonal blocks of L (needed by the solves): pmr_potrf_dinv_doubles(N) doubles per matrix.
+ * ---------------------------------------------------------------------------------------- */
+long long pmr_potrf_dinv_doubles(int N);
+int pmr_potrf(double* A, int N, long long lda, int batch, long long stride_a, double* dinv,
+              int* info /* device, batch ints */, void* stream);
+/* Solve A X = B in place of B (B is N x nrhs, row stride ldb); `work` has N*nrhs doubles/batch. */
+int pmr_potrs(const double* L, int N, long long lda, int batch, long long stride_l,
+              const double* dinv, double* B, int nrhs, long long ldb, long long stride_b,
+              double* work, void* stream);
+/* Lower triangle of A^-1 from the Cholesky factor (out may not alias L); work: N*N doubles. */
+int pmr_potri_lower(const double* L, int N, long long lda, const double* dinv, double* out,
+                    long long ldo, double* work, void* stream);
+/* S_f = M + shift_a[f] * I + shift_b[f] * W on the lower triangle, f < nf (frequency batch). */
+int pmr_shifted_combine(const double* M, const double* W, int N, long long ldm, long long ldw,
+                        const double* shift_a_host, const double* shift_b_host, int nf,
+                        double* S, long long lds, long long stride_s, void* stream);
+/* A[i][i] += value, i < N (frequency shift of the explicit super-Hessian, solvers.py:230-231) */
+int pmr_shift_diagonal(double* A, int N, long long lda, double value, void* stream);
+/* LU with partial pivoting (general / above-pole case): row-major A = P L U in place. */
+int pmr_getrf(double* A, int N, long long lda, int* ipiv /* device, N */, int* info,
+              double* work /* pmr_getrf_work_doubles(N) */, void* stream);
+long long pmr_getrf_work_doubles(int N);
+int pmr_getrs(const double* LU, int N, long long lda, const int* ipiv, double* B, int nrhs,
+              long long ldb, double* work /* N*nrhs */, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Operator right-hand sides and property contraction
+ * (operators.py:57-125, utils.py:17-27, cphf.py:68-253).
+ * ---------------------------------------------------------------------------------------- */
+/* rhs[c, 0:nov] = scale * vec(C_v^T O_c C_o) (index i*nv+a), rhs[c, nov:2nov] = sign * same.
+ * mask (device, nov ints or NULL): entries with mask != 0 are zeroed (triplet operators). */
+int pmr_form_rhs(const double* O, int ncomp, int n, const double* C, int ldc, int nocc,
+                 double sign, double scale, const int* mask, double* rhs /* ncomp x 2nov */,
+                 double* rhs_ai /* ncomp x nov or NULL */, double* workspace /* ncomp*n*nocc */,
+                 void* stream);
+/* out[a,b] = pref * sum_k P[a,k] R[b,k]; partial: nblocks*nP*nR doubles of workspace. */
+long long pmr_contract_workspace(int nP, int nR, long long len);
+int pmr_contract_results(const double* P, int nP, long long ldp, const double* R, int nR,
+                         long long ldr, long long len, double pref, double* out /* nP x nR */,
+                         double* workspace, void* stream);
+/* Elementwise helpers used by the half-size solver:
+ *   xy[c,0:nov] = (p+m)/2, xy[c,nov:2nov] = (p-m)/2   (supervector [X;Y], solvers.py:418-425) */
+int pmr_pm_to_xy(const double* p, const double* m, int ncomp, long long nov, long long ldp,
+                 long long ldm, double* xy, long long ldxy, void* stream);
+/* y = a*x + b*y on ncols x nrows strided blocks */
+int pmr_axpby(long long rows, long long cols, double a, const double* x, long long ldx, double b,
+              double* y, long long ldy, void* stream);
+/* out[c,k] = in[c,k] / (ediff[k mod nov] -/+ w)  (uncoupled response, cphf.py:94-141) */
+int pmr_uncoupled_divide(const double* sv, int ncomp, long long nov, const double* ediff, double w,
+                         double* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Matrix-free path (IterativeLinEqSolver, solvers.py:603-630; JK contract integrals.py:41-67):
+ *   J_d[p,q] = sum_rs I[p,q,r,s] D_d[r,s],  K_d[p,q] = sum_rs I[p,r,q,s] D_d[r,s]
+ * for nd densities in ONE pass over the AO ERI tensor.
+ * ---------------------------------------------------------------------------------------- */
+int pmr_jk_contract(const double* I, int n, const double* D /* nd x n x n */, int nd,
+                    double* J /* nd x n x n */, double* K /* nd x n x n */, void* stream);
+
+/* One fixed-point sweep of the reference's iterative CPHF (solvers.py:621-637) for ncomp
+ * (n x n) amplitude matrices x: on the occupied-virtual and virtual-occupied blocks
+ *   x += (rhs - (x * d - G)) / d,   d[p,q] = eps[p] - eps[q] - omega,  G = C^T (2J1-K1+2J2-K2) C
+ * and maxdiff[c] = max over all elements of (x_new - x_old) (signed, as the reference). */
+int pmr_cphf_update(double* x, const double* x_old, const double* rhs, const double* G,
+                    const double* eps, double omega, int n, int nocc, int ncomp,
+                    int init /* 1: x = uncoupled guess rhs/(+-(e_a-e_i-w)), solvers.py:606-611 */,
+                    double* maxdiff /* device, ncomp */, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMR_B200_H */

@@ -1,0 +1,283 @@
+"""Device-resident linear-response engine behind the ExactInv / ExactInvCholesky solvers.
+
+The reference builds the (2 nov)^2 super-Hessian ``G(w) = [[A-w, B],[B, A+w]]`` and calls
+``np.linalg.inv`` on it once per frequency (solvers.py:166-231, 468-505).  With
+``K = A + B``, ``M = A - B``, ``p = X + Y``, ``m = X - Y`` and a right-hand side ``[g; s g]``
+(s = -1 real operator, +1 imaginary; operators.py:75-77) the same equations read
+
+    K p - w m = (1 + s) g            M m - w p = (1 - s) g
+
+so for every frequency   S(w) m = (1 - s) g + w (1 + s) K^-1 g,   S(w) = M - w^2 K^-1
+                         K p    = (1 + s) g + w m
+
+with K, M and S(w) symmetric positive definite below the first pole: three Cholesky
+factorisations of size nov instead of an LU + explicit inverse of size 2 nov, and ALL
+frequencies are factorised in ONE batched call (the GPU analogue of "one solve per frequency",
+and what keeps the serial 128-wide panel steps off the critical path).  For UHF the alpha and
+beta excitation spaces are stacked; TDA is the special case K = M = A.
+When a factorisation reports a non-positive pivot (w above the first pole, unstable reference)
+the affected frequencies fall back to LU with partial pivoting on the full G(w).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from pymolresponse_b200 import _native as nv
+
+
+def _darr(vals):
+    arr = (C.c_double * len(vals))(*[float(v) for v in vals])
+    return arr
+
+
+def potrf(A, batch=1):
+    """In-place batched lower Cholesky of (batch, N, N) / (N, N) tensor -> (dinv, info tensor)."""
+    L = nv.lib()
+    N = int(A.shape[-1])
+    lda = int(A.stride(-2))
+    stride = int(A.stride(0)) if A.dim() == 3 else 0
+    torch = nv.torch_mod()
+    dinv = nv.empty(batch, max(1, int(L.pmr_potrf_dinv_doubles(N))))
+    info = torch.zeros(batch, dtype=torch.int32, device=nv.device())
+    nv.check(L.pmr_potrf(nv.ptr(A), N, lda, batch, stride, nv.ptr(dinv), nv.ptr(info),
+                         nv.stream_ptr()))
+    return dinv, info
+
+
+def potrs(Lfac, dinv, B, batch=1):
+    """Solve in place: B is (batch, N, nrhs) or (N, nrhs), contiguous."""
+    L = nv.lib()
+    N = int(Lfac.shape[-1])
+    nrhs = int(B.shape[-1])
+    if N == 0 or nrhs == 0:
+        return B
+    lda = int(Lfac.stride(-2))
+    sl = int(Lfac.stride(0)) if Lfac.dim() == 3 else 0
+    sb = int(B.stride(0)) if B.dim() == 3 else 0
+    work = nv.empty(batch, N, nrhs)
+    nv.check(L.pmr_potrs(nv.ptr(Lfac), N, lda, batch, sl, nv.ptr(dinv), nv.ptr(B), nrhs,
+                         int(B.stride(-2)), sb, nv.ptr(work), nv.stream_ptr()))
+    return B
+
+
+def potri_lower(Lfac, dinv):
+    L = nv.lib()
+    N = int(Lfac.shape[-1])
+    out = nv.empty(N, N)
+    work = nv.empty(N, N)
+    nv.check(L.pmr_potri_lower(nv.ptr(Lfac), N, int(Lfac.stride(0)), nv.ptr(dinv), nv.ptr(out), N,
+                               nv.ptr(work), nv.stream_ptr()))
+    return out
+
+
+def shifted_combine(M, W, shift_a, shift_b):
+    """S_f(lower) = M + shift_a[f] I + shift_b[f] W for all f -> (nf, N, N)."""
+    L = nv.lib()
+    N = int(M.shape[0])
+    nf = len(shift_a)
+    S = nv.empty(nf, N, N)
+    nv.check(L.pmr_shifted_combine(nv.ptr(M), nv.ptr(W) if W is not None else C.c_void_p(0), N,
+                                   int(M.stride(0)), int(W.stride(0)) if W is not None else N,
+                                   _darr(shift_a), _darr(shift_b), nf, nv.ptr(S), N, N * N,
+                                   nv.stream_ptr()))
+    return S
+
+
+def axpby(a, x, b, y):
+    """y = a*x + b*y on 2-D tensors whose last dimension is contiguous (row strides free)."""
+    rows, cols = int(y.shape[0]), int(y.shape[1])
+    assert y.stride(1) == 1 and (x is None or x.stride(1) == 1)
+    r0 = 0
+    while r0 < rows:  # grid.y limit
+        r1 = min(rows, r0 + 65535)
+        nv.check(nv.lib().pmr_axpby(r1 - r0, cols, float(a),
+                                    nv.ptr(x, r0 * int(x.stride(0))) if x is not None else C.c_void_p(0),
+                                    int(x.stride(0)) if x is not None else 0, float(b),
+                                    nv.ptr(y, r0 * int(y.stride(0))), int(y.stride(0)),
+                                    nv.stream_ptr()))
+        r0 = r1
+    return y
+
+
+def getrf(A):
+    L = nv.lib()
+    torch = nv.torch_mod()
+    N = int(A.shape[0])
+    ipiv = torch.zeros(max(1, N), dtype=torch.int32, device=nv.device())
+    info = torch.zeros(1, dtype=torch.int32, device=nv.device())
+    work = nv.empty(int(L.pmr_getrf_work_doubles(N)))
+    nv.check(L.pmr_getrf(nv.ptr(A), N, int(A.stride(0)), nv.ptr(ipiv), nv.ptr(info), nv.ptr(work),
+                         nv.stream_ptr()))
+    return ipiv, info
+
+
+def getrs(LU, ipiv, B):
+    L = nv.lib()
+    N, nrhs = int(B.shape[0]), int(B.shape[1])
+    work = nv.empty(max(1, N * nrhs))
+    nv.check(L.pmr_getrs(nv.ptr(LU), N, int(LU.stride(0)), nv.ptr(ipiv), nv.ptr(B), nrhs,
+                         int(B.stride(0)), nv.ptr(work), nv.stream_ptr()))
+    return B
+
+
+def shift_diagonal(A, n, value, offset=0):
+    nv.check(nv.lib().pmr_shift_diagonal(nv.ptr(A, offset), int(n), int(A.stride(0)), float(value),
+                                         nv.stream_ptr()))
+
+
+def super_hessian(A, B, frequency):
+    """G(w) = [[A, B],[B, A]] - w diag(1, -1) on the device (solvers.py:179-187, 230-231)."""
+    N = int(A.shape[0])
+    G = nv.empty(2 * N, 2 * N)
+    G[:N, :N].copy_(A)
+    G[N:, N:].copy_(A)
+    if B is None:
+        G[:N, N:].zero_()
+        G[N:, :N].zero_()
+    else:
+        G[:N, N:].copy_(B)
+        G[N:, :N].copy_(B)
+    if frequency != 0.0:
+        shift_diagonal(G, N, -frequency, 0)
+        shift_diagonal(G, N, +frequency, N * 2 * N + N)
+    return G
+
+
+class LinAlgError(np.linalg.LinAlgError):
+    pass
+
+
+class HalfSizeSystem:
+    """K = A + B_ref and M = A - B_ref on the device; solves all frequencies and columns."""
+
+    def __init__(self, M, K, A=None, B=None, memory_fraction: float = 0.45):
+        self.M, self.K = M, K   # lower triangles are what the factorisations read
+        self.A, self.B = A, B   # only kept when the LU fallback / explicit G may be needed
+        self.N = int(M.shape[0])
+        self.memory_fraction = memory_fraction
+        self.stats = {"potrf": 0, "potrf_batch": 0, "potri": 0, "lu_fallback": 0}
+
+    def _chunk(self, nf):
+        torch = nv.torch_mod()
+        free, _ = torch.cuda.mem_get_info()
+        per = max(1, self.N * self.N * 8)
+        return int(max(1, min(nf, (free * self.memory_fraction) // per)))
+
+    def solve(self, g_rows, signs, frequencies, allow_fallback=True):
+        """g_rows: (ncols, N) CUDA tensor of property gradients g (first half of the supervector);
+        signs[c] = -1 (real) / +1 (imaginary).  Returns xy: (nf, ncols, 2N) CUDA tensor of
+        supervector solutions [X; Y] of G(w) [X;Y] = [g; s g]."""
+        N = self.N
+        nf, ncols = len(frequencies), int(g_rows.shape[0])
+        xy = nv.zeros(nf, ncols, 2 * N)
+        if N == 0 or ncols == 0 or nf == 0:
+            return xy
+        signs = [int(s) for s in signs]
+        real_cols = [c for c, s in enumerate(signs) if s < 0]
+        imag_cols = [c for c, s in enumerate(signs) if s > 0]
+        freqs = [float(w) for w in frequencies]
+        any_dyn = any(w != 0.0 for w in freqs)
+        need_K = any_dyn or bool(imag_cols)
+        G = g_rows.t().contiguous()  # (N, ncols)
+
+        Kfac = dinvK = Kinv = T = None
+        bad = set()
+        if need_K:
+            Kfac = self.K.clone()
+            dinvK, infoK = potrf(Kfac)
+            self.stats["potrf"] += 1
+            if int(infoK.item()) != 0:
+                bad = set(range(nf))  # K itself is not SPD: everything goes to LU
+        if not bad and any_dyn:
+            Kinv = potri_lower(Kfac, dinvK)
+            self.stats["potri"] += 1
+        if not bad and any_dyn and imag_cols:
+            T = G[:, imag_cols].contiguous()
+            potrs(Kfac, dinvK, T)  # T = K^-1 g for the imaginary columns
+
+        if not bad:
+            step = self._chunk(nf)
+            for f0 in range(0, nf, step):
+                fs = list(range(f0, min(nf, f0 + step)))
+                ws = [freqs[f] for f in fs]
+                nfc = len(fs)
+                # all frequencies of the chunk are built and factorised together
+                need_m = bool(real_cols) or any(w != 0.0 for w in ws)
+                rhs_m = nv.zeros(nfc, N, ncols)
+                S = dinvS = None
+                infos = np.zeros(nfc, dtype=np.int32)
+                if need_m:
+                    S = shifted_combine(self.M, Kinv if any_dyn else None, [0.0] * nfc,
+                                        [-(w * w) for w in ws])
+                    dinvS, infoS = potrf(S, batch=nfc)
+                    self.stats["potrf_batch"] += nfc
+                    infos = infoS.cpu().numpy()
+                two_g_real = None
+                if real_cols:
+                    two_g_real = axpby(2.0, G[:, real_cols].contiguous(), 0.0,
+                                       nv.empty(N, len(real_cols)))
+                for q, w in enumerate(ws):
+                    if real_cols:
+                        rhs_m[q][:, real_cols] = two_g_real
+                    if imag_cols and w != 0.0:
+                        rhs_m[q][:, imag_cols] = axpby(2.0 * w, T, 0.0, nv.empty(N, len(imag_cols)))
+                if need_m:
+                    potrs(S, dinvS, rhs_m, batch=nfc)  # rhs_m now holds m_f
+                # p_f = K^-1 ((1+s) g + w m_f)
+                need_p = bool(imag_cols) or any(w != 0.0 for w in ws)
+                p_all = None
+                if need_p:
+                    p_all = nv.zeros(N, nfc * ncols)
+                    for q, w in enumerate(ws):
+                        blk = p_all[:, q * ncols:(q + 1) * ncols]
+                        if w != 0.0:
+                            axpby(w, rhs_m[q], 0.0, blk)
+                        if imag_cols:
+                            tmp = blk[:, imag_cols].contiguous()
+                            axpby(2.0, G[:, imag_cols].contiguous(), 1.0, tmp)
+                            blk[:, imag_cols] = tmp
+                    potrs(Kfac, dinvK, p_all)
+                for q, f in enumerate(fs):
+                    if infos[q] != 0:
+                        bad.add(f)
+                        continue
+                    m_rows = rhs_m[q].t().contiguous()
+                    p_rows = (p_all[:, q * ncols:(q + 1) * ncols].t().contiguous()
+                              if p_all is not None else None)
+                    nv.check(nv.lib().pmr_pm_to_xy(
+                        nv.ptr(p_rows) if p_rows is not None else C.c_void_p(0), nv.ptr(m_rows),
+                        ncols, N, N, N, nv.ptr(xy[f]), 2 * N, nv.stream_ptr()))
+                del S, dinvS, rhs_m, p_all
+
+        if bad:
+            if not allow_fallback:
+                raise LinAlgError(
+                    "orbital Hessian is not positive definite at frequencies "
+                    f"{[freqs[f] for f in sorted(bad)]} (Cholesky failed)")
+            for f in sorted(bad):
+                xy[f].copy_(self.solve_lu(g_rows, signs, freqs[f]))
+                self.stats["lu_fallback"] += 1
+        return xy
+
+    def solve_lu(self, g_rows, signs, w):
+        """General path: LU with partial pivoting on the full super-Hessian G(w)."""
+        assert self.A is not None, "LU fallback needs the A and B blocks"
+        N = self.N
+        ncols = int(g_rows.shape[0])
+        G = super_hessian(self.A, self.B, w)
+        ipiv, info = getrf(G)
+        if int(info.item()) != 0:
+            raise LinAlgError(f"super-Hessian is singular at frequency {w}")
+        rhs = nv.zeros(2 * N, ncols)
+        Gt = g_rows.t().contiguous()
+        axpby(1.0, Gt, 0.0, rhs[:N])
+        for c, s in enumerate(signs):
+            col = Gt[:, c:c + 1].contiguous()
+            tmp = nv.empty(N, 1)
+            axpby(float(s), col, 0.0, tmp)
+            rhs[N:, c:c + 1] = tmp
+        getrs(G, ipiv, rhs)
+        return rhs.t().contiguous()

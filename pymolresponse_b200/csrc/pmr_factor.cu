@@ -1,0 +1,485 @@
+// Dense factorisations and triangular solves built on the DMMA GEMM (pmr_gemm.cu).
+//
+// Replaces np.linalg.inv / scipy.linalg.cholesky + inv (solvers.py:499-555) and the
+// G^-1 . rhs products (solvers.py:401-466) of the reference.  No explicit inverse of the
+// Hessian is ever formed on the product path.
+//
+// Cholesky (right-looking, NB = 128, batched over independent matrices = frequencies):
+//   1. potf2_trtri_kernel: one CTA per matrix factors the 128x128 diagonal block in shared
+//      memory and writes inv(L_kk) (one warp per column, register-resident substitution);
+//   2. panel:     A21 <- A21 * inv(L_kk)^T            (DMMA GEMM, in place, N = 128 = one tile)
+//   3. trailing:  A22 <- A22 - A21 A21^T  (lower)     (DMMA GEMM, PMR_GEMM_LOWER)
+// Triangular solves use the stored diagonal-block inverses, so every step is a GEMM.
+#include <algorithm>
+#include <vector>
+
+#include "pmr_common.cuh"
+
+namespace pmr {
+namespace {
+
+constexpr int NB = 128;
+constexpr int NBLD = NB + 1;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+__global__ void __launch_bounds__(1024, 1)
+potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, int jb,
+                   double* __restrict__ dinv, long long stride_dinv, int* __restrict__ info,
+                   int k0) {
+  extern __shared__ double L[];  // [NB][NBLD]
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  A += (long long)blockIdx.x * stride_a;
+  dinv += (long long)blockIdx.x * stride_dinv;
+  info += blockIdx.x;
+
+  for (int idx = tid; idx < jb * jb; idx += 1024) {
+    const int r = idx / jb, c = idx - r * jb;
+    L[r * NBLD + c] = (c <= r) ? A[(long long)r * lda + c] : 0.0;
+  }
+
+  for (int j = 0; j < jb; ++j) {
+    __syncthreads();
+    const double d = L[j * NBLD + j];
+    if (!(d > 0.0)) {
+      if (tid == 0 && *info == 0) *info = k0 + j + 1;
+    }
+    const double ljj = sqrt(d);
+    for (int i = j + 1 + tid; i < jb; i += 1024) L[i * NBLD + j] /= ljj;
+    __syncthreads();
+    if (tid == 0) L[j * NBLD + j] = ljj;
+    for (int i = j + 1 + warp; i < jb; i += 32) {
+      const double lij = L[i * NBLD + j];
+      for (int k = j + 1 + lane; k <= i; k += 32) L[i * NBLD + k] -= lij * L[k * NBLD + j];
+    }
+  }
+  __syncthreads();
+
+  for (int idx = tid; idx < jb * jb; idx += 1024) {
+    const int r = idx / jb, c = idx - r * jb;
+    if (c <= r) A[(long long)r * lda + c] = L[r * NBLD + c];
+  }
+
+  // inv(L): warp w solves L x = e_c for columns c = w, w+32, ...; lane owns x[k], k = lane (mod 32)
+  for (int c = warp; c < jb; c += 32) {
+    double xr[NB / 32];
+#pragma unroll
+    for (int q = 0; q < NB / 32; ++q) xr[q] = 0.0;
+    for (int i = c; i < jb; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < NB / 32; ++q) {
+        const int k = q * 32 + lane;
+        if (k >= c && k < i) s += L[i * NBLD + k] * xr[q];
+      }
+      s = warp_sum(s);
+      const double xi = ((i == c ? 1.0 : 0.0) - s) / L[i * NBLD + i];
+#pragma unroll
+      for (int q = 0; q < NB / 32; ++q)
+        if (q == (i >> 5) && lane == (i & 31)) xr[q] = xi;
+      if (lane == 0) dinv[(long long)i * NB + c] = xi;
+    }
+  }
+}
+
+__global__ void shifted_combine_kernel(const double* __restrict__ M, const double* __restrict__ W,
+                                       int N, long long ldm, long long ldw, int nf,
+                                       double* __restrict__ S, long long lds, long long stride_s,
+                                       const double* __restrict__ shifts /* 2*nf on device */) {
+  const int row = blockIdx.y;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col > row || col >= N) return;
+  const double m = M[(long long)row * ldm + col];
+  const double w = W ? W[(long long)row * ldw + col] : 0.0;
+  for (int f = 0; f < nf; ++f) {
+    double v = m + shifts[nf + f] * w;
+    if (col == row) v += shifts[f];
+    S[(long long)f * stride_s + (long long)row * lds + col] = v;
+  }
+}
+
+__global__ void copy_block_kernel(const double* __restrict__ src, long long lds,
+                                  double* __restrict__ dst, long long ldd, int rows, int cols) {
+  const int r = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows && c < cols) dst[(long long)r * ldd + c] = src[(long long)r * lds + c];
+}
+
+// ------------------------------------------------------------------------------------ LU
+constexpr int PB = 64;  // LU panel width
+
+// stage 1 of the pivot search in column j over rows [j, N)
+__global__ void lu_pivot_partial_kernel(const double* __restrict__ A, long long lda, int N, int j,
+                                        double* __restrict__ pval, int* __restrict__ pidx) {
+  __shared__ double sv[256];
+  __shared__ int si[256];
+  double best = -1.0;
+  int bi = j;
+  for (int i = j + blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    const double v = fabs(A[(long long)i * lda + j]);
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+  sv[threadIdx.x] = best;
+  si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      const double v = sv[threadIdx.x + s];
+      const int i2 = si[threadIdx.x + s];
+      if (v > sv[threadIdx.x] || (v == sv[threadIdx.x] && i2 < si[threadIdx.x])) {
+        sv[threadIdx.x] = v;
+        si[threadIdx.x] = i2;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { pval[blockIdx.x] = sv[0]; pidx[blockIdx.x] = si[0]; }
+}
+
+// stage 2: pick the pivot, record it, swap rows j <-> p over all N columns
+__global__ void lu_pivot_swap_kernel(double* __restrict__ A, long long lda, int N, int j,
+                                     const double* __restrict__ pval, const int* __restrict__ pidx,
+                                     int nparts, int* __restrict__ ipiv, int* __restrict__ info) {
+  __shared__ int sp;
+  if (threadIdx.x == 0) {
+    double best = -1.0;
+    int bi = j;
+    for (int q = 0; q < nparts; ++q)
+      if (pval[q] > best || (pval[q] == best && pidx[q] < bi)) { best = pval[q]; bi = pidx[q]; }
+    ipiv[j] = bi;
+    if (!(best > 0.0) && *info == 0) *info = j + 1;
+    sp = bi;
+  }
+  __syncthreads();
+  const int p = sp;
+  if (p == j) return;
+  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+    const double a = A[(long long)j * lda + c];
+    const double b = A[(long long)p * lda + c];
+    A[(long long)j * lda + c] = b;
+    A[(long long)p * lda + c] = a;
+  }
+}
+
+// scale column j below the diagonal and update the rest of the panel row-wise (warp per row)
+__global__ void lu_panel_update_kernel(double* __restrict__ A, long long lda, int N, int j,
+                                       int pend) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int i = j + 1 + blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  if (i >= N) return;
+  const double piv = A[(long long)j * lda + j];
+  double* row = A + (long long)i * lda;
+  const double l = row[j] / piv;
+  for (int c = j + 1 + lane; c < pend; c += 32) row[c] -= l * A[(long long)j * lda + c];
+  __syncwarp();
+  if (lane == 0) row[j] = l;
+}
+
+// U12 <- inv(L11) A12 with L11 unit lower (pb x pb) : thread per column
+__global__ void lu_trsm_u12_kernel(double* __restrict__ A, long long lda, int k0, int pb, int N) {
+  __shared__ double L11[PB][PB + 1];
+  for (int idx = threadIdx.x; idx < pb * pb; idx += blockDim.x) {
+    const int r = idx / pb, c = idx - r * pb;
+    L11[r][c] = A[(long long)(k0 + r) * lda + k0 + c];
+  }
+  __syncthreads();
+  const int c = k0 + pb + blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  double x[PB];
+#pragma unroll 1
+  for (int r = 0; r < pb; ++r) {
+    double s = A[(long long)(k0 + r) * lda + c];
+    for (int q = 0; q < r; ++q) s -= L11[r][q] * x[q];
+    x[r] = s;
+    A[(long long)(k0 + r) * lda + c] = s;
+  }
+}
+
+__global__ void lu_apply_pivots_kernel(double* __restrict__ B, long long ldb, int nrhs, int N,
+                                       const int* __restrict__ ipiv) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nrhs) return;
+  for (int j = 0; j < N; ++j) {
+    const int p = ipiv[j];
+    if (p != j) {
+      const double a = B[(long long)j * ldb + c];
+      B[(long long)j * ldb + c] = B[(long long)p * ldb + c];
+      B[(long long)p * ldb + c] = a;
+    }
+  }
+}
+
+// Solve with the pb x pb diagonal block (unit lower, or upper) for every rhs column in place.
+__global__ void lu_diag_solve_kernel(const double* __restrict__ LU, long long lda, int k0, int pb,
+                                     double* __restrict__ B, long long ldb, int nrhs, int upper) {
+  __shared__ double T[PB][PB + 1];
+  for (int idx = threadIdx.x; idx < pb * pb; idx += blockDim.x) {
+    const int r = idx / pb, c = idx - r * pb;
+    T[r][c] = LU[(long long)(k0 + r) * lda + k0 + c];
+  }
+  __syncthreads();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nrhs) return;
+  double x[PB];
+  if (!upper) {
+#pragma unroll 1
+    for (int r = 0; r < pb; ++r) {
+      double s = B[(long long)(k0 + r) * ldb + c];
+      for (int q = 0; q < r; ++q) s -= T[r][q] * x[q];
+      x[r] = s;
+      B[(long long)(k0 + r) * ldb + c] = s;
+    }
+  } else {
+#pragma unroll 1
+    for (int r = pb - 1; r >= 0; --r) {
+      double s = B[(long long)(k0 + r) * ldb + c];
+      for (int q = r + 1; q < pb; ++q) s -= T[r][q] * x[q];
+      s /= T[r][r];
+      x[r] = s;
+      B[(long long)(k0 + r) * ldb + c] = s;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace pmr
+
+using namespace pmr;
+
+extern "C" long long pmr_potrf_dinv_doubles(int N) {
+  const long long nblk = (N + NB - 1) / NB;
+  return nblk * NB * NB;
+}
+
+extern "C" int pmr_potrf(double* A, int N, long long lda, int batch, long long stride_a,
+                         double* dinv, int* info, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  PMR_REQUIRE(N >= 0 && batch >= 1 && batch <= 65535, "potrf: bad N/batch");
+  PMR_REQUIRE(A && dinv && info, "potrf: null pointer");
+  PMR_REQUIRE(lda >= N, "potrf: lda < N");
+  const long long dstride = pmr_potrf_dinv_doubles(N);
+  PMR_CHECK_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * batch, st));
+  if (N == 0) return 0;
+  PMR_CHECK_CUDA(cudaMemsetAsync(dinv, 0, sizeof(double) * dstride * batch, st));
+  static thread_local bool configured = false;
+  const size_t smem = sizeof(double) * NB * NBLD;
+  if (!configured) {
+    PMR_CHECK_CUDA(cudaFuncSetAttribute(potf2_trtri_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int nblk = (N + NB - 1) / NB;
+  for (int kb = 0; kb < nblk; ++kb) {
+    const int k0 = kb * NB;
+    const int jb = std::min(NB, N - k0);
+    const int rest = N - k0 - jb;
+    double* Akk = A + (long long)k0 * lda + k0;
+    double* dk = dinv + (long long)kb * NB * NB;
+    potf2_trtri_kernel<<<batch, 1024, smem, st>>>(Akk, lda, stride_a, jb, dk, dstride, info, k0);
+    PMR_CHECK_LAUNCH("potf2_trtri_kernel");
+    if (rest > 0) {
+      double* A21 = A + (long long)(k0 + jb) * lda + k0;
+      pmr_gemm_t g = make_gemm(rest, jb, jb, 1.0, A21, lda, 1, dk, 1, NB, 0.0, A21, lda, 1);
+      g.batch1 = batch; g.a_b1 = stride_a; g.b_b1 = dstride; g.c_b1 = stride_a;
+      PMR_TRY(gemm(g, st));
+      double* A22 = A + (long long)(k0 + jb) * lda + (k0 + jb);
+      pmr_gemm_t t = make_gemm(rest, rest, jb, -1.0, A21, lda, 1, A21, 1, lda, 1.0, A22, lda, 1);
+      t.batch1 = batch; t.a_b1 = stride_a; t.b_b1 = stride_a; t.c_b1 = stride_a;
+      t.flags = PMR_GEMM_LOWER;
+      PMR_TRY(gemm(t, st));
+    }
+  }
+  return 0;
+}
+
+extern "C" int pmr_potrs(const double* L, int N, long long lda, int batch, long long stride_l,
+                         const double* dinv, double* B, int nrhs, long long ldb,
+                         long long stride_b, double* work, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  PMR_REQUIRE(N >= 0 && nrhs >= 0 && batch >= 1 && batch <= 65535, "potrs: bad sizes");
+  if (N == 0 || nrhs == 0) return 0;
+  PMR_REQUIRE(L && dinv && B && work, "potrs: null pointer");
+  PMR_REQUIRE(ldb >= nrhs, "potrs: ldb < nrhs");
+  const long long dstride = pmr_potrf_dinv_doubles(N);
+  const long long wstride = (long long)N * nrhs;
+  const int nblk = (N + NB - 1) / NB;
+  // forward: L Y = B, Y -> work
+  for (int kb = 0; kb < nblk; ++kb) {
+    const int k0 = kb * NB, jb = std::min(NB, N - k0), rest = N - k0 - jb;
+    const double* dk = dinv + (long long)kb * NB * NB;
+    pmr_gemm_t g = make_gemm(jb, nrhs, jb, 1.0, dk, NB, 1, B + (long long)k0 * ldb, ldb, 1, 0.0,
+                             work + (long long)k0 * nrhs, nrhs, 1);
+    g.batch1 = batch; g.a_b1 = dstride; g.b_b1 = stride_b; g.c_b1 = wstride;
+    PMR_TRY(gemm(g, st));
+    if (rest > 0) {
+      pmr_gemm_t u = make_gemm(rest, nrhs, jb, -1.0, L + (long long)(k0 + jb) * lda + k0, lda, 1,
+                               work + (long long)k0 * nrhs, nrhs, 1, 1.0,
+                               B + (long long)(k0 + jb) * ldb, ldb, 1);
+      u.batch1 = batch; u.a_b1 = stride_l; u.b_b1 = wstride; u.c_b1 = stride_b;
+      PMR_TRY(gemm(u, st));
+    }
+  }
+  // backward: L^T X = Y, X -> B
+  for (int kb = nblk - 1; kb >= 0; --kb) {
+    const int k0 = kb * NB, jb = std::min(NB, N - k0);
+    const double* dk = dinv + (long long)kb * NB * NB;
+    pmr_gemm_t g = make_gemm(jb, nrhs, jb, 1.0, dk, 1, NB, work + (long long)k0 * nrhs, nrhs, 1,
+                             0.0, B + (long long)k0 * ldb, ldb, 1);
+    g.batch1 = batch; g.a_b1 = dstride; g.b_b1 = wstride; g.c_b1 = stride_b;
+    PMR_TRY(gemm(g, st));
+    if (k0 > 0) {
+      pmr_gemm_t u = make_gemm(k0, nrhs, jb, -1.0, L + (long long)k0 * lda, 1, lda,
+                               B + (long long)k0 * ldb, ldb, 1, 1.0, work, nrhs, 1);
+      u.batch1 = batch; u.a_b1 = stride_l; u.b_b1 = stride_b; u.c_b1 = wstride;
+      PMR_TRY(gemm(u, st));
+    }
+  }
+  return 0;
+}
+
+extern "C" int pmr_potri_lower(const double* L, int N, long long lda, const double* dinv,
+                               double* out, long long ldo, double* work, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  PMR_REQUIRE(N >= 0, "potri: bad N");
+  if (N == 0) return 0;
+  PMR_REQUIRE(L && dinv && out && work, "potri: null pointer");
+  PMR_REQUIRE(ldo >= N, "potri: ldo < N");
+  const int nblk = (N + NB - 1) / NB;
+  const long long ldw = N;
+  // Z = inv(L) (lower) -> work ; right-looking forward substitution on the identity, the running
+  // right-hand side lives in `out` (only its nonzero block columns are touched).
+  PMR_CHECK_CUDA(cudaMemset2DAsync(out, sizeof(double) * ldo, 0, sizeof(double) * N, N, st));
+  for (int kb = 0; kb < nblk; ++kb) {
+    const int k0 = kb * NB, jb = std::min(NB, N - k0), rest = N - k0 - jb;
+    const double* dk = dinv + (long long)kb * NB * NB;
+    double* Zk = work + (long long)k0 * ldw;
+    if (k0 > 0) {
+      pmr_gemm_t g = make_gemm(jb, k0, jb, 1.0, dk, NB, 1, out + (long long)k0 * ldo, ldo, 1, 0.0,
+                               Zk, ldw, 1);
+      PMR_TRY(gemm(g, st));
+    }
+    {
+      dim3 grid((jb + 127) / 128, jb);
+      copy_block_kernel<<<grid, 128, 0, st>>>(dk, NB, Zk + k0, ldw, jb, jb);
+      PMR_CHECK_LAUNCH("copy_block_kernel");
+    }
+    if (rest > 0) {
+      pmr_gemm_t u = make_gemm(rest, k0 + jb, jb, -1.0, L + (long long)(k0 + jb) * lda + k0, lda, 1,
+                               Zk, ldw, 1, 1.0, out + (long long)(k0 + jb) * ldo, ldo, 1);
+      PMR_TRY(gemm(u, st));
+    }
+  }
+  // out(lower) = Z^T Z ; Z(r, a) = 0 for r < a lets the k loop start at the row-tile origin
+  pmr_gemm_t s = make_gemm(N, N, N, 1.0, work, 1, ldw, work, ldw, 1, 0.0, out, ldo, 1);
+  s.flags = PMR_GEMM_LOWER | PMR_GEMM_KSTART_M;
+  PMR_TRY(gemm(s, st));
+  return 0;
+}
+
+extern "C" int pmr_shifted_combine(const double* M, const double* W, int N, long long ldm,
+                                   long long ldw, const double* shift_a_host,
+                                   const double* shift_b_host, int nf, double* S, long long lds,
+                                   long long stride_s, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  PMR_REQUIRE(N >= 0 && nf >= 0, "shifted_combine: bad sizes");
+  if (N == 0 || nf == 0) return 0;
+  PMR_REQUIRE(M && S && shift_a_host && shift_b_host, "shifted_combine: null pointer");
+  double* dshift = nullptr;
+  PMR_CHECK_CUDA(cudaMallocAsync(&dshift, sizeof(double) * 2 * nf, st));
+  std::vector<double> h(2 * (size_t)nf);
+  for (int f = 0; f < nf; ++f) { h[f] = shift_a_host[f]; h[nf + f] = shift_b_host[f]; }
+  // pageable host memory: the copy is staged by the runtime before the call returns
+  PMR_CHECK_CUDA(cudaMemcpyAsync(dshift, h.data(), sizeof(double) * 2 * nf,
+                                 cudaMemcpyHostToDevice, st));
+  dim3 grid((N + 255) / 256, N);
+  shifted_combine_kernel<<<grid, 256, 0, st>>>(M, W, N, ldm, ldw, nf, S, lds, stride_s, dshift);
+  PMR_CHECK_LAUNCH("shifted_combine_kernel");
+  PMR_CHECK_CUDA(cudaFreeAsync(dshift, st));
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------- LU
+extern "C" long long pmr_getrf_work_doubles(int N) {
+  (void)N;
+  return 2 * 1024;  // pivot-search partials (values + indices packed as doubles)
+}
+
+extern "C" int pmr_getrf(double* A, int N, long long lda, int* ipiv, int* info, double* work,
+                         void* stream) {
+  cudaStream_t st = as_stream(stream);
+  PMR_REQUIRE(N >= 0, "getrf: bad N");
+  PMR_REQUIRE(A && ipiv && info && work, "getrf: null pointer");
+  PMR_CHECK_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
+  if (N == 0) return 0;
+  double* pval = work;
+  int* pidx = reinterpret_cast<int*>(work + 1024);
+  for (int k0 = 0; k0 < N; k0 += PB) {
+    const int pb = std::min(PB, N - k0);
+    const int pend = k0 + pb;
+    for (int j = k0; j < pend; ++j) {
+      const int rows = N - j;
+      const int nparts = std::max(1, std::min(512, (rows + 1023) / 1024));
+      lu_pivot_partial_kernel<<<nparts, 256, 0, st>>>(A, lda, N, j, pval, pidx);
+      PMR_CHECK_LAUNCH("lu_pivot_partial_kernel");
+      lu_pivot_swap_kernel<<<1, 256, 0, st>>>(A, lda, N, j, pval, pidx, nparts, ipiv, info);
+      PMR_CHECK_LAUNCH("lu_pivot_swap_kernel");
+      if (rows > 1) {
+        const int wpb = 8;
+        lu_panel_update_kernel<<<(rows - 1 + wpb - 1) / wpb, wpb * 32, 0, st>>>(A, lda, N, j, pend);
+        PMR_CHECK_LAUNCH("lu_panel_update_kernel");
+      }
+    }
+    const int rest = N - pend;
+    if (rest > 0) {
+      lu_trsm_u12_kernel<<<(rest + 127) / 128, 128, 0, st>>>(A, lda, k0, pb, N);
+      PMR_CHECK_LAUNCH("lu_trsm_u12_kernel");
+      pmr_gemm_t g = make_gemm(rest, rest, pb, -1.0, A + (long long)pend * lda + k0, lda, 1,
+                               A + (long long)k0 * lda + pend, lda, 1, 1.0,
+                               A + (long long)pend * lda + pend, lda, 1);
+      PMR_TRY(gemm(g, st));
+    }
+  }
+  return 0;
+}
+
+extern "C" int pmr_getrs(const double* LU, int N, long long lda, const int* ipiv, double* B,
+                         int nrhs, long long ldb, double* work, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  (void)work;
+  PMR_REQUIRE(N >= 0 && nrhs >= 0, "getrs: bad sizes");
+  if (N == 0 || nrhs == 0) return 0;
+  PMR_REQUIRE(LU && ipiv && B, "getrs: null pointer");
+  lu_apply_pivots_kernel<<<(nrhs + 63) / 64, 64, 0, st>>>(B, ldb, nrhs, N, ipiv);
+  PMR_CHECK_LAUNCH("lu_apply_pivots_kernel");
+  // forward (unit lower), right-looking
+  for (int k0 = 0; k0 < N; k0 += PB) {
+    const int pb = std::min(PB, N - k0), rest = N - k0 - pb;
+    lu_diag_solve_kernel<<<(nrhs + 63) / 64, 64, 0, st>>>(LU, lda, k0, pb, B, ldb, nrhs, 0);
+    PMR_CHECK_LAUNCH("lu_diag_solve_kernel");
+    if (rest > 0) {
+      pmr_gemm_t g = make_gemm(rest, nrhs, pb, -1.0, LU + (long long)(k0 + pb) * lda + k0, lda, 1,
+                               B + (long long)k0 * ldb, ldb, 1, 1.0,
+                               B + (long long)(k0 + pb) * ldb, ldb, 1);
+      PMR_TRY(gemm(g, st));
+    }
+  }
+  // backward (upper)
+  const int nblk = (N + PB - 1) / PB;
+  for (int kb = nblk - 1; kb >= 0; --kb) {
+    const int k0 = kb * PB, pb = std::min(PB, N - k0);
+    lu_diag_solve_kernel<<<(nrhs + 63) / 64, 64, 0, st>>>(LU, lda, k0, pb, B, ldb, nrhs, 1);
+    PMR_CHECK_LAUNCH("lu_diag_solve_kernel");
+    if (k0 > 0) {
+      pmr_gemm_t g = make_gemm(k0, nrhs, pb, -1.0, LU + k0, lda, 1, B + (long long)k0 * ldb, ldb,
+                               1, 1.0, B, ldb, 1);
+      PMR_TRY(gemm(g, st));
+    }
+  }
+  return 0;
+}

@@ -1,0 +1,318 @@
+// FP64 tensor-core (DMMA, mma.sync.m8n8k4.f64) GEMM for sm_100a.
+//
+//   C(m,n) = alpha * sum_k A(m,k) B(k,n) + beta * C(m,n)      (two-level strided batch)
+//
+// Design (DESIGN.md section "K1 dgemm"):
+//   * CTA tile BM x BN (128x128 / 128x64 / 128x32), BK = 16, 4-stage cp.async (LDGSTS) ring with
+//     hardware zero-fill for ragged M/N/K edges, so every shape and 8-byte-aligned stride is legal;
+//   * operands stay in their global layout in shared memory (k-contiguous [x][BK+4] or
+//     mn-contiguous [BK][BX+4]); the +4-double row padding makes the per-lane 64-bit fragment
+//     loads of the m8n8k4 shapes bank-conflict free for both layouts;
+//   * each warp owns a 64x32 (or 32x32) accumulator block = 8x4 DMMA.8x8x4 tiles in registers; on
+//     sm_100a all f64 mma shapes lower to DMMA.8x8x4 (checked with cuobjdump), 16 cycles per SMSP,
+//     so the kernel is DMMA-issue bound by construction: 12 LDS.64 per 32 DMMA;
+//   * C is written with arbitrary (row, column) element strides: transposed / packed-index
+//     epilogues (ov packing of operators.py:94, quarter-transform output orders) are free.
+#include <algorithm>
+#include <cstdint>
+
+#include "pmr_common.cuh"
+
+namespace pmr {
+namespace {
+
+constexpr int BK = 16;
+constexpr int STAGES = 4;
+constexpr int PAD = 4;
+
+struct GemmArgs {
+  int M, N, K;
+  double alpha, beta;
+  const double* A;
+  long long a_ld;  // stride between smem rows of A (m rows if k-contig, k rows otherwise)
+  const double* B;
+  long long b_ld;
+  double* C;
+  long long c_sm, c_sn;
+  long long a_b1, a_b2, b_b1, b_b2, c_b1, c_b2;
+  int tiles_m;
+  int flags;
+  int a_vec2, b_vec2, c_vec2;
+};
+
+template <int BM, int BN, int WM, int WN, bool AKC, bool BKC>
+struct Cfg {
+  static constexpr int WARPS_M = BM / WM;
+  static constexpr int WARPS_N = BN / WN;
+  static constexpr int NT = WARPS_M * WARPS_N * 32;
+  static constexpr int MI = WM / 8;
+  static constexpr int NI = WN / 8;
+  static constexpr int LDA = AKC ? (BK + PAD) : (BM + PAD);
+  static constexpr int A_ELEMS = AKC ? BM * LDA : BK * LDA;
+  static constexpr int LDB = BKC ? (BK + PAD) : (BN + PAD);
+  static constexpr int B_ELEMS = BKC ? BN * LDB : BK * LDB;
+  static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
+  static constexpr size_t SMEM = size_t(STAGES) * STAGE_ELEMS * sizeof(double);
+};
+
+__device__ __forceinline__ void cp_async16(double* smem, const double* gmem, int src_bytes) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(double* smem, const double* gmem, int src_bytes) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c[0]), "+d"(c[1])
+      : "d"(a), "d"(b));
+}
+
+// Copy one operand tile global -> shared.  XT = tile extent along the m/n ("x") dimension.
+// KC: element (x,k) at g[x*ld + k], smem [x][LD];  !KC: element at g[k*ld + x], smem [k][LD].
+// Out-of-range elements are zero-filled by the copy engine (src-size < cp-size).
+template <int XT, bool KC, int LD, int NT, int VEC>
+__device__ __forceinline__ void load_tile_v(double* s, const double* __restrict__ g, long long ld,
+                                            int x0, int k0, int X, int K, int tid) {
+  if (KC) {
+    constexpr int CPR = BK / VEC;
+    constexpr int TOTAL = XT * CPR;
+#pragma unroll
+    for (int c = tid; c < TOTAL; c += NT) {
+      const int x = c / CPR;
+      const int kc = (c % CPR) * VEC;
+      const int gx = x0 + x, gk = k0 + kc;
+      int valid = (gx < X) ? min(max(K - gk, 0), VEC) : 0;
+      const double* src = valid ? (g + (long long)gx * ld + gk) : g;
+      if (VEC == 2) cp_async16(s + x * LD + kc, src, valid * 8);
+      else cp_async8(s + x * LD + kc, src, valid * 8);
+    }
+  } else {
+    constexpr int CPR = XT / VEC;
+    constexpr int TOTAL = BK * CPR;
+#pragma unroll
+    for (int c = tid; c < TOTAL; c += NT) {
+      const int k = c / CPR;
+      const int xc = (c % CPR) * VEC;
+      const int gk = k0 + k, gx = x0 + xc;
+      int valid = (gk < K) ? min(max(X - gx, 0), VEC) : 0;
+      const double* src = valid ? (g + (long long)gk * ld + gx) : g;
+      if (VEC == 2) cp_async16(s + k * LD + xc, src, valid * 8);
+      else cp_async8(s + k * LD + xc, src, valid * 8);
+    }
+  }
+}
+
+template <int BM, int BN, int WM, int WN, bool AKC, bool BKC>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) dgemm_dmma_kernel(const GemmArgs p) {
+  using C_ = Cfg<BM, BN, WM, WN, AKC, BKC>;
+  constexpr int NT = C_::NT, MI = C_::MI, NI = C_::NI, LDA = C_::LDA, LDB = C_::LDB;
+  extern __shared__ __align__(16) double smem[];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int tm = blockIdx.x % p.tiles_m, tn = blockIdx.x / p.tiles_m;
+  const int bm0 = tm * BM, bn0 = tn * BN;
+  const bool lower = (p.flags & PMR_GEMM_LOWER) != 0;
+  if (lower && bn0 > bm0 + BM - 1) return;
+
+  const long long b1 = blockIdx.z, b2 = blockIdx.y;
+  const double* __restrict__ Ab = p.A + b1 * p.a_b1 + b2 * p.a_b2;
+  const double* __restrict__ Bb = p.B + b1 * p.b_b1 + b2 * p.b_b2;
+  double* __restrict__ Cb = p.C + b1 * p.c_b1 + b2 * p.c_b2;
+
+  int kt_begin = 0;
+  int kt_end = (p.K + BK - 1) / BK;
+  if (p.flags & PMR_GEMM_KSTART_M) kt_begin = bm0 / BK;
+  if (p.flags & PMR_GEMM_KEND_M) kt_end = min(kt_end, (min(p.K, bm0 + BM) + BK - 1) / BK);
+  const int KT = max(kt_end - kt_begin, 0);
+
+  const int wm0 = (warp % C_::WARPS_M) * WM;
+  const int wn0 = (warp / C_::WARPS_M) * WN;
+
+  double acc[MI][NI][2];
+#pragma unroll
+  for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+  auto load_stage = [&](int slot, int kt) {
+    double* As = smem + slot * C_::STAGE_ELEMS;
+    double* Bs = As + C_::A_ELEMS;
+    const int k0 = (kt_begin + kt) * BK;
+    if (p.a_vec2) load_tile_v<BM, AKC, LDA, NT, 2>(As, Ab, p.a_ld, bm0, k0, p.M, p.K, tid);
+    else load_tile_v<BM, AKC, LDA, NT, 1>(As, Ab, p.a_ld, bm0, k0, p.M, p.K, tid);
+    if (p.b_vec2) load_tile_v<BN, BKC, LDB, NT, 2>(Bs, Bb, p.b_ld, bn0, k0, p.N, p.K, tid);
+    else load_tile_v<BN, BKC, LDB, NT, 1>(Bs, Bb, p.b_ld, bn0, k0, p.N, p.K, tid);
+  };
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < KT) load_stage(s, s);
+    cp_async_commit();
+  }
+
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int nk = kt + STAGES - 1;
+      if (nk < KT) load_stage(nk % STAGES, nk);
+      cp_async_commit();
+    }
+    const double* As = smem + (kt % STAGES) * C_::STAGE_ELEMS;
+    const double* Bs = As + C_::A_ELEMS;
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; ++kk) {
+      double a[MI], b[NI];
+#pragma unroll
+      for (int mi = 0; mi < MI; ++mi)
+        a[mi] = AKC ? As[(wm0 + mi * 8 + g) * LDA + kk * 4 + t]
+                    : As[(kk * 4 + t) * LDA + wm0 + mi * 8 + g];
+#pragma unroll
+      for (int ni = 0; ni < NI; ++ni)
+        b[ni] = BKC ? Bs[(wn0 + ni * 8 + g) * LDB + kk * 4 + t]
+                    : Bs[(kk * 4 + t) * LDB + wn0 + ni * 8 + g];
+#pragma unroll
+      for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: thread owns C(m = ..+g, n = ..+2t, 2t+1) of every 8x8 tile
+  const double alpha = p.alpha, beta = p.beta;
+  const bool use_beta = (beta != 0.0);
+#pragma unroll
+  for (int mi = 0; mi < MI; ++mi) {
+    const int m = bm0 + wm0 + mi * 8 + g;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int ni = 0; ni < NI; ++ni) {
+      const int n = bn0 + wn0 + ni * 8 + 2 * t;
+      if (n >= p.N) continue;
+      const bool ok1 = (n + 1 < p.N) && (!lower || n + 1 <= m);
+      const bool ok0 = (!lower || n <= m);
+      double* c = Cb + (long long)m * p.c_sm + (long long)n * p.c_sn;
+      if (p.c_vec2 && ok0 && ok1) {
+        double2 v;
+        v.x = alpha * acc[mi][ni][0];
+        v.y = alpha * acc[mi][ni][1];
+        if (use_beta) {
+          const double2 o = *reinterpret_cast<const double2*>(c);
+          v.x += beta * o.x;
+          v.y += beta * o.y;
+        }
+        *reinterpret_cast<double2*>(c) = v;
+      } else {
+        if (ok0) {
+          double v = alpha * acc[mi][ni][0];
+          if (use_beta) v += beta * c[0];
+          c[0] = v;
+        }
+        if (ok1) {
+          double v = alpha * acc[mi][ni][1];
+          if (use_beta) v += beta * c[p.c_sn];
+          c[p.c_sn] = v;
+        }
+      }
+    }
+  }
+}
+
+template <int BM, int BN, int WM, int WN, bool AKC, bool BKC>
+int launch_cfg(const GemmArgs& a, int tiles_n, int batch1, int batch2, cudaStream_t st) {
+  using C_ = Cfg<BM, BN, WM, WN, AKC, BKC>;
+  auto kern = dgemm_dmma_kernel<BM, BN, WM, WN, AKC, BKC>;
+  static thread_local bool configured = false;
+  if (!configured) {
+    PMR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)C_::SMEM));
+    configured = true;
+  }
+  dim3 grid((unsigned)(a.tiles_m * (long long)tiles_n), (unsigned)batch2, (unsigned)batch1);
+  kern<<<grid, C_::NT, C_::SMEM, st>>>(a);
+  PMR_CHECK_LAUNCH("dgemm_dmma_kernel");
+  return 0;
+}
+
+template <int BM, int BN, int WM, int WN>
+int launch_layout(const GemmArgs& a, bool akc, bool bkc, int tiles_n, int b1, int b2,
+                  cudaStream_t st) {
+  if (akc && bkc) return launch_cfg<BM, BN, WM, WN, true, true>(a, tiles_n, b1, b2, st);
+  if (akc && !bkc) return launch_cfg<BM, BN, WM, WN, true, false>(a, tiles_n, b1, b2, st);
+  if (!akc && bkc) return launch_cfg<BM, BN, WM, WN, false, true>(a, tiles_n, b1, b2, st);
+  return launch_cfg<BM, BN, WM, WN, false, false>(a, tiles_n, b1, b2, st);
+}
+
+inline bool even(long long x) { return (x & 1LL) == 0; }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+int gemm(const pmr_gemm_t& g0, cudaStream_t st) {
+  pmr_gemm_t g = g0;
+  PMR_REQUIRE(g.M >= 0 && g.N >= 0 && g.K >= 0, "dgemm: negative dimension");
+  PMR_REQUIRE(g.batch1 >= 1 && g.batch2 >= 1, "dgemm: batch counts must be >= 1");
+  PMR_REQUIRE(g.batch1 <= 65535 && g.batch2 <= 65535, "dgemm: batch count above 65535");
+  if (g.M == 0 || g.N == 0) return 0;
+  PMR_REQUIRE(g.C != nullptr, "dgemm: null C");
+  PMR_REQUIRE(g.K == 0 || (g.A != nullptr && g.B != nullptr), "dgemm: null operand");
+  PMR_REQUIRE(g.a_sm == 1 || g.a_sk == 1, "dgemm: A needs a unit stride (a_sm=%lld a_sk=%lld)",
+              g.a_sm, g.a_sk);
+  PMR_REQUIRE(g.b_sk == 1 || g.b_sn == 1, "dgemm: B needs a unit stride (b_sk=%lld b_sn=%lld)",
+              g.b_sk, g.b_sn);
+
+  // Put the long dimension on M (the 128-row tile): C^T = B^T A^T with C's strides swapped.
+  if (g.N > g.M && g.flags == 0) {
+    std::swap(g.M, g.N);
+    const double* A = g.A;
+    const long long a_sm = g.a_sm, a_sk = g.a_sk, a_b1 = g.a_b1, a_b2 = g.a_b2;
+    g.A = g.B; g.a_sm = g.b_sn; g.a_sk = g.b_sk; g.a_b1 = g.b_b1; g.a_b2 = g.b_b2;
+    g.B = A; g.b_sk = a_sk; g.b_sn = a_sm; g.b_b1 = a_b1; g.b_b2 = a_b2;
+    std::swap(g.c_sm, g.c_sn);
+  }
+
+  // k-contiguous wins ties (a dimension of extent 1 has a free stride)
+  const bool akc = (g.a_sk == 1);
+  const bool bkc = (g.b_sk == 1);
+
+  GemmArgs a{};
+  a.M = g.M; a.N = g.N; a.K = g.K;
+  a.alpha = g.alpha; a.beta = g.beta;
+  a.A = g.A; a.B = g.B; a.C = g.C;
+  a.a_ld = akc ? g.a_sm : g.a_sk;
+  a.b_ld = bkc ? g.b_sn : g.b_sk;
+  a.c_sm = g.c_sm; a.c_sn = g.c_sn;
+  a.a_b1 = g.a_b1; a.a_b2 = g.a_b2; a.b_b1 = g.b_b1; a.b_b2 = g.b_b2;
+  a.c_b1 = g.c_b1; a.c_b2 = g.c_b2;
+  a.flags = g.flags;
+  a.a_vec2 = aligned16(g.A) && even(a.a_ld) && even(g.a_b1) && even(g.a_b2);
+  a.b_vec2 = aligned16(g.B) && even(a.b_ld) && even(g.b_b1) && even(g.b_b2);
+  a.c_vec2 = (g.c_sn == 1) && aligned16(g.C) && even(g.c_sm) && even(g.c_b1) && even(g.c_b2);
+
+  constexpr int BM = 128;
+  a.tiles_m = (g.M + BM - 1) / BM;
+  int bn = (g.N > 64) ? 128 : (g.N > 32 ? 64 : 32);
+  const long long tiles_n = (g.N + bn - 1) / bn;
+  PMR_REQUIRE((long long)a.tiles_m * tiles_n < (1LL << 31), "dgemm: too many tiles");
+  if (bn == 128) return launch_layout<128, 128, 64, 32>(a, akc, bkc, (int)tiles_n, g.batch1, g.batch2, st);
+  if (bn == 64) return launch_layout<128, 64, 32, 32>(a, akc, bkc, (int)tiles_n, g.batch1, g.batch2, st);
+  return launch_layout<128, 32, 32, 32>(a, akc, bkc, (int)tiles_n, g.batch1, g.batch2, st);
+}
+
+}  // namespace pmr
+
+extern "C" int pmr_dgemm(const pmr_gemm_t* g, void* stream) {
+  if (!g) return pmr::set_error(PMR_ERR_ARG, "pmr_dgemm: null descriptor");
+  return pmr::gemm(*g, pmr::as_stream(stream));
+}

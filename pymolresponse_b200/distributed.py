@@ -1,0 +1,124 @@
+"""One process per GPU: how the hot path is sharded over the ranks of one box.
+
+* AO ERI tensor: sharded over the second index of the first AO pair (``nu``); every rank holds
+  ``I[:, nu_lo:nu_hi, :, :]`` with mu local, so the 2 n^4 o first quarter needs no reduction.  The
+  finished (ia|jb) / (ij|ab) blocks are partial sums over the local nu and are completed with one
+  ``all_reduce`` each (GBs, against tens of GBs for the half-transformed tensor).
+* Orbital-Hessian assembly: row blocks by occupied index i (both index swaps stay rank-local).
+* Solves: independent frequencies are dealt round-robin to ranks; the small result tensors and
+  response vectors are all-gathered.
+
+``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) is the only transport; nothing here
+does arithmetic.
+"""
+
+from __future__ import annotations
+
+import os
+
+
+def dist():
+    import torch.distributed as d
+
+    return d
+
+
+def is_initialized() -> bool:
+    d = dist()
+    return d.is_available() and d.is_initialized()
+
+
+def rank_world() -> tuple[int, int]:
+    if is_initialized():
+        return dist().get_rank(), dist().get_world_size()
+    return 0, 1
+
+
+def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
+    """Initialise from torchrun's environment; returns (rank, world, local_rank)."""
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist().init_process_group(backend=backend, rank=rank, world_size=world)
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    return rank, world, local
+
+
+def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous, balanced [lo, hi) slice of range(n) for this rank (first ranks get the extras)."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def round_robin(n_items: int, rank: int, world: int) -> list[int]:
+    """Indices of the items (frequencies) this rank owns."""
+    return list(range(rank, n_items, world))
+
+
+def owner_of(item: int, world: int) -> int:
+    return item % world
+
+
+def allreduce_blocks(tensors) -> None:
+    """In-place sum over ranks of the partial MO-integral blocks."""
+    if not is_initialized():
+        return
+    d = dist()
+    for t in tensors:
+        d.all_reduce(t, op=d.ReduceOp.SUM)
+
+
+def gather_round_robin(local_items: list, n_items: int):
+    """Inverse of :func:`round_robin`: every rank contributes the tensors of the items it owns
+    (same shape for all items) and receives the full list in item order."""
+    rank, world = rank_world()
+    if world == 1:
+        return list(local_items)
+    import torch
+
+    d = dist()
+    per_rank_max = (n_items + world - 1) // world
+    proto = None
+    for t in local_items:
+        proto = t
+        break
+    if proto is not None:
+        dev = proto.device
+    elif d.get_backend() == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device())
+    else:
+        dev = torch.device("cpu")
+    shape_t = torch.zeros(8, dtype=torch.int64, device=dev)
+    if proto is not None:
+        shape_t[0] = proto.dim()
+        for k, s in enumerate(proto.shape):
+            shape_t[1 + k] = s
+    d.all_reduce(shape_t, op=d.ReduceOp.MAX)
+    ndim = int(shape_t[0].item())
+    shape = [int(shape_t[1 + k].item()) for k in range(ndim)]
+    device = shape_t.device
+    buf = torch.zeros([per_rank_max] + shape, dtype=torch.float64, device=device)
+    for k, t in enumerate(local_items):
+        buf[k].copy_(t)
+    gathered = [torch.zeros_like(buf) for _ in range(world)]
+    d.all_gather(gathered, buf)
+    out = []
+    for item in range(n_items):
+        out.append(gathered[owner_of(item, world)][item // world].clone())
+    return out
+
+
+def barrier() -> None:
+    if is_initialized():
+        dist().barrier()

@@ -1,0 +1,638 @@
+"""Linear-response solvers on the GPU.
+
+Drop-in for the linear-equation part of the reference's ``pymolresponse/solvers.py``
+(``Solver`` -> ``LineqSolver`` -> ``ExactLineqSolver`` -> ``ExactInv`` / ``ExactInvCholesky`` and
+``IterativeLinEqSolver``): same constructors, same attributes (``tei_mo``, ``tei_mo_type``,
+``explicit_hessian``, ``explicit_hessian_inv``, ``left_alph``/``left_beta``, ``operators``,
+``frequencies``), same side effects (``operator.rspvecs_alph/beta.append(ndarray(ncomp, 2nov, 1))``
+once per frequency) and the same exceptions.  What differs is how the numbers are produced:
+
+* the A/B blocks are assembled ONCE per run by ``pmr_assemble`` directly as M = A - B and
+  K = A + B (the reference re-forms A and B at every frequency, solvers.py:477-478);
+* no (2 nov)^2 matrix is built, inverted or multiplied: see ``_engine.HalfSizeSystem``;
+  ``explicit_hessian`` / ``explicit_hessian_inv`` are materialised lazily, on access, for the
+  last frequency (parity checks and downstream code that reads them);
+* UHF uses the joint (nov_a + nov_b) system instead of four explicit inverses and two Schur
+  complements (solvers.py:506-520).
+"""
+
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from collections.abc import Callable, Sequence
+from typing import Any
+
+import numpy as np
+
+from pymolresponse_b200 import _blocks as bl
+from pymolresponse_b200 import _engine as eng
+from pymolresponse_b200 import _native as nv
+from pymolresponse_b200.core import AO2MOTransformationType, Hamiltonian, Program, Spin
+from pymolresponse_b200.indices import form_indices_from_occupations
+from pymolresponse_b200.integrals import JK
+from pymolresponse_b200.operators import Operator
+
+
+class Solver(ABC):
+    """State shared by all solvers (reference solvers.py:41-154)."""
+
+    def __init__(self, mocoeffs, moenergies, occupations) -> None:
+        # MO coefficients: first axis is alpha/beta
+        assert len(mocoeffs.shape) == 3
+        assert (mocoeffs.shape[0] == 1) or (mocoeffs.shape[0] == 2)
+        self.is_uhf = mocoeffs.shape[0] == 2
+        # MO energies: first axis alpha/beta, then a diagonal square matrix
+        assert len(moenergies.shape) == 3
+        assert (moenergies.shape[0] == 1) or (moenergies.shape[0] == 2)
+        if self.is_uhf:
+            assert moenergies.shape[0] == 2
+        else:
+            assert moenergies.shape[0] == 1
+        assert moenergies.shape[1] == moenergies.shape[2]
+        assert len(occupations) == 4
+
+        self.mocoeffs = mocoeffs
+        self.moenergies = moenergies
+        self.occupations = occupations
+        self.indices = form_indices_from_occupations(occupations)
+
+        self.operators = []
+        self.frequencies = []
+
+        self._tei_mo = None
+        self._tei_mo_dev = None
+        self.tei_mo_type = AO2MOTransformationType.partial
+        self._explicit_hessian = None
+        self._explicit_hessian_inv = None
+        self._lazy_hessian = None
+        # keep response vectors on the device as torch tensors instead of NumPy arrays
+        self.device_results = False
+
+    # ---------------------------------------------------------------- MO integrals
+    explicit_hessian = None
+    explicit_hessian_inv = None
+
+    @property
+    def tei_mo(self):
+        """Tuple of MO-basis ERI blocks (length 1/2/4/6, reference solvers.py:170)."""
+        return self._tei_mo
+
+    @tei_mo.setter
+    def tei_mo(self, value):
+        self._tei_mo = value
+        self._tei_mo_dev = None  # device mirror is rebuilt on demand
+
+    def form_tei_mo(self, program: Program, program_obj: Any,
+                    tei_mo_type: AO2MOTransformationType) -> None:
+        """AO -> MO transformation on the GPU (reference solvers.py:86-127).
+
+        ``program_obj`` may be the AO ERI tensor itself (NumPy / CUDA, ``Program.Arrays``), an
+        object with an ``ao_eri`` attribute, a pyscf ``Mole`` (``Program.PySCF``) or a psi4
+        molecule (``Program.Psi4``); the quantum-chemistry packages are imported lazily and only
+        to *generate* the AO integrals.
+        """
+        from pymolresponse_b200.ao2mo import AO2MO
+
+        nden = self.mocoeffs.shape[0]
+        assert nden in (1, 2)
+        I = None  # noqa: E741
+        if isinstance(program_obj, np.ndarray) or nv.is_device_array(program_obj):
+            I = program_obj  # noqa: E741
+        elif hasattr(program_obj, "ao_eri"):
+            I = program_obj.ao_eri  # noqa: E741
+        elif program == Program.PySCF:
+            I = program_obj.intor("int2e", aosym="s1")  # noqa: E741
+        elif program == Program.Psi4:
+            import psi4
+
+            I = np.asarray(  # noqa: E741
+                psi4.core.MintsHelper(
+                    psi4.core.Wavefunction.build(
+                        program_obj, psi4.core.get_global_option("BASIS")
+                    ).basisset()
+                ).ao_eri()
+            )
+        else:
+            raise RuntimeError
+        ao2mo = AO2MO(self.mocoeffs, self.occupations, I=I, device_results=True)
+        if tei_mo_type == AO2MOTransformationType.partial and nden == 2:
+            ao2mo.perform_uhf_partial()
+        elif tei_mo_type == AO2MOTransformationType.partial and nden == 1:
+            ao2mo.perform_rhf_partial()
+        elif tei_mo_type == AO2MOTransformationType.full and nden == 2:
+            ao2mo.perform_uhf_full()
+        elif tei_mo_type == AO2MOTransformationType.full and nden == 1:
+            ao2mo.perform_rhf_full()
+        else:
+            msg = f"Unknown combination of tei_mo_type {tei_mo_type} and nden {nden}"
+            raise ValueError(msg)
+        dev = tuple(ao2mo.tei_mo)
+        self.tei_mo = dev if self.device_results else tuple(nv.to_host(t) for t in dev)
+        self._tei_mo_dev = list(dev)
+        self.tei_mo_type = tei_mo_type
+
+    def set_frequencies(self, frequencies: Sequence[float] | None = None) -> None:
+        if frequencies is None:
+            self.frequencies = [0.0]
+        else:
+            self.frequencies = frequencies
+        if hasattr(self, "operators"):
+            for operator in self.operators:
+                operator.frequencies = self.frequencies
+
+    def add_operator(self, operator: Operator) -> None:
+        # first dimension: Cartesian components; then (nao, nao)
+        assert hasattr(operator, "ao_integrals")
+        shape = operator.ao_integrals.shape
+        assert len(shape) == 3
+        assert shape[0] >= 1
+        assert shape[1] == shape[2]
+        operator.form_rhs(self.mocoeffs, self.occupations, self.indices)
+        self.operators.append(operator)
+
+    @abstractmethod
+    def run(self, hamiltonian: Hamiltonian, spin: Spin, program: Program | None,
+            program_obj: Any) -> None:
+        """Run the solver."""
+
+    # ---------------------------------------------------------------- helpers
+    def _append_rspvecs(self, operator, tag, xy):
+        """xy: (ncomp, 2nov) CUDA tensor for one frequency."""
+        getattr(operator, f"_rspvecs_{tag}_dev").append(xy)
+        if self.device_results:
+            getattr(operator, f"rspvecs_{tag}").append(xy[:, :, None])
+        else:
+            getattr(operator, f"rspvecs_{tag}").append(nv.to_host(xy)[:, :, None])
+
+
+class LineqSolver(Solver, ABC):
+    """Base class for all solvers of the type AX = B."""
+
+
+def _kind(spin: Spin, uhf: bool) -> str:
+    if spin == Spin.triplet:
+        return "triplet"
+    return "ss" if uhf else "singlet"
+
+
+class ExactLineqSolver(LineqSolver, ABC):
+    """Solvers that (conceptually) form the orbital Hessian explicitly
+    (reference solvers.py:160-480)."""
+
+    #: ExactInv falls back to pivoted LU on G(w) when a Cholesky pivot fails; the Cholesky
+    #: solver raises instead (the reference's scipy.linalg.cholesky would).
+    _allow_lu_fallback = True
+
+    # -------------------------------------------------------------- assembly
+    def _tei_dev(self):
+        assert self.tei_mo is not None
+        assert len(self.tei_mo) in (1, 2, 4, 6)
+        assert isinstance(self.tei_mo_type, AO2MOTransformationType)
+        if self._tei_mo_dev is None:
+            self._tei_mo_dev = [nv.to_dev(t) for t in self.tei_mo]
+        return self._tei_mo_dev
+
+    def _assemble_rhf(self, hamiltonian, spin, want_ab):
+        """-> (M, K, A, B); A/B only when want_ab (LU fallback, explicit_hessian)."""
+        nocc, nvirt, _, _ = self.occupations
+        nov = nocc * nvirt
+        tei = self._tei_dev()
+        kind = _kind(spin, False)
+        eps = bl.split_energies(self.moenergies[0], nocc)
+        if self.tei_mo_type == AO2MOTransformationType.full:
+            assert len(tei) == 1
+            terms = bl.full_terms(kind, tei[0], nocc, nocc)
+        else:
+            assert len(tei) == 2
+            terms = bl.partial_terms(kind, tei[0], tei[1])
+        tda = hamiltonian == Hamiltonian.TDA
+        if tda:
+            terms = (terms[0], terms[1], bl.absent(), bl.absent())
+        A = B = None
+        if tda:
+            A, _ = bl.run(nocc, nvirt, nocc, nvirt, terms, eps, "P")
+            M = K = A
+        else:
+            M = nv.empty(nov, nov)
+            K = nv.empty(nov, nov)
+            bl.run(nocc, nvirt, nocc, nvirt, terms, eps, "PQ", out_mode=1, out0=M, out1=K, ld=nov)
+            if want_ab:
+                A, B = bl.run(nocc, nvirt, nocc, nvirt, terms, eps, "PQ")
+        return M, K, A, B
+
+    def _assemble_uhf(self, hamiltonian, spin, want_ab):
+        """Joint (nov_a + nov_b) matrices [[ss_a, os_a],[os_b, ss_b]] -> (M, K, A, B)."""
+        na, va, nb, vb = self.occupations
+        nova, novb = na * va, nb * vb
+        nt = nova + novb
+        tei = self._tei_dev()
+        full = self.tei_mo_type == AO2MOTransformationType.full
+        assert len(tei) == (4 if full else 6)
+        tda = hamiltonian == Hamiltonian.TDA
+        kind = _kind(spin, True)
+        eps_a = bl.split_energies(self.moenergies[0], na)
+        eps_b = bl.split_energies(self.moenergies[1], nb)
+
+        def terms(block):
+            if full:
+                aaaa, aabb, bbaa, bbbb = tei
+                t = {"aa": (kind, aaaa, na, na), "bb": (kind, bbbb, nb, nb),
+                     "ab": ("os", aabb, na, nb), "ba": ("os", bbaa, nb, na)}[block]
+                out = bl.full_terms(*t)
+            else:
+                ovov_aaaa, ovov_aabb, ovov_bbaa, ovov_bbbb, oovv_aaaa, oovv_bbbb = tei
+                t = {"aa": (kind, ovov_aaaa, oovv_aaaa), "bb": (kind, ovov_bbbb, oovv_bbbb),
+                     "ab": ("os", ovov_aabb, None), "ba": ("os", ovov_bbaa, None)}[block]
+                out = bl.partial_terms(*t)
+            if tda:
+                out = (out[0], out[1], bl.absent(), bl.absent())
+            return out
+
+        def fill(out0, out1, mode):
+            # offsets of the four blocks inside an (nt x nt) matrix
+            blocks = (("aa", na, va, na, va, eps_a, 0), ("bb", nb, vb, nb, vb, eps_b, nova * nt + nova),
+                      ("ab", na, va, nb, vb, None, nova), ("ba", nb, vb, na, va, None, nova * nt))
+            for name, ox, vx, oy, vy, eps, off in blocks:
+                if name in ("ab", "ba") and spin == Spin.triplet:
+                    # no Coulomb term, hence no opposite-spin coupling (solvers.py:272-285)
+                    rows, cols = ox * vx, oy * vy
+                    r0, c0 = divmod(off, nt)
+                    for o in (out0, out1):
+                        if o is not None:
+                            o[r0:r0 + rows, c0:c0 + cols].zero_()
+                    continue
+                bl.run(ox, vx, oy, vy, terms(name), eps, "PQ", out_mode=mode, out0=out0, out1=out1,
+                       ld=nt, off0=off, off1=off)
+
+        A = B = None
+        if tda:
+            A = nv.empty(nt, nt)
+            fill(A, None, 0)
+            M = K = A
+        else:
+            M, K = nv.empty(nt, nt), nv.empty(nt, nt)
+            fill(M, K, 1)
+            if want_ab:
+                A, B = nv.empty(nt, nt), nv.empty(nt, nt)
+                fill(A, B, 0)
+        return M, K, A, B
+
+    def _prepare(self, hamiltonian: Hamiltonian, spin: Spin, want_ab: bool = False):
+        assemble = self._assemble_uhf if self.is_uhf else self._assemble_rhf
+        M, K, A, B = assemble(hamiltonian, spin, want_ab)
+        self._system = eng.HalfSizeSystem(M, K, A, B)
+        self._prepared_for = (hamiltonian, spin)
+        return self._system
+
+    # -------------------------------------------------------------- reference API
+    def form_explicit_hessian(self, hamiltonian: Hamiltonian, spin: Spin,
+                              frequency: float | None) -> None:
+        """Materialise G(w) exactly as the reference lays it out (solvers.py:166-385): an
+        ndarray (2nov, 2nov) for RHF, the 4-tuple (G_aa - wD, G_ab, G_ba, G_bb - wD) for UHF."""
+        assert self.tei_mo is not None
+        assert len(self.tei_mo) in (1, 2, 4, 6)
+        assert isinstance(self.tei_mo_type, AO2MOTransformationType)
+        assert isinstance(frequency, float)
+        self._last_call = (hamiltonian, spin, frequency)
+        _, _, A, B = (self._assemble_uhf if self.is_uhf else self._assemble_rhf)(
+            hamiltonian, spin, True)
+        if hamiltonian == Hamiltonian.TDA:
+            B = None
+        if not self.is_uhf:
+            self._explicit_hessian = nv.to_host(eng.super_hessian(A, B, frequency))
+        else:
+            na, va, nb, vb = self.occupations
+            nova = na * va
+
+            def sup(r, c, w):
+                Ab = A[r, c].contiguous()
+                Bb = B[r, c].contiguous() if B is not None else None
+                if w is None:
+                    N1, N2 = Ab.shape
+                    G = nv.zeros(2 * N1, 2 * N2)
+                    G[:N1, :N2] = Ab
+                    G[N1:, N2:] = Ab
+                    if Bb is not None:
+                        G[:N1, N2:] = Bb
+                        G[N1:, :N2] = Bb
+                    return nv.to_host(G)
+                return nv.to_host(eng.super_hessian(Ab, Bb, w))
+
+            a, b = slice(0, nova), slice(nova, None)
+            self._explicit_hessian = (sup(a, a, frequency), sup(a, b, None), sup(b, a, None),
+                                      sup(b, b, frequency))
+        self._lazy_hessian = None
+
+    @property
+    def explicit_hessian(self):
+        if self._explicit_hessian is None and self._lazy_hessian is not None:
+            ham, spin, w = self._lazy_hessian
+            self.form_explicit_hessian(ham, spin, w)
+        return self._explicit_hessian
+
+    @explicit_hessian.setter
+    def explicit_hessian(self, value):
+        self._explicit_hessian = value
+        self._lazy_hessian = None
+
+    @staticmethod
+    def _gpu_inverse(G: np.ndarray) -> np.ndarray:
+        Gd = nv.to_dev(G).clone()
+        ipiv, info = eng.getrf(Gd)
+        if int(info.item()) != 0:
+            raise np.linalg.LinAlgError("Singular matrix")
+        N = int(Gd.shape[0])
+        eye = nv.zeros(N, N)
+        eng.shift_diagonal(eye, N, 1.0)
+        return nv.to_host(eng.getrs(Gd, ipiv, eye))
+
+    @property
+    def explicit_hessian_inv(self):
+        if self._explicit_hessian_inv is None and self.explicit_hessian is not None:
+            self.invert_explicit_hessian()
+        return self._explicit_hessian_inv
+
+    @explicit_hessian_inv.setter
+    def explicit_hessian_inv(self, value):
+        self._explicit_hessian_inv = value
+
+    @abstractmethod
+    def invert_explicit_hessian(self) -> None:
+        """Invert the explicitly constructed electronic Hessian (parity/inspection only: the
+        response vectors never use an explicit inverse)."""
+
+    def _invert_with(self, inv) -> None:
+        G = self.explicit_hessian
+        if not self.is_uhf:
+            assert isinstance(G, np.ndarray)
+            assert len(G.shape) == 2 and G.shape[0] == G.shape[1]
+            self._explicit_hessian_inv = inv(G)
+        else:
+            assert isinstance(G, tuple) and len(G) == 4
+            G_aa, G_ab, G_ba, G_bb = G
+            G_aa_inv, G_bb_inv = inv(G_aa), inv(G_bb)
+            self._explicit_hessian_inv = [G_aa_inv, G_bb_inv]
+            # Schur complements of the spin blocks (reference solvers.py:519-520), via the joint
+            # inverse: left_alph = [G_joint^-1]_aa, left_beta = [G_joint^-1]_bb
+            joint = np.block([[G_aa, G_ab], [G_ba, G_bb]])
+            joint_inv = inv(joint)
+            na2 = G_aa.shape[0]
+            self.left_alph = np.ascontiguousarray(joint_inv[:na2, :na2])
+            self.left_beta = np.ascontiguousarray(joint_inv[na2:, na2:])
+
+    def form_response_vectors(self) -> None:
+        """Solve for the frequency the last ``form_explicit_hessian`` call was made for and append
+        to every operator (reference solvers.py:391-466)."""
+        assert self._last_call is not None, "call form_explicit_hessian / run first"
+        ham, spin, w = self._last_call
+        self._solve_frequencies(ham, spin, [w])
+
+    def _gradient_rows(self):
+        """All operators' property gradients g stacked as rows, plus their supervector signs."""
+        na, va, nb, vb = self.occupations
+        nova, novb = na * va, nb * vb
+        rows, signs = [], []
+        for op in self.operators:
+            ga = op.supervector_dev("alph")[:, :nova]
+            if self.is_uhf:
+                gb = op.supervector_dev("beta")[:, :novb]
+                rows.append(nv.torch_mod().cat((ga, gb), dim=1))
+            else:
+                rows.append(ga)
+            signs += [+1 if op.is_imaginary else -1] * int(ga.shape[0])
+        if not rows:
+            return None, signs
+        return nv.torch_mod().cat(rows, dim=0).contiguous(), signs
+
+    def _solve_xy(self, hamiltonian, spin, frequencies):
+        """(nf, ncols, 2N) CUDA tensor of [X;Y] for the given frequencies (this rank's share)."""
+        if getattr(self, "_prepared_for", None) != (hamiltonian, spin):
+            self._prepare(hamiltonian, spin, want_ab=False)
+        system = self._system
+        g_rows, signs = self._gradient_rows()
+        if g_rows is None:
+            return None
+        try:
+            xy = system.solve(g_rows, signs, frequencies, allow_fallback=False)
+        except eng.LinAlgError:
+            if not self._allow_lu_fallback:
+                raise
+            # pivoted LU on the full G(w) needs the A and B blocks themselves
+            self._prepare(hamiltonian, spin, want_ab=True)
+            system = self._system
+            xy = system.solve(g_rows, signs, frequencies, allow_fallback=True)
+        self.solve_stats = dict(system.stats)
+        return xy
+
+    def _store_xy(self, xy, n_frequencies):
+        na, va, nb, vb = self.occupations
+        nova, novb = na * va, nb * vb
+        nt = nova + novb if self.is_uhf else nova
+        torch = nv.torch_mod()
+        for f in range(n_frequencies):
+            c0 = 0
+            for op in self.operators:
+                nc = int(op.supervector_dev("alph").shape[0])
+                blk = xy[f][c0:c0 + nc]
+                if self.is_uhf:
+                    X, Y = blk[:, :nt], blk[:, nt:]
+                    self._append_rspvecs(op, "alph",
+                                         torch.cat((X[:, :nova], Y[:, :nova]), dim=1).contiguous())
+                    self._append_rspvecs(op, "beta",
+                                         torch.cat((X[:, nova:], Y[:, nova:]), dim=1).contiguous())
+                else:
+                    self._append_rspvecs(op, "alph", blk.contiguous())
+                c0 += nc
+
+    def _solve_frequencies(self, hamiltonian, spin, frequencies):
+        """Solve every frequency (dealt round-robin to the ranks when torch.distributed is up and
+        ``distribute_frequencies`` is set) and append the response vectors in frequency order."""
+        from pymolresponse_b200 import distributed as pd
+
+        rank, world = pd.rank_world()
+        if world > 1 and getattr(self, "distribute_frequencies", False):
+            mine = pd.round_robin(len(frequencies), rank, world)
+            xy_local = self._solve_xy(hamiltonian, spin, [frequencies[i] for i in mine])
+            if xy_local is None:
+                return
+            xy = pd.gather_round_robin([xy_local[k] for k in range(len(mine))], len(frequencies))
+        else:
+            xy = self._solve_xy(hamiltonian, spin, frequencies)
+            if xy is None:
+                return
+        self._store_xy(xy, len(frequencies))
+
+    def run(self, hamiltonian: Hamiltonian, spin: Spin, program: Program | None,
+            program_obj: Any) -> None:
+        if not self.tei_mo:
+            if program is None:
+                msg = "Program must be specified for computing 2-electron integrals in MO basis"
+                raise RuntimeError(msg)
+            self.form_tei_mo(program, program_obj, AO2MOTransformationType.partial)
+        for frequency in self.frequencies:
+            assert isinstance(frequency, float)
+        freqs = [float(w) for w in self.frequencies]
+        self._prepared_for = None
+        if getattr(self, "inv_func", None) is not None and self.inv_func is not np.linalg.inv:
+            # caller-injected inversion routine (reference solvers.py:490-497): honour it literally
+            for w in freqs:
+                self.form_explicit_hessian(hamiltonian, spin, w)
+                self.invert_explicit_hessian()
+                self._response_from_explicit_inverse()
+            return
+        if freqs:
+            self._solve_frequencies(hamiltonian, spin, freqs)
+            self._explicit_hessian = None
+            self._explicit_hessian_inv = None
+            self._lazy_hessian = (hamiltonian, spin, freqs[-1])
+            self._last_call = (hamiltonian, spin, freqs[-1])
+
+    _last_call = None
+
+    def _response_from_explicit_inverse(self):
+        """rsp = G^-1 . rhs with a caller-supplied inverse (device GEMM)."""
+        for op in self.operators:
+            sva = op.supervector_dev("alph")
+            if not self.is_uhf:
+                Ginv = nv.to_dev(self._explicit_hessian_inv)
+                self._append_rspvecs(op, "alph", nv.matmul(sva, Ginv, transpose_b=True))
+            else:
+                svb = op.supervector_dev("beta")
+                _, G_ab, G_ba, _ = (nv.to_dev(g) for g in self._explicit_hessian)
+                G_aa_inv, G_bb_inv = (nv.to_dev(g) for g in self._explicit_hessian_inv)
+                torch = nv.torch_mod()
+                t_b = nv.matmul(nv.matmul(svb, G_bb_inv, transpose_b=True), G_ab, transpose_b=True)
+                t_a = nv.matmul(nv.matmul(sva, G_aa_inv, transpose_b=True), G_ba, transpose_b=True)
+                right_a = eng.axpby(-1.0, t_b, 1.0, sva.clone())
+                right_b = eng.axpby(-1.0, t_a, 1.0, svb.clone())
+                self._append_rspvecs(op, "alph", nv.matmul(right_a, nv.to_dev(self.left_alph),
+                                                          transpose_b=True))
+                self._append_rspvecs(op, "beta", nv.matmul(right_b, nv.to_dev(self.left_beta),
+                                                          transpose_b=True))
+                del torch
+
+
+class ExactInv(ExactLineqSolver):
+    """Exact response vectors; semantics of ``np.linalg.inv(G) @ rhs`` for any frequency
+    (reference solvers.py:483-520)."""
+
+    _allow_lu_fallback = True
+
+    def __init__(self, mocoeffs, moenergies, occupations, *,
+                 inv_func: Callable[[np.ndarray], np.ndarray] | None = None) -> None:
+        super().__init__(mocoeffs, moenergies, occupations)
+        if inv_func is not None:
+            self.inv_func = inv_func
+        else:
+            self.inv_func = np.linalg.inv
+
+    def invert_explicit_hessian(self) -> None:
+        assert self.explicit_hessian is not None
+        if self.inv_func is np.linalg.inv:
+            self._invert_with(self._gpu_inverse)
+        else:
+            self._invert_with(self.inv_func)
+
+
+class ExactInvCholesky(ExactLineqSolver):
+    """Cholesky-only variant: raises ``numpy.linalg.LinAlgError`` when G(w) is not positive
+    definite, as ``scipy.linalg.cholesky`` does in the reference (solvers.py:523-555)."""
+
+    _allow_lu_fallback = False
+
+    def invert_explicit_hessian(self) -> None:
+        assert self.explicit_hessian is not None
+        self._invert_with(self._gpu_inverse)
+
+
+class IterativeLinEqSolver(LineqSolver):
+    """Fixed-point CPHF with J/K builds (reference solvers.py:558-660), RHF only.
+
+    ``jk_generator`` is any :class:`pymolresponse_b200.integrals.JK`; with the GPU ``JKDense``
+    both J/K builds of every operator component are ONE pass of ``pmr_jk_contract`` over the AO
+    ERI tensor per iteration (the reference makes 2 * ncomp separate JK calls, solvers.py:618-619).
+    """
+
+    def __init__(self, mocoeffs, moenergies, occupations, jk_generator: JK, *, maxiter: int = 40,
+                 conv: float = 1.0e-9) -> None:
+        super().__init__(mocoeffs, moenergies, occupations)
+        self.jk_generator = jk_generator
+        self.maxiter = maxiter
+        self.conv = conv
+        self.iterations = []
+
+    def run(self, hamiltonian: Hamiltonian, spin: Spin, program: Program | None,
+            program_obj: Any) -> None:
+        assert self.frequencies
+        for frequency in self.frequencies:
+            self._run(hamiltonian, spin, frequency, self.maxiter, self.conv)
+
+    def _run(self, hamiltonian: Hamiltonian, spin: Spin, omega: float, maxiter: int,
+             conv: float) -> None:
+        nocc, nvirt, nocc_b, nvirt_b = self.occupations
+        assert (nocc + nvirt) == (nocc_b + nvirt_b)
+        norb = nocc + nvirt
+        if self.is_uhf:
+            raise RuntimeError
+        torch = nv.torch_mod()
+        L = nv.lib()
+        Cd = nv.to_dev(self.mocoeffs[0])
+        eps = nv.to_dev(self.moenergies[0]).diagonal().contiguous()
+        Co = Cd[:, :nocc].contiguous()
+        for operator in self.operators:
+            O = nv.to_dev(operator.ao_integrals)
+            ncomp = int(O.shape[0])
+            # rhsmats[c] = C^T O_c C
+            rhs = nv.empty(ncomp, norb, norb)
+            for c in range(ncomp):
+                rhs[c] = nv.matmul(nv.matmul(Cd, O[c].contiguous(), transpose_a=True), Cd)
+            x = nv.zeros(ncomp, norb, norb)
+            x_old = nv.zeros(ncomp, norb, norb)
+            maxdiff = nv.empty(ncomp)
+            # initial guess: uncoupled amplitudes rhs/(+-(e_a - e_i - w)) (solvers.py:606-611)
+            nv.check(L.pmr_cphf_update(nv.ptr(x), nv.ptr(x_old), nv.ptr(rhs), nv.ptr(rhs),
+                                       nv.ptr(eps), float(omega), norb, nocc, ncomp, 1,
+                                       nv.ptr(maxdiff), nv.stream_ptr()))
+            converged = False
+            for it in range(1, maxiter + 1):
+                G = nv.empty(ncomp, norb, norb)
+                # densities D1 = Co (C x^T)[:, :o]^T, D2 = (-C x)[:, :o] Co^T, all components
+                left, right = [], []
+                for c in range(ncomp):
+                    xc = x[c].contiguous()
+                    left.append(Co)
+                    right.append(nv.matmul(Cd, xc, transpose_b=True)[:, :nocc].contiguous())
+                    cl2 = nv.matmul(Cd, xc)[:, :nocc].contiguous()
+                    left.append(eng.axpby(-1.0, cl2, 0.0, nv.empty(cl2.shape[0], cl2.shape[1])))
+                    right.append(Co)
+                JK_list = self.jk_generator.compute_from_mocoeffs_batch(left, right)
+                for c in range(ncomp):
+                    (J1, K1), (J2, K2) = JK_list[2 * c], JK_list[2 * c + 1]
+                    F = eng.axpby(2.0, J1, 0.0, nv.empty(J1.shape[0], J1.shape[1]))
+                    eng.axpby(-1.0, K1, 1.0, F)
+                    eng.axpby(2.0, J2, 1.0, F)
+                    eng.axpby(-1.0, K2, 1.0, F)
+                    G[c] = nv.matmul(nv.matmul(Cd, F, transpose_a=True), Cd)
+                # x_old lags one sweep behind and starts at zero, as in the reference
+                nv.check(L.pmr_cphf_update(nv.ptr(x), nv.ptr(x_old), nv.ptr(rhs), nv.ptr(G),
+                                           nv.ptr(eps), float(omega), norb, nocc, ncomp, 0,
+                                           nv.ptr(maxdiff), nv.stream_ptr()))
+                rms = (maxdiff.cpu().numpy()) ** 2
+                x_old.copy_(x)
+                if rms.max() < conv:
+                    self.iterations.append(it)
+                    ov = x[:, :nocc, nocc:].reshape(ncomp, nocc * nvirt)                   # i*v + a
+                    vo = x[:, nocc:, :nocc].transpose(1, 2).reshape(ncomp, nocc * nvirt)   # i*v + a
+                    vec = torch.cat((ov, vo), dim=1).contiguous()
+                    out = eng.axpby(-1.0, vec, 0.0, nv.empty(ncomp, 2 * nocc * nvirt))
+                    self._append_rspvecs(operator, "alph", out)
+                    converged = True
+                    break
+            if not converged:
+                # the reference silently appends nothing (solvers.py:638-660)
+                self.iterations.append(-1)
+
+
+class EigSolver(Solver, ABC):
+    """Eigen-solvers (TDHF/TDA excitation energies) are outside the linear-response hot path;
+    see DESIGN.md "out of scope"."""

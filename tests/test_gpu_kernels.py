@@ -1,0 +1,252 @@
+"""GPU: each CUDA kernel family of libpmr_b200 against NumPy / the oracle, through the C ABI."""
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _nv():
+    from pymolresponse_b200 import _native as nv
+
+    return nv
+
+
+def _rng(seed=0):
+    return np.random.default_rng(seed)
+
+
+# ----------------------------------------------------------------------------------- GEMM
+def _gemm_case(M, N, K, a_kc, b_kc, pad_a=0, pad_b=0, pad_c=0, alpha=1.0, beta=0.0, seed=0,
+               flags=0, offset=0):
+    """Build operands in the requested memory layout, run pmr_dgemm, return (got, want)."""
+    nv = _nv()
+    r = _rng(seed)
+    A = r.standard_normal((M, K))
+    B = r.standard_normal((K, N))
+    C0 = r.standard_normal((M, N))
+    if a_kc:   # A stored [m][k]
+        Ast = np.zeros((M, K + pad_a)); Ast[:, :K] = A
+        a_sm, a_sk = K + pad_a, 1
+    else:      # A stored [k][m]
+        Ast = np.zeros((K, M + pad_a)); Ast[:, :M] = A.T
+        a_sm, a_sk = 1, M + pad_a
+    if b_kc:   # B stored [n][k]
+        Bst = np.zeros((N, K + pad_b)); Bst[:, :K] = B.T
+        b_sk, b_sn = 1, K + pad_b
+    else:      # B stored [k][n]
+        Bst = np.zeros((K, N + pad_b)); Bst[:, :N] = B
+        b_sk, b_sn = N + pad_b, 1
+    Cst = np.zeros((M, N + pad_c)); Cst[:, :N] = C0
+    # `offset` shifts the base pointers by an odd number of doubles => 8-byte-aligned code path
+    Ad = nv.to_dev(np.concatenate((np.zeros(offset), Ast.ravel())))
+    Bd = nv.to_dev(np.concatenate((np.zeros(offset), Bst.ravel())))
+    Cd = nv.to_dev(np.concatenate((np.zeros(offset), Cst.ravel())))
+    nv.dgemm(M, N, K, alpha, Ad, offset, a_sm, a_sk, Bd, offset, b_sk, b_sn, beta, Cd, offset,
+             N + pad_c, 1, flags=flags)
+    got = nv.to_host(Cd)[offset:].reshape(M, N + pad_c)[:, :N]
+    want = alpha * (A @ B) + beta * C0
+    return got, want, C0
+
+
+@pytest.mark.parametrize("a_kc", [True, False])
+@pytest.mark.parametrize("b_kc", [True, False])
+@pytest.mark.parametrize("shape", [(128, 128, 64), (131, 77, 53), (5, 3, 1), (300, 257, 129),
+                                   (64, 1000, 40), (257, 33, 16), (1, 1, 7), (200, 40, 0)])
+def test_dgemm_layouts_and_ragged_edges(a_kc, b_kc, shape):
+    M, N, K = shape
+    got, want, _ = _gemm_case(M, N, K, a_kc, b_kc, alpha=0.75, beta=-0.5)
+    scale = max(1.0, np.abs(want).max())
+    assert np.abs(got - want).max() <= 1e-13 * scale * max(1, K) ** 0.5
+
+
+@pytest.mark.parametrize("pads", [(1, 1, 1), (2, 0, 3), (0, 3, 0)])
+@pytest.mark.parametrize("offset", [0, 1])
+def test_dgemm_unaligned_strides(pads, offset):
+    """Odd leading dimensions / odd base offsets force the 8-byte cp.async path."""
+    for a_kc in (True, False):
+        for b_kc in (True, False):
+            got, want, _ = _gemm_case(150, 90, 70, a_kc, b_kc, *pads, alpha=1.0, beta=1.0,
+                                      offset=offset, seed=3)
+            assert np.abs(got - want).max() <= 1e-12
+
+
+def test_dgemm_lower_flag_leaves_upper_untouched():
+    nv = _nv()
+    got, want, C0 = _gemm_case(260, 260, 48, True, True, alpha=-1.0, beta=1.0,
+                               flags=nv.GEMM_LOWER, seed=5)
+    low = np.tril(np.ones((260, 260), dtype=bool))
+    assert np.abs(got[low] - want[low]).max() <= 1e-12
+    assert np.array_equal(got[~low], C0[~low])
+
+
+def test_dgemm_batched_two_levels():
+    nv = _nv()
+    r = _rng(7)
+    b1, b2, M, N, K = 3, 4, 70, 45, 33
+    A = r.standard_normal((b1, b2, M, K))
+    B = r.standard_normal((b2, K, N))          # shared across b1 (stride 0)
+    Ad, Bd = nv.to_dev(A), nv.to_dev(B)
+    Cd = nv.zeros(b1, b2, M, N)
+    nv.dgemm(M, N, K, 1.0, Ad, 0, K, 1, Bd, 0, N, 1, 0.0, Cd, 0, N, 1, batch1=b1, batch2=b2,
+             a_b=(b2 * M * K, M * K), b_b=(0, K * N), c_b=(b2 * M * N, M * N))
+    want = np.einsum("xymk,ykn->xymn", A, B)
+    assert np.abs(nv.to_host(Cd) - want).max() <= 1e-12
+
+
+def test_dgemm_strided_c_store_transposes():
+    """C written with (row, col) strides (1, M): the packed-index epilogue used by form_rhs."""
+    nv = _nv()
+    r = _rng(9)
+    M, N, K = 37, 19, 23
+    A, B = r.standard_normal((M, K)), r.standard_normal((K, N))
+    Cd = nv.zeros(N, M)
+    nv.dgemm(M, N, K, 1.0, nv.to_dev(A), 0, K, 1, nv.to_dev(B), 0, N, 1, 0.0, Cd, 0, 1, M)
+    assert np.abs(nv.to_host(Cd) - (A @ B).T).max() <= 1e-12
+
+
+def test_dgemm_rejects_bad_strides():
+    nv = _nv()
+    x = nv.zeros(16)
+    with pytest.raises(nv.PmrError):
+        nv.dgemm(2, 2, 2, 1.0, x, 0, 3, 2, x, 0, 2, 1, 0.0, x, 0, 2, 1)
+
+
+# ----------------------------------------------------------------------------------- Cholesky
+def _spd(n, seed, batch=None):
+    r = _rng(seed)
+    shape = (n, n) if batch is None else (batch, n, n)
+    X = r.standard_normal(shape)
+    return X @ np.swapaxes(X, -1, -2) / max(n, 1) + np.eye(n) * 1.5
+
+
+@pytest.mark.parametrize("n", [1, 5, 128, 129, 300, 515])
+def test_potrf_potrs_batched(n):
+    from pymolresponse_b200 import _engine as eng
+
+    nv = _nv()
+    batch = 3
+    A = _spd(n, 11, batch)
+    Ad = nv.to_dev(A).clone()
+    dinv, info = eng.potrf(Ad, batch=batch)
+    assert (nv.to_host(info) == 0).all()
+    L = np.tril(nv.to_host(Ad))
+    want = np.linalg.cholesky(A)
+    assert np.abs(L - want).max() <= 1e-12 * max(1, n)
+    # the strictly upper triangle is neither read nor written
+    iu = np.triu_indices(n, 1)
+    assert np.array_equal(nv.to_host(Ad)[:, iu[0], iu[1]], A[:, iu[0], iu[1]])
+    rhs = _rng(12).standard_normal((batch, n, 4))
+    X = nv.to_host(eng.potrs(Ad, dinv, nv.to_dev(rhs).clone(), batch=batch))
+    assert np.abs(X - np.linalg.solve(A, rhs)).max() <= 1e-11 * max(1, n)
+
+
+def test_potrf_reports_first_bad_pivot():
+    from pymolresponse_b200 import _engine as eng
+
+    nv = _nv()
+    A = _spd(200, 13)
+    A[150, 150] = -5.0
+    _, info = eng.potrf(nv.to_dev(A).clone())
+    assert int(nv.to_host(info)[0]) == 151
+    B = np.stack((_spd(140, 14), -np.eye(140)))
+    _, info = eng.potrf(nv.to_dev(B).clone(), batch=2)
+    assert list(nv.to_host(info)) == [0, 1]
+
+
+@pytest.mark.parametrize("n", [3, 128, 200, 385])
+def test_potri_lower(n):
+    from pymolresponse_b200 import _engine as eng
+
+    nv = _nv()
+    A = _spd(n, 15)
+    Ad = nv.to_dev(A).clone()
+    dinv, info = eng.potrf(Ad)
+    W = nv.to_host(eng.potri_lower(Ad, dinv))
+    want = np.linalg.inv(A)
+    il = np.tril_indices(n)
+    assert np.abs(W[il] - want[il]).max() <= 1e-11 * max(1, n)
+
+
+def test_shifted_combine_lower_triangle():
+    from pymolresponse_b200 import _engine as eng
+
+    nv = _nv()
+    r = _rng(16)
+    n = 70
+    M, W = r.standard_normal((n, n)), r.standard_normal((n, n))
+    S = nv.to_host(eng.shifted_combine(nv.to_dev(M), nv.to_dev(W), [0.0, 0.25], [-0.5, 2.0]))
+    il = np.tril_indices(n)
+    for f, (a, b) in enumerate(((0.0, -0.5), (0.25, 2.0))):
+        want = M + a * np.eye(n) + b * W
+        assert np.abs(S[f][il] - want[il]).max() <= 1e-14
+
+
+# ----------------------------------------------------------------------------------- LU
+@pytest.mark.parametrize("n", [1, 7, 64, 65, 200])
+def test_getrf_getrs_with_pivoting(n):
+    from pymolresponse_b200 import _engine as eng
+
+    nv = _nv()
+    r = _rng(17)
+    A = r.standard_normal((n, n))
+    if n > 2:
+        A[0, 0] = 0.0          # forces a row interchange in the first column
+        A[2, 2] = 1e-14
+    rhs = r.standard_normal((n, 3))
+    Ad = nv.to_dev(A).clone()
+    ipiv, info = eng.getrf(Ad)
+    assert int(nv.to_host(info)[0]) == 0
+    X = nv.to_host(eng.getrs(Ad, ipiv, nv.to_dev(rhs).clone()))
+    want = np.linalg.solve(A, rhs)
+    assert np.abs(X - want).max() <= 1e-9 * max(1.0, np.abs(want).max())
+    # P A = L U
+    LU = nv.to_host(Ad)
+    Lm, Um = np.tril(LU, -1) + np.eye(n), np.triu(LU)
+    PA = A.copy()
+    for j, p in enumerate(nv.to_host(ipiv)[:n]):
+        PA[[j, p]] = PA[[p, j]]
+    assert np.abs(Lm @ Um - PA).max() <= 1e-12 * max(1, n)
+
+
+def test_getrf_flags_singular_matrix():
+    from pymolresponse_b200 import _engine as eng
+
+    nv = _nv()
+    A = np.ones((6, 6))
+    _, info = eng.getrf(nv.to_dev(A).clone())
+    assert int(nv.to_host(info)[0]) != 0
+
+
+# ----------------------------------------------------------------------------------- small helpers
+def test_contract_and_energy_differences():
+    from pymolresponse_b200 import utils
+
+    r = _rng(18)
+    P, R = r.standard_normal((3, 5000, 1)), r.standard_normal((4, 5000, 1))
+    got = utils.form_results(P, R)
+    assert got.shape == (3, 4)
+    assert np.abs(got - P[:, :, 0] @ R[:, :, 0].T).max() <= 1e-11
+    eo, ev = np.sort(r.uniform(-2, -1, 4)), np.sort(r.uniform(0.5, 2, 9))
+    ed = utils.form_vec_energy_differences(eo, ev)
+    want = np.array([ev[a] - eo[i] for i in range(4) for a in range(9)])
+    assert np.array_equal(ed, want)
+
+
+def test_jk_contract_matches_einsum():
+    from pymolresponse_b200.integrals import JKDense
+
+    r = _rng(19)
+    n = 11
+    I = r.standard_normal((n, n, n, n))
+    D = r.standard_normal((5, n, n))
+    jk = JKDense(I)
+    for d in range(5):
+        J, K = jk.compute_from_density(D[d])
+        assert np.abs(J - np.einsum("pqrs,rs->pq", I, D[d])).max() <= 1e-12
+        assert np.abs(K - np.einsum("prqs,rs->pq", I, D[d])).max() <= 1e-12
+    Cl, Cr = r.standard_normal((n, 3)), r.standard_normal((n, 3))
+    J, K = jk.compute_from_mocoeffs(Cl, Cr)
+    Dm = Cl @ Cr.T
+    assert np.abs(J - np.einsum("pqrs,rs->pq", I, Dm)).max() <= 1e-12
+    assert np.abs(K - np.einsum("prqs,rs->pq", I, Dm)).max() <= 1e-12

@@ -1,0 +1,628 @@
+"""GPU: the reference-facing API of pymolresponse_b200 against the golden vectors of the
+unmodified reference and against the oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): index maps / Hessian layouts bit-exact; MO integrals and
+Hessian elements <= 1e-12 * max|ref|; property tensors <= 1e-8 absolute (we hold 1e-10).
+"""
+
+import numpy as np
+import pytest
+
+from oracle import pmr_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+HAMS = ["rpa", "tda"]
+SPINS = ["singlet", "triplet"]
+
+
+def _enums():
+    from pymolresponse_b200.core import AO2MOTransformationType, Hamiltonian, Spin
+
+    return (AO2MOTransformationType,
+            {"rpa": Hamiltonian.RPA, "tda": Hamiltonian.TDA},
+            {"singlet": Spin.singlet, "triplet": Spin.triplet})
+
+
+def _run(C, E, occ, tei, ttype, ops, freqs, ham, spin, solver_cls=None, **kw):
+    from pymolresponse_b200 import cphf, operators, solvers
+
+    T, H, S = _enums()
+    solver = (solver_cls or solvers.ExactInv)(C, E, occ, **kw)
+    solver.tei_mo = tei
+    solver.tei_mo_type = T[ttype]
+    driver = cphf.CPHF(solver)
+    objs = []
+    for o in ops:
+        op = operators.Operator(label=o.get("label", "dipole"), is_imaginary=o["is_imaginary"],
+                                is_spin_dependent=False, triplet=o.get("triplet", False),
+                                ao_integrals=o["ao_integrals"])
+        driver.add_operator(op)
+        objs.append(op)
+    driver.set_frequencies([float(f) for f in freqs])
+    driver.run(hamiltonian=H[ham], spin=S[spin], program=None, program_obj=None)
+    return solver, driver, objs
+
+
+# ------------------------------------------------------------------------- Hessian blocks (K4/K5)
+def test_hessian_blocks_bit_exact_vs_reference(golden_dir):
+    from pymolresponse_b200 import explicit_equations_full as eqf
+    from pymolresponse_b200 import explicit_equations_partial as eqp
+    from pymolresponse_b200 import synthetic
+
+    g = np.load(golden_dir / "synthetic_rhf_n10.npz")
+    n, o = int(g["n"]), int(g["nocc"])
+    E = synthetic.rhf_case(n, o, build_eri=False)["E"][0]
+    ovov, oovv, full = g["ovov"], g["oovv"], g["full"]
+    got = {
+        "A_singlet_partial": eqp.form_rpa_a_matrix_mo_singlet_partial(E, ovov, oovv),
+        "A_triplet_partial": eqp.form_rpa_a_matrix_mo_triplet_partial(E, oovv),
+        "B_singlet_partial": eqp.form_rpa_b_matrix_mo_singlet_partial(ovov),
+        "B_triplet_partial": eqp.form_rpa_b_matrix_mo_triplet_partial(ovov),
+        "A_singlet_ss_partial": eqp.form_rpa_a_matrix_mo_singlet_ss_partial(E, ovov, oovv),
+        "A_singlet_os_partial": eqp.form_rpa_a_matrix_mo_singlet_os_partial(ovov),
+        "B_singlet_ss_partial": eqp.form_rpa_b_matrix_mo_singlet_ss_partial(ovov),
+        "B_singlet_os_partial": eqp.form_rpa_b_matrix_mo_singlet_os_partial(ovov),
+        "A_singlet_full": eqf.form_rpa_a_matrix_mo_singlet_full(E, full, o),
+        "A_triplet_full": eqf.form_rpa_a_matrix_mo_triplet_full(E, full, o),
+        "B_singlet_full": eqf.form_rpa_b_matrix_mo_singlet_full(full, o),
+        "B_triplet_full": eqf.form_rpa_b_matrix_mo_triplet_full(full, o),
+        "A_singlet_ss_full": eqf.form_rpa_a_matrix_mo_singlet_ss_full(E, full, o),
+        "A_singlet_os_full": eqf.form_rpa_a_matrix_mo_singlet_os_full(full, o, o),
+        "B_singlet_ss_full": eqf.form_rpa_b_matrix_mo_singlet_ss_full(full, o),
+        "B_singlet_os_full": eqf.form_rpa_b_matrix_mo_singlet_os_full(full, o, o),
+    }
+    for key, val in got.items():
+        assert isinstance(val, np.ndarray) and val.dtype == np.float64
+        assert val.shape == g[key].shape, key
+        assert np.array_equal(val, g[key]), key
+
+
+def test_hessian_index_maps_with_integer_fill():
+    """Layout contract: fill the tensors with exact integers that encode their own index and check
+    every element of every block lands where the reference puts it (ragged sizes, tiles + edges)."""
+    from pymolresponse_b200 import explicit_equations_full as eqf
+    from pymolresponse_b200 import explicit_equations_partial as eqp
+
+    o, v = 3, 37
+    n = o + v
+    ovov = np.arange(o * v * o * v, dtype=np.float64).reshape(o, v, o, v)
+    oovv = 7.0 * np.arange(o * o * v * v, dtype=np.float64).reshape(o, o, v, v) + 1.0
+    E = np.diag(np.arange(n, dtype=np.float64) * 3.0)
+    assert np.array_equal(eqp.form_rpa_a_matrix_mo_singlet_partial(E, ovov, oovv),
+                          orc.a_singlet_partial(E, ovov, oovv))
+    assert np.array_equal(eqp.form_rpa_a_matrix_mo_triplet_partial(E, oovv),
+                          orc.a_triplet_partial(E, oovv))
+    assert np.array_equal(eqp.form_rpa_b_matrix_mo_singlet_partial(ovov), orc.b_singlet_partial(ovov))
+    assert np.array_equal(eqp.form_rpa_b_matrix_mo_triplet_partial(ovov), orc.b_triplet_partial(ovov))
+    assert np.array_equal(eqp.form_rpa_a_matrix_mo_singlet_ss_partial(E, ovov, oovv),
+                          orc.a_singlet_ss_partial(E, ovov, oovv))
+    assert np.array_equal(eqp.form_rpa_b_matrix_mo_singlet_ss_partial(ovov),
+                          orc.b_singlet_ss_partial(ovov))
+    # rectangular opposite-spin block (o_x, v_x) x (o_y, v_y)
+    xxyy = np.arange(3 * 37 * 2 * 38, dtype=np.float64).reshape(3, 37, 2, 38)
+    assert np.array_equal(eqp.form_rpa_a_matrix_mo_singlet_os_partial(xxyy), orc.a_singlet_os_partial(xxyy))
+    assert np.array_equal(eqp.form_rpa_b_matrix_mo_singlet_os_partial(xxyy), orc.b_singlet_os_partial(xxyy))
+    # full layout, n = 13, nocc = 4 / 3
+    n = 13
+    T = np.arange(n ** 4, dtype=np.float64).reshape(n, n, n, n)
+    E = np.diag(np.arange(n, dtype=np.float64))
+    assert np.array_equal(eqf.form_rpa_a_matrix_mo_singlet_full(E, T, 4), orc.a_singlet_full(E, T, 4))
+    assert np.array_equal(eqf.form_rpa_a_matrix_mo_triplet_full(E, T, 4), orc.a_triplet_full(E, T, 4))
+    assert np.array_equal(eqf.form_rpa_b_matrix_mo_singlet_full(T, 4), orc.b_singlet_full(T, 4))
+    assert np.array_equal(eqf.form_rpa_b_matrix_mo_triplet_full(T, 4), orc.b_triplet_full(T, 4))
+    assert np.array_equal(eqf.form_rpa_a_matrix_mo_singlet_ss_full(E, T, 4), orc.a_singlet_ss_full(E, T, 4))
+    assert np.array_equal(eqf.form_rpa_b_matrix_mo_singlet_ss_full(T, 4), orc.b_singlet_ss_full(T, 4))
+    assert np.array_equal(eqf.form_rpa_a_matrix_mo_singlet_os_full(T, 4, 3), orc.a_singlet_os_full(T, 4, 3))
+    assert np.array_equal(eqf.form_rpa_b_matrix_mo_singlet_os_full(T, 4, 3), orc.b_singlet_os_full(T, 4, 3))
+
+
+def test_hessian_blocks_empty_and_device_io():
+    from pymolresponse_b200 import _native as nv
+    from pymolresponse_b200 import explicit_equations_partial as eqp
+
+    # no virtual orbitals: empty (0, 0) blocks, as NumPy would give
+    E = np.diag(np.arange(3.0))
+    A = eqp.form_rpa_a_matrix_mo_singlet_partial(E, np.zeros((3, 0, 3, 0)), np.zeros((3, 3, 0, 0)))
+    assert A.shape == (0, 0)
+    # CUDA tensors in -> CUDA tensor out
+    r = np.random.default_rng(3)
+    ovov = r.standard_normal((2, 5, 2, 5))
+    B = eqp.form_rpa_b_matrix_mo_singlet_partial(nv.to_dev(ovov))
+    assert nv.is_device_array(B)
+    assert np.array_equal(nv.to_host(B), orc.b_singlet_partial(ovov))
+
+
+# ------------------------------------------------------------------------- AO2MO (K1-K3)
+def test_ao2mo_rhf_vs_reference(golden_dir):
+    from pymolresponse_b200 import synthetic
+    from pymolresponse_b200.ao2mo import AO2MO
+
+    g = np.load(golden_dir / "synthetic_rhf_n10.npz")
+    n, o = int(g["n"]), int(g["nocc"])
+    case = synthetic.rhf_case(n, o)
+    a = AO2MO(case["C"], case["occupations"], I=case["I"])
+    a.perform_rhf_partial()
+    assert len(a.tei_mo) == 2
+    for got, key in zip(a.tei_mo, ("ovov", "oovv")):
+        assert got.shape == g[key].shape and got.flags["C_CONTIGUOUS"]
+        assert np.abs(got - g[key]).max() <= 1e-12 * np.abs(g[key]).max()
+    a.perform_rhf_full()
+    assert np.abs(a.tei_mo[0] - g["full"]).max() <= 1e-12 * np.abs(g["full"]).max()
+    C = case["C"][0]
+    t = AO2MO.transform(case["I"], C[:, :o], C[:, o:], C[:, :o], C[:, o:])
+    assert np.abs(t - g["ovov"]).max() <= 1e-12 * np.abs(g["ovov"]).max()
+
+
+def test_ao2mo_uhf_vs_reference(golden_dir):
+    from pymolresponse_b200 import synthetic
+    from pymolresponse_b200.ao2mo import AO2MO
+
+    g = np.load(golden_dir / "synthetic_uhf_n9.npz")
+    n, na, nb = int(g["n"]), int(g["na"]), int(g["nb"])
+    case = synthetic.uhf_case(n, na, nb)
+    a = AO2MO(case["C"], case["occupations"], I=case["I"])
+    a.perform_uhf_partial()
+    assert len(a.tei_mo) == 6
+    for k, got in enumerate(a.tei_mo):
+        ref = g[f"partial_{k}"]
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max(), k
+    a.perform_uhf_full()
+    assert len(a.tei_mo) == 4
+    for k, got in enumerate(a.tei_mo):
+        ref = g[f"full_{k}"]
+        assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max(), k
+
+
+@pytest.mark.parametrize("n,o,nu_block", [(24, 5, 0), (24, 5, 7), (33, 4, 16)])
+def test_ao2mo_partial_vs_oracle_and_nu_slabs(n, o, nu_block):
+    """Bigger/odd sizes against the oracle; nu-blocking and nu-sharded slabs give the same blocks."""
+    from pymolresponse_b200 import _native as nv
+    from pymolresponse_b200 import synthetic
+    from pymolresponse_b200.ao2mo import AO2MO
+
+    case = synthetic.rhf_case(n, o)
+    # break the permutational symmetry: the transform must not assume any
+    r = np.random.default_rng(1)
+    I = case["I"] + 0.01 * r.standard_normal(case["I"].shape)
+    ovov_ref, oovv_ref = orc.ao2mo_rhf_partial(I, case["C"], o)
+    a = AO2MO(case["C"], case["occupations"], I=I, nu_block=nu_block)
+    a.perform_rhf_partial()
+    assert np.abs(a.tei_mo[0] - ovov_ref).max() <= 1e-12 * np.abs(ovov_ref).max()
+    assert np.abs(a.tei_mo[1] - oovv_ref).max() <= 1e-12 * np.abs(oovv_ref).max()
+    # two nu-slabs ("two ranks"): partial sums add up to the full blocks
+    half = n // 2 + 1
+    parts = []
+    for lo, hi in ((0, half), (half, n)):
+        s = AO2MO(case["C"], case["occupations"], I=np.ascontiguousarray(I[:, lo:hi]),
+                  nu_range=(lo, hi), device_results=True)
+        s.perform_rhf_partial()
+        parts.append(s.tei_mo)
+    ovov = nv.to_host(parts[0][0] + parts[1][0])
+    oovv = nv.to_host(parts[0][1] + parts[1][1])
+    assert np.abs(ovov - ovov_ref).max() <= 1e-12 * np.abs(ovov_ref).max()
+    assert np.abs(oovv - oovv_ref).max() <= 1e-12 * np.abs(oovv_ref).max()
+
+
+# ------------------------------------------------------------------------- RHS (K11)
+def test_form_rhs_vs_reference(golden_dir):
+    from pymolresponse_b200 import operators, synthetic
+    from pymolresponse_b200.indices import form_indices_from_occupations
+
+    g = np.load(golden_dir / "synthetic_rhf_n10.npz")
+    n, o = int(g["n"]), int(g["nocc"])
+    case = synthetic.rhf_case(n, o, build_eri=False)
+    idx = form_indices_from_occupations(case["occupations"])
+    op = operators.Operator(label="dipole", is_imaginary=False,
+                            ao_integrals=synthetic.operator_integrals(n, 3, False))
+    op.form_rhs(case["C"], case["occupations"], idx)
+    assert op.mo_integrals_ai_alph.shape == g["rhs0_ai"].shape
+    assert op.mo_integrals_ai_supervector_alph.shape == g["rhs0_super"].shape
+    assert np.abs(op.mo_integrals_ai_alph - g["rhs0_ai"]).max() <= 1e-14
+    assert np.abs(op.mo_integrals_ai_supervector_alph - g["rhs0_super"]).max() <= 1e-14
+    op1 = operators.Operator(label="angmom", is_imaginary=True,
+                             ao_integrals=synthetic.operator_integrals(n, 3, True))
+    op1.form_rhs(case["C"], case["occupations"], idx)
+    assert np.abs(op1.mo_integrals_ai_supervector_alph - g["rhs1_super"]).max() <= 1e-14
+    # triplet masking + spin-orbit prefactor against the oracle (operators.py:39-40, 91-98)
+    occ = (4, 6, 3, 7)
+    Cu = np.stack((case["C"][0], case["C"][0][:, ::-1].copy()))
+    O = synthetic.operator_integrals(n, 2, True)
+    op2 = operators.Operator(label="spinorb1", is_imaginary=True, triplet=True, ao_integrals=O)
+    op2.form_rhs(Cu, occ, form_indices_from_occupations(occ))
+    ref = orc.form_rhs(O, Cu, occ, is_imaginary=True, triplet=True, hsofac=op2.hsofac)
+    for tag in ("alph", "beta"):
+        key = f"mo_integrals_ai_supervector_{tag}"
+        assert np.abs(getattr(op2, key) - ref[key]).max() <= 1e-16
+
+
+# ------------------------------------------------------------------------- full path: water (config 1)
+WATER_LITERALS = {
+    ("rpa", "singlet"): [[7.93556221, 3.06821077, 0.05038621], [7.94312371, 3.07051688, 0.05054685],
+                         [8.00414009, 3.08913608, 0.05186977], [8.1290378, 3.12731363, 0.05473482]],
+    ("rpa", "triplet"): [[26.59744305, 18.11879557, 0.07798969], [26.68282287, 18.19390051, 0.07837521],
+                         [27.38617401, 18.81922578, 0.08160226], [28.91067234, 20.21670386, 0.08892512]],
+    ("tda", "singlet"): [[8.89855952, 4.00026556, 0.0552774], [8.90690928, 4.00298342, 0.05545196],
+                         [8.97427725, 4.02491517, 0.05688918], [9.11212633, 4.06981937, 0.05999934]],
+    ("tda", "triplet"): [[14.64430714, 8.80921432, 0.06859496], [14.68168443, 8.83562647, 0.0689291],
+                         [14.98774296, 9.0532224, 0.07172414], [15.63997724, 9.52504267, 0.07805428]],
+}
+
+
+@pytest.mark.parametrize("ham", HAMS)
+@pytest.mark.parametrize("spin", SPINS)
+def test_water_sto3g_polarizability(golden_dir, ham, spin):
+    """Config 1: the reference's tests/test_final_result.py re-hosted on the GPU path."""
+    from pymolresponse_b200 import solvers
+
+    g = np.load(golden_dir / "water_sto3g.npz")
+    ops = [{"ao_integrals": g["dipole"], "is_imaginary": False}]
+    for cls, tag in ((solvers.ExactInv, "inv"), (solvers.ExactInvCholesky, "chol")):
+        solver, driver, objs = _run(g["C"], g["E"], (5, 2, 5, 2), (g["TEI_MO"],), "full", ops,
+                                    g["frequencies"], ham, spin, solver_cls=cls)
+        assert len(driver.results) == 4
+        for f in range(4):
+            assert driver.results[f].shape == (3, 3)
+            np.testing.assert_allclose(driver.results[f], np.diag(WATER_LITERALS[(ham, spin)][f]),
+                                       rtol=0, atol=1e-8)
+        key = f"{ham}_{spin}_{tag}"
+        np.testing.assert_allclose(np.stack(driver.results), g[f"results_{key}"], rtol=0, atol=1e-10)
+        np.testing.assert_allclose(np.stack(driver.uncoupled_results), g[f"uncoupled_{key}"], rtol=0,
+                                   atol=1e-12)
+        assert objs[0].rspvecs_alph[0].shape == (3, 20, 1)
+        np.testing.assert_allclose(np.stack(objs[0].rspvecs_alph), g[f"rspvecs_{key}"], rtol=0,
+                                   atol=1e-10)
+        assert len(objs[0].rspvecs_beta) == 0
+    # lazily materialised explicit Hessian of the last frequency: bit-exact layout
+    solver, _, _ = _run(g["C"], g["E"], (5, 2, 5, 2), (g["TEI_MO"],), "full", ops, g["frequencies"],
+                        ham, spin)
+    assert np.array_equal(solver.explicit_hessian, g[f"hessian_last_{ham}_{spin}_inv"])
+
+
+# ------------------------------------------------------------------------- full path: synthetic RHF
+@pytest.mark.parametrize("ham", HAMS)
+@pytest.mark.parametrize("spin", SPINS)
+@pytest.mark.parametrize("ttype", ["partial", "full"])
+def test_synthetic_rhf_mixed_operators(golden_dir, ham, spin, ttype):
+    from pymolresponse_b200 import synthetic
+
+    g = np.load(golden_dir / "synthetic_rhf_n10.npz")
+    n, o = int(g["n"]), int(g["nocc"])
+    case = synthetic.rhf_case(n, o, build_eri=False)
+    ops = [{"label": "dipole", "ao_integrals": synthetic.operator_integrals(n, 3, False),
+            "is_imaginary": False},
+           {"label": "angmom", "ao_integrals": synthetic.operator_integrals(n, 3, True),
+            "is_imaginary": True}]
+    tei = (g["ovov"], g["oovv"]) if ttype == "partial" else (g["full"],)
+    solver, driver, objs = _run(case["C"], case["E"], case["occupations"], tei, ttype, ops,
+                                g["frequencies"], ham, spin)
+    tag = f"{ham}_{spin}_{ttype}"
+    np.testing.assert_allclose(np.stack(driver.results), g[f"results_{tag}"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(np.stack(driver.uncoupled_results), g[f"uncoupled_{tag}"], rtol=0,
+                               atol=1e-12)
+    for k in (0, 1):
+        ref = g[f"rspvecs{k}_{tag}"]
+        got = np.stack(objs[k].rspvecs_alph)
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max())
+    if ttype == "partial":
+        assert np.array_equal(solver.explicit_hessian, g[f"hessian_last_{tag}"])
+        ref_inv = g[f"hessian_inv_last_{tag}"]
+        assert np.abs(solver.explicit_hessian_inv - ref_inv).max() <= 1e-10 * np.abs(ref_inv).max()
+
+
+def test_rhf_cholesky_solver_and_api_quirks(golden_dir):
+    from pymolresponse_b200 import cphf, operators, solvers, synthetic
+    from pymolresponse_b200.core import Hamiltonian, Spin
+
+    g = np.load(golden_dir / "synthetic_rhf_n10.npz")
+    n, o = int(g["n"]), int(g["nocc"])
+    case = synthetic.rhf_case(n, o, build_eri=False)
+    ops = [{"ao_integrals": synthetic.operator_integrals(n, 3, False), "is_imaginary": False},
+           {"ao_integrals": synthetic.operator_integrals(n, 3, True), "is_imaginary": True}]
+    _, driver, _ = _run(case["C"], case["E"], case["occupations"], (g["ovov"], g["oovv"]), "partial",
+                        ops, g["frequencies"], "rpa", "singlet", solver_cls=solvers.ExactInvCholesky)
+    np.testing.assert_allclose(np.stack(driver.results), g["results_rpa_singlet_partial_chol"],
+                               rtol=0, atol=1e-10)
+    # quirks the drop-in keeps: frequencies must be float (solvers.py:173); no program and no
+    # tei_mo is a RuntimeError (solvers.py:473-475); results default to the static case
+    s = solvers.ExactInv(case["C"], case["E"], case["occupations"])
+    d = cphf.CPHF(s)
+    d.add_operator(operators.Operator(label="dipole", is_imaginary=False,
+                                      ao_integrals=ops[0]["ao_integrals"]))
+    with pytest.raises(RuntimeError):
+        d.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet, program=None, program_obj=None)
+    s.tei_mo = (g["ovov"], g["oovv"])
+    d.set_frequencies([0])
+    with pytest.raises(AssertionError):
+        d.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet, program=None, program_obj=None)
+    s2 = solvers.ExactInv(case["C"], case["E"], case["occupations"])
+    s2.tei_mo = (g["ovov"], g["oovv"])
+    d2 = cphf.CPHF(s2)
+    d2.add_operator(operators.Operator(label="dipole", is_imaginary=False,
+                                       ao_integrals=ops[0]["ao_integrals"]))
+    assert not hasattr(d2, "results")
+    d2.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet, program=None, program_obj=None)
+    assert d2.frequencies == [0.0]
+    np.testing.assert_allclose(d2.results[0], g["results_rpa_singlet_partial"][0][:3, :3], rtol=0,
+                               atol=1e-10)
+
+
+def test_rhf_above_first_pole_lu_fallback(golden_dir):
+    """w above the first pole: G(w) is indefinite.  ExactInv must still return inv(G) rhs (pivoted
+    LU on the device); ExactInvCholesky must raise LinAlgError like scipy.linalg.cholesky."""
+    from pymolresponse_b200 import solvers, synthetic
+
+    g = np.load(golden_dir / "synthetic_rhf_n10.npz")
+    n, o = int(g["n"]), int(g["nocc"])
+    case = synthetic.rhf_case(n, o, build_eri=False)
+    Or = synthetic.operator_integrals(n, 3, False)
+    ops = [{"ao_integrals": Or, "is_imaginary": False}]
+    freqs = [0.1, 1.9]
+    tei = (g["ovov"], g["oovv"])
+    ref = orc.run_cphf(case["C"], case["E"], case["occupations"], tei, "partial", ops, freqs)
+    solver, driver, _ = _run(case["C"], case["E"], case["occupations"], tei, "partial", ops, freqs,
+                             "rpa", "singlet")
+    assert solver.solve_stats["lu_fallback"] >= 1
+    for f in range(2):
+        np.testing.assert_allclose(driver.results[f], ref["results"][f], rtol=0, atol=1e-9)
+    with pytest.raises(np.linalg.LinAlgError):
+        _run(case["C"], case["E"], case["occupations"], tei, "partial", ops, freqs, "rpa", "singlet",
+             solver_cls=solvers.ExactInvCholesky)
+
+
+def test_rhf_custom_inv_func(golden_dir):
+    from pymolresponse_b200 import synthetic
+
+    g = np.load(golden_dir / "synthetic_rhf_n10.npz")
+    n, o = int(g["n"]), int(g["nocc"])
+    case = synthetic.rhf_case(n, o, build_eri=False)
+    ops = [{"ao_integrals": synthetic.operator_integrals(n, 3, False), "is_imaginary": False},
+           {"ao_integrals": synthetic.operator_integrals(n, 3, True), "is_imaginary": True}]
+    calls = []
+
+    def my_inv(G):
+        calls.append(G.shape)
+        return np.linalg.pinv(G)
+
+    _, driver, _ = _run(case["C"], case["E"], case["occupations"], (g["ovov"], g["oovv"]), "partial",
+                        ops, g["frequencies"], "rpa", "singlet", inv_func=my_inv)
+    assert len(calls) == len(g["frequencies"])
+    np.testing.assert_allclose(np.stack(driver.results), g["results_rpa_singlet_partial"], rtol=0,
+                               atol=1e-9)
+
+
+# ------------------------------------------------------------------------- full path: synthetic UHF
+@pytest.mark.parametrize("ham", HAMS)
+@pytest.mark.parametrize("spin", SPINS)
+@pytest.mark.parametrize("ttype", ["partial", "full"])
+def test_synthetic_uhf_mixed_operators(golden_dir, ham, spin, ttype):
+    from pymolresponse_b200 import synthetic
+
+    g = np.load(golden_dir / "synthetic_uhf_n9.npz")
+    n, na, nb = int(g["n"]), int(g["na"]), int(g["nb"])
+    case = synthetic.uhf_case(n, na, nb, build_eri=False)
+    ops = [{"label": "dipole", "ao_integrals": synthetic.operator_integrals(n, 3, False),
+            "is_imaginary": False},
+           {"label": "angmom", "ao_integrals": synthetic.operator_integrals(n, 3, True),
+            "is_imaginary": True}]
+    tei = tuple(g[f"{ttype}_{k}"] for k in range(6 if ttype == "partial" else 4))
+    solver, driver, objs = _run(case["C"], case["E"], case["occupations"], tei, ttype, ops,
+                                g["frequencies"], ham, spin)
+    tag = f"{ham}_{spin}_{ttype}"
+    np.testing.assert_allclose(np.stack(driver.results), g[f"results_{tag}"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(np.stack(driver.uncoupled_results), g[f"uncoupled_{tag}"], rtol=0,
+                               atol=1e-12)
+    for k in (0, 1):
+        for sp in ("alph", "beta"):
+            ref = g[f"rspvecs{k}_{sp}_{tag}"]
+            got = np.stack(getattr(objs[k], f"rspvecs_{sp}"))
+            assert got.shape == ref.shape
+            assert np.abs(got - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max())
+    if tag == "rpa_singlet_partial":
+        G4 = solver.explicit_hessian
+        assert isinstance(G4, tuple) and len(G4) == 4
+        for q in range(4):
+            assert np.array_equal(G4[q], g[f"hessian_last_{q}"])
+        solver.invert_explicit_hessian()
+        assert np.abs(solver.left_alph - g["left_alph_last"]).max() <= 1e-10 * np.abs(g["left_alph_last"]).max()
+        assert np.abs(solver.left_beta - g["left_beta_last"]).max() <= 1e-10 * np.abs(g["left_beta_last"]).max()
+
+
+def test_uhf_cholesky_solver(golden_dir):
+    from pymolresponse_b200 import solvers, synthetic
+
+    g = np.load(golden_dir / "synthetic_uhf_n9.npz")
+    n, na, nb = int(g["n"]), int(g["na"]), int(g["nb"])
+    case = synthetic.uhf_case(n, na, nb, build_eri=False)
+    ops = [{"ao_integrals": synthetic.operator_integrals(n, 3, False), "is_imaginary": False},
+           {"ao_integrals": synthetic.operator_integrals(n, 3, True), "is_imaginary": True}]
+    tei = tuple(g[f"partial_{k}"] for k in range(6))
+    _, driver, _ = _run(case["C"], case["E"], case["occupations"], tei, "partial", ops,
+                        g["frequencies"], "rpa", "singlet", solver_cls=solvers.ExactInvCholesky)
+    np.testing.assert_allclose(np.stack(driver.results), g["results_rpa_singlet_partial_chol"],
+                               rtol=0, atol=1e-10)
+
+
+# ------------------------------------------------------------------------- LiH disk fixtures
+@pytest.mark.parametrize("case,uhf,thresh", [("r_lih_hf_sto-3g", False, 5.0e-3),
+                                             ("u_lih_cation_hf_sto-3g", True, 1.0e-1)])
+def test_lih_dalton_fixtures(golden_dir, case, uhf, thresh):
+    """tests/test_runners.py re-hosted: DALTON values with the reference's thresholds, the
+    reference's own numbers to 1e-10, operator-interchange symmetry (test_calculators.py:87-91)."""
+    from pymolresponse_b200 import cphf, solvers
+    from pymolresponse_b200.core import AO2MOTransformationType, Hamiltonian, Spin
+    from pymolresponse_b200.interfaces.dalton.utils import dalton_label_to_operator
+
+    g = np.load(golden_dir / f"{case}.npz")
+    occ = tuple(int(x) for x in g["occupations"])
+    if uhf:
+        E = np.stack((np.diag(g["moene"][:, 0]), np.diag(g["moene"][:, 1])), axis=0)
+        tei = tuple(g[k] for k in ("moints_iajb_aaaa", "moints_iajb_aabb", "moints_iajb_bbaa",
+                                   "moints_iajb_bbbb", "moints_ijab_aaaa", "moints_ijab_bbbb"))
+    else:
+        E = np.diag(g["moene"][:, 0])[None]
+        tei = (g["moints_iajb_aaaa"], g["moints_ijab_aaaa"])
+    idx = [k for k in range(len(g["ref_value"])) if not np.isnan(g["reference_value"][k])]
+    checked = 0
+    for k in idx[3::41]:
+        solver = solvers.ExactInv(g["C"], E, occ)
+        solver.tei_mo = tei
+        solver.tei_mo_type = AO2MOTransformationType.partial
+        driver = cphf.CPHF(solver)
+        for lab in (str(g["ref_label_1"][k]), str(g["ref_label_2"][k])):
+            op = dalton_label_to_operator(lab)
+            op.ao_integrals = g[f"operator_mn_{op.label}"][op.slice_idx][None]
+            driver.add_operator(op)
+        driver.set_frequencies([float(g["ref_frequency"][k])])
+        driver.run(hamiltonian=Hamiltonian[str(g["ref_hamiltonian"][k]).upper()],
+                   spin=Spin[str(g["ref_spin"][k])], program=None, program_obj=None)
+        res = driver.results[0]
+        assert res.shape == (2, 2)
+        assert abs(abs(res[1, 0]) - abs(res[0, 1])) < 1e-12
+        assert abs(res[1, 0] - g["reference_value"][k]) < 1e-10 * max(1.0, abs(g["reference_value"][k]))
+        assert abs(g["ref_value"][k]) - abs(res[1, 0]) < thresh
+        checked += 1
+    assert checked >= 90
+
+
+# ------------------------------------------------------------------------- iterative path (K10)
+def test_iterative_solver_vs_reference(golden_dir):
+    from pymolresponse_b200 import cphf, operators, solvers, synthetic
+    from pymolresponse_b200.core import Hamiltonian, Spin
+    from pymolresponse_b200.integrals import JKDense
+
+    g = np.load(golden_dir / "synthetic_rhf_n10.npz")
+    n, o = int(g["n"]), int(g["nocc"])
+    case = synthetic.rhf_case(n, o)
+    it = solvers.IterativeLinEqSolver(case["C"], case["E"], case["occupations"], JKDense(case["I"]),
+                                      maxiter=200, conv=1e-24)
+    drv = cphf.CPHF(it)
+    op = operators.Operator(label="dipole", is_imaginary=False,
+                            ao_integrals=synthetic.operator_integrals(n, 3, False))
+    drv.add_operator(op)
+    drv.set_frequencies([0.0, 0.05])
+    drv.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet, program=None, program_obj=None)
+    assert all(k > 0 for k in it.iterations)
+    np.testing.assert_allclose(np.stack(op.rspvecs_alph), g["iterative_rspvecs"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(np.stack(drv.results), g["iterative_results"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(drv.results[0], g["results_rpa_singlet_partial"][0][:3, :3], rtol=0,
+                               atol=1e-8)
+
+
+# ------------------------------------------------------------------------- property wrappers
+def test_polarizability_and_magnetizability_wrappers():
+    """End to end from AO integrals (AO2MO on the GPU inside solver.run) through the wrappers,
+    against the oracle; n = 40, nocc = 6 (nov = 204: several Cholesky panels)."""
+    from pymolresponse_b200 import cphf, integrals, solvers, synthetic
+    from pymolresponse_b200.core import Hamiltonian, Program, Spin
+    from pymolresponse_b200.properties.electric import Polarizability
+    from pymolresponse_b200.properties.magnetic import Magnetizability
+
+    n, o = 40, 6
+    case = synthetic.rhf_case(n, o)
+    Or, Oi = synthetic.operator_integrals(n, 3, False), synthetic.operator_integrals(n, 3, True)
+    gen = integrals.IntegralsArrays({"dipole": Or, "angmom_common_gauge": Oi})
+    freqs = [0.0, 0.1, 0.2, 0.3]
+    tei = orc.ao2mo_rhf_partial(case["I"], case["C"], o)
+    ref_p = orc.run_cphf(case["C"], case["E"], case["occupations"], tei, "partial",
+                         [{"ao_integrals": Or, "is_imaginary": False}], freqs)
+    ref_m = orc.run_cphf(case["C"], case["E"], case["occupations"], tei, "partial",
+                         [{"ao_integrals": Oi, "is_imaginary": True}], [0.0])
+
+    class Prog:  # stands for "a program object that can hand out AO ERIs"
+        ao_eri = case["I"]
+
+    solver = solvers.ExactInv(case["C"], case["E"], case["occupations"])
+    pol = Polarizability(Program.Arrays, gen, cphf.CPHF(solver), frequencies=freqs)
+    pol.form_operators()
+    solver.form_tei_mo(Program.Arrays, Prog(), solver.tei_mo_type)
+    assert np.abs(solver.tei_mo[0] - tei[0]).max() <= 1e-12 * np.abs(tei[0]).max()
+    pol.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet)
+    pol.form_results()
+    assert len(pol.polarizabilities) == 4
+    for f in range(4):
+        np.testing.assert_allclose(pol.polarizabilities[f], ref_p["results"][f], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(pol.polarizabilities[f], pol.polarizabilities[f].T, rtol=0,
+                                   atol=1e-11)
+    solver_m = solvers.ExactInvCholesky(case["C"], case["E"], case["occupations"])
+    solver_m.tei_mo = solver.tei_mo
+    mag = Magnetizability(Program.Arrays, gen, cphf.CPHF(solver_m))
+    mag.form_operators()
+    mag.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet)
+    mag.form_results()
+    np.testing.assert_allclose(mag.magnetizability, ref_m["results"][0] / 4, rtol=0, atol=1e-9)
+
+
+def test_uhf_end_to_end_from_ao_integrals():
+    """Config-4 shaped small case: UHF (5 alpha, 4 beta), AO2MO + joint Cholesky on the GPU."""
+    from pymolresponse_b200 import cphf, operators, solvers, synthetic
+    from pymolresponse_b200.core import AO2MOTransformationType, Hamiltonian, Program, Spin
+
+    n, na, nb = 26, 5, 4
+    case = synthetic.uhf_case(n, na, nb)
+    Or = synthetic.operator_integrals(n, 3, False)
+    tei = orc.ao2mo_uhf_partial(case["I"], case["C"], case["occupations"])
+    ref = orc.run_cphf(case["C"], case["E"], case["occupations"], tei, "partial",
+                       [{"ao_integrals": Or, "is_imaginary": False}], [0.0, 0.15])
+    solver = solvers.ExactInv(case["C"], case["E"], case["occupations"])
+    driver = cphf.CPHF(solver)
+    op = operators.Operator(label="dipole", is_imaginary=False, ao_integrals=Or)
+    driver.add_operator(op)
+    driver.set_frequencies([0.0, 0.15])
+    driver.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet, program=Program.Arrays,
+               program_obj=case["I"])
+    assert solver.tei_mo_type == AO2MOTransformationType.partial and len(solver.tei_mo) == 6
+    for f in range(2):
+        np.testing.assert_allclose(driver.results[f], ref["results"][f], rtol=0, atol=1e-9)
+        assert np.abs(op.rspvecs_alph[f] - ref["rspvecs_alph"][0][f]).max() <= 1e-9
+        assert np.abs(op.rspvecs_beta[f] - ref["rspvecs_beta"][0][f]).max() <= 1e-9
+
+
+# ------------------------------------------------------------------------- larger sizes: properties
+def test_larger_rhf_size_independent_properties():
+    """n = 96, nocc = 12 (nov = 1008): too slow for repeated oracle runs inside the GPU suite, so
+    check what the domain guarantees: (ia|jb) pair symmetry, M/K symmetry, the residual of the
+    solved equations G(w)[X;Y] = rhs formed with the bit-exact A and B blocks, the symmetry of the
+    polarizability tensor, and agreement of the Cholesky path with the pivoted-LU path."""
+    from pymolresponse_b200 import _engine as eng
+    from pymolresponse_b200 import _native as nv
+    from pymolresponse_b200 import cphf, operators, solvers, synthetic
+    from pymolresponse_b200 import explicit_equations_partial as eqp
+    from pymolresponse_b200.ao2mo import AO2MO
+    from pymolresponse_b200.core import Hamiltonian, Spin
+
+    n, o = 96, 12
+    v = n - o
+    case = synthetic.rhf_case(n, o)
+    a = AO2MO(case["C"], case["occupations"], I=case["I"])
+    a.perform_rhf_partial()
+    ovov, oovv = a.tei_mo
+    nov = o * v
+    assert np.abs(ovov.reshape(nov, nov) - ovov.reshape(nov, nov).T).max() <= 1e-13
+    assert np.abs(oovv - oovv.transpose(1, 0, 2, 3)).max() <= 1e-13
+    Or = synthetic.operator_integrals(n, 3, False)
+    freqs = [0.0, 0.2]
+    solver = solvers.ExactInv(case["C"], case["E"], case["occupations"])
+    solver.tei_mo = (ovov, oovv)
+    driver = cphf.CPHF(solver)
+    op = operators.Operator(label="dipole", is_imaginary=False, ao_integrals=Or)
+    driver.add_operator(op)
+    driver.set_frequencies(freqs)
+    driver.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet, program=None, program_obj=None)
+    A = eqp.form_rpa_a_matrix_mo_singlet_partial(case["E"][0], ovov, oovv)
+    B = eqp.form_rpa_b_matrix_mo_singlet_partial(ovov)
+    rhs = op.mo_integrals_ai_supervector_alph[:, :, 0]
+    for f, w in enumerate(freqs):
+        G = np.block([[A, B], [B, A]]) - w * np.diag(np.concatenate((np.ones(nov), -np.ones(nov))))
+        X = op.rspvecs_alph[f][:, :, 0]
+        resid = X @ G.T - rhs
+        assert np.abs(resid).max() <= 1e-11 * max(1.0, np.abs(rhs).max())
+        assert np.abs(driver.results[f] - driver.results[f].T).max() <= 1e-10
+    # pivoted LU on the same G agrees with the batched-Cholesky path
+    sysm = solver._prepare(Hamiltonian.RPA, Spin.singlet, want_ab=True)
+    g_rows = nv.to_dev(rhs[:, :nov])
+    xy_lu = nv.to_host(sysm.solve_lu(g_rows, [-1, -1, -1], 0.2))
+    assert np.abs(xy_lu - op.rspvecs_alph[1][:, :, 0]).max() <= 1e-10
+    del eng

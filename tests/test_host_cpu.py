@@ -1,0 +1,216 @@
+"""CPU: the C-ABI library loads and exports every symbol include/pmr_b200.h declares; host-side
+logic (shapes, index bookkeeping, DALTON labels, sharding helpers, 2-rank gloo exchange); the
+product path refuses to compute without a GPU (no CPU fallback)."""
+
+import os
+import re
+import socket
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+REPO = Path(__file__).resolve().parent.parent
+
+
+def _header_symbols():
+    text = (REPO / "include" / "pmr_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pmr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    import __graft_entry__ as entry
+
+    entry.build()
+    from pymolresponse_b200 import _native as nv
+
+    lib = nv.load_library()
+    names = _header_symbols()
+    assert len(names) >= 25
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in pmr_b200.h but not exported"
+        assert name in nv.SYMBOLS, f"{name} has no ctypes signature"
+    assert set(nv.SYMBOLS) == set(names)
+    assert lib.pmr_version() >= 100
+    assert lib.pmr_launch_count() == 0
+
+
+def test_library_is_sm100a_with_dmma_and_async_copies():
+    from pymolresponse_b200 import _native as nv
+
+    out = subprocess.run(["cuobjdump", "-lelf", str(nv.library_path())], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out.stdout
+    sass = subprocess.run(["cuobjdump", "-sass", str(nv.library_path())], capture_output=True,
+                          text=True).stdout
+    assert "DMMA.8x8x4" in sass and "LDGSTS" in sass
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from pymolresponse_b200 import _native as nv
+    from pymolresponse_b200 import explicit_equations_partial as eqp
+    from pymolresponse_b200.ao2mo import AO2MO
+
+    with pytest.raises(nv.PmrUnavailableError):
+        eqp.form_rpa_b_matrix_mo_singlet_partial(np.zeros((2, 3, 2, 3)))
+    a = AO2MO(np.eye(4), (1, 3, 1, 3), I=np.zeros((4, 4, 4, 4)))
+    with pytest.raises(nv.PmrUnavailableError):
+        a.perform_rhf_partial()
+
+
+def test_product_never_imports_the_oracle():
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|import_module\(.oracle|pmr_oracle", re.M)
+    for path in (REPO / "pymolresponse_b200").rglob("*.py"):
+        assert not pat.search(path.read_text()), path
+
+
+def test_shape_helpers_and_index_maps():
+    from pymolresponse_b200 import utils
+    from pymolresponse_b200.indices import form_indices_from_occupations
+
+    C = np.arange(12.0).reshape(3, 4)
+    assert utils.fix_mocoeffs_shape(C).shape == (1, 3, 4)
+    assert utils.fix_mocoeffs_shape((C, C)).shape == (2, 3, 4)
+    e = np.array([1.0, 2.0, 3.0])
+    E = utils.fix_moenergies_shape(e)
+    assert E.shape == (1, 3, 3) and np.array_equal(np.diag(E[0]), e)
+    assert utils.fix_moenergies_shape(np.stack((e, e))).shape == (2, 3, 3)
+    assert utils.fix_moenergies_shape(np.diag(e)).shape == (1, 3, 3)
+    m = np.arange(6.0).reshape(3, 2)   # (v, o): index i*v + a
+    vec = utils.repack_matrix_to_vector(m)
+    assert np.array_equal(vec, [0, 2, 4, 1, 3, 5])
+    assert np.array_equal(utils.repack_vector_to_matrix(vec, (3, 2)), m)
+    idx = form_indices_from_occupations((3, 4, 2, 5))
+    assert idx.indices_closed_act == [(0, 2), (1, 2)]
+    assert idx.indices_closed_secondary[0] == (0, 3) and len(idx.indices_closed_secondary) == 8
+    assert idx.indices_act_secondary == [(2, 3), (2, 4), (2, 5), (2, 6)]
+
+
+def test_enums_match_reference_names():
+    from pymolresponse_b200.core import AO2MOTransformationType, Hamiltonian, Program, Spin
+
+    assert Hamiltonian["RPA"].value == "rpa" and Hamiltonian["TDA"].value == "tda"
+    assert Spin["singlet"].value == 0 and Spin["triplet"].value == 1
+    assert AO2MOTransformationType.partial.value == "partial"
+    assert {p.value for p in Program} >= {"pyscf", "psi4", "dalton"}
+
+
+def test_dalton_labels():
+    from pymolresponse_b200.interfaces.dalton.utils import clean_dalton_label, dalton_label_to_operator
+
+    assert clean_dalton_label("PSO 002") == "pso_002"
+    op = dalton_label_to_operator("XDIPLEN")
+    assert (op.label, op.slice_idx, op.is_imaginary, op.is_spin_dependent) == ("dipole", 0, False, False)
+    op = dalton_label_to_operator("ZANGMOM")
+    assert (op.label, op.slice_idx, op.is_imaginary) == ("angmom", 2, True)
+    op = dalton_label_to_operator("Y1SPNORB")
+    assert (op.label, op.slice_idx, op.is_imaginary, op.is_spin_dependent) == ("spinorb1", 1, True, True)
+    assert hasattr(op, "hsofac") and abs(op.hsofac - (0.0072973525693 ** 2) / 4) < 1e-12
+    op = dalton_label_to_operator("FC H  02")
+    assert (op.label, op.slice_idx, op.is_spin_dependent) == ("fermi", 1, True)
+    op = dalton_label_to_operator("SD 004 y")
+    assert (op.label, op.slice_idx) == ("sd", 6 + 1)
+
+
+def test_fixture_readers(tmp_path):
+    from pymolresponse_b200 import utils
+
+    (tmp_path / "occ").write_text("2 4 2 4\n")
+    assert utils.read_file_occupations(tmp_path / "occ") == (2, 4, 2, 4)
+    (tmp_path / "m").write_text("2 3\n" + "\n".join(str(float(k)) for k in range(6)) + "\n")
+    assert np.array_equal(utils.read_file_2(tmp_path / "m"), np.arange(6.0).reshape(2, 3))
+    (tmp_path / "d").write_text("1 2 0.5\n2 2 1.5\n")
+    assert np.array_equal(utils.parse_int_file_2(tmp_path / "d", 2), [[0, 0.5], [0.5, 1.5]])
+
+
+def test_solver_constructor_contract():
+    from pymolresponse_b200 import solvers
+    from pymolresponse_b200.core import AO2MOTransformationType
+
+    C, E = np.zeros((1, 4, 4)), np.zeros((1, 4, 4))
+    s = solvers.ExactInv(C, E, (1, 3, 1, 3))
+    assert not s.is_uhf and s.tei_mo is None and s.explicit_hessian is None
+    assert s.tei_mo_type == AO2MOTransformationType.partial and s.inv_func is np.linalg.inv
+    s.set_frequencies(None)
+    assert s.frequencies == [0.0]
+    with pytest.raises(AssertionError):
+        solvers.ExactInv(np.zeros((4, 4)), E, (1, 3, 1, 3))
+    with pytest.raises(AssertionError):
+        solvers.ExactInv(np.zeros((2, 4, 4)), E, (1, 3, 1, 3))
+    it = solvers.IterativeLinEqSolver(C, E, (1, 3, 1, 3), None)
+    assert (it.maxiter, it.conv) == (40, 1.0e-9)
+
+
+def test_shard_helpers():
+    from pymolresponse_b200 import distributed as pd
+
+    for n, w in ((512, 8), (10, 3), (3, 8)):
+        parts = [pd.shard_range(n, r, w) for r in range(w)]
+        assert parts[0][0] == 0 and parts[-1][1] == n
+        assert all(parts[k][1] == parts[k + 1][0] for k in range(w - 1))
+        assert max(hi - lo for lo, hi in parts) - min(hi - lo for lo, hi in parts) <= 1
+    assert pd.round_robin(10, 1, 4) == [1, 5, 9]
+    assert sorted(sum((pd.round_robin(10, r, 4) for r in range(4)), [])) == list(range(10))
+    assert pd.rank_world() == (0, 1)
+
+
+def test_flop_model_matches_survey():
+    from pymolresponse_b200 import synthetic
+
+    assert abs(synthetic.flops_ao2mo_rhf_partial(512, 64) / 1.460e13 - 1) < 2e-3
+    nov = 64 * 448
+    assert abs(synthetic.flops_solve_rhf(nov, 1, 7, 3) / 8.65e13 - 1) < 5e-3
+    assert abs(synthetic.bytes_assemble(nov) / 26.3e9 - 1) < 2e-3
+
+
+_WORKER = r"""
+import sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[3])
+from pymolresponse_b200 import distributed as pd
+rank, world = int(sys.argv[1]), 2
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=rank, world_size=world)
+assert pd.rank_world() == (rank, 2)
+# partial MO-integral blocks are summed over ranks
+blk = torch.full((3, 4), float(rank + 1), dtype=torch.float64)
+pd.allreduce_blocks([blk])
+assert torch.equal(blk, torch.full((3, 4), 3.0, dtype=torch.float64))
+# frequencies dealt round-robin; every rank ends with all response vectors in frequency order
+nf = 5
+mine = pd.round_robin(nf, rank, world)
+local = [torch.full((2, 6), float(f), dtype=torch.float64) for f in mine]
+full = pd.gather_round_robin(local, nf)
+assert len(full) == nf and all(torch.equal(full[f], torch.full((2, 6), float(f), dtype=torch.float64)) for f in range(nf))
+# fewer items than ranks: rank 1 owns nothing
+full = pd.gather_round_robin([torch.ones(2, 2, dtype=torch.float64)] if rank == 0 else [], 1)
+assert len(full) == 1 and torch.equal(full[0], torch.ones(2, 2, dtype=torch.float64))
+lo, hi = pd.shard_range(9, rank, world)
+assert (lo, hi) == ((0, 5) if rank == 0 else (5, 9))
+pd.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_two_rank_gloo_exchange(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), str(port), str(REPO)],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+             for r in range(2)]
+    for r, p in enumerate(procs):
+        out, _ = p.communicate(timeout=240)
+        assert p.returncode == 0, out
+        assert f"ok {r}" in out

@@ -64,6 +64,12 @@ typedef struct {
 } pmr_gemm_t;
 
 int pmr_dgemm(const pmr_gemm_t* g, void* stream);
+/* Measurement aid (bench.py roofline pass): while enabled every GEMM launch of the calling thread
+ * is bracketed by CUDA events on its own stream; fetch sums them per tile class
+ * (out_host[cls*4 + {0,1,2,3}] = launches, ms, algorithmic flops, algorithmic bytes).
+ * Disabling frees the events.  Off by default; never enabled inside a timed region. */
+void pmr_profile_enable(int on);
+int pmr_profile_fetch(double* out_host, int ncls);
 
 /* ------------------------------------------------------------------------------------------
  * AO -> MO two-electron integral transformation.

@@ -77,6 +77,8 @@ SYMBOLS = {
     "pmr_launch_count": (c_ll, []),
     "pmr_reset_launch_count": (None, []),
     "pmr_dgemm": (C.c_int, [C.POINTER(GemmDesc), c_dp]),
+    "pmr_profile_enable": (None, [C.c_int]),
+    "pmr_profile_fetch": (C.c_int, [C.POINTER(C.c_double), C.c_int]),
     "pmr_ao2mo_transform_workspace": (c_ll, [C.c_int] * 5),
     "pmr_ao2mo_transform": (C.c_int, [c_dp, C.c_int, c_dp, C.c_int, C.c_int, c_dp, C.c_int, C.c_int,
                                       c_dp, C.c_int, C.c_int, c_dp, C.c_int, C.c_int, c_dp, c_dp,

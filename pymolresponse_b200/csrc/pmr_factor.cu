@@ -27,63 +27,150 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-__global__ void __launch_bounds__(1024, 1)
+// Diagonal-block kernel: Cholesky of a (<=128)^2 block and the inverse of its factor, one CTA per
+// matrix of the batch, everything in shared memory.  The block is padded with the identity to
+// 128x128 so every loop is uniform.  Work is organised in 32-wide block columns:
+//   factor : warp 0 factors the 32x32 diagonal block in REGISTERS (row per lane, shuffles for the
+//            column broadcasts), then all threads do the TRSM of the rows below (row per thread,
+//            right-looking, accumulators in registers) and the SYRK of the trailing block;
+//   inverse: in place, right to left: inv(D_j) per warp in registers, then
+//            L[below, j] <- -inv(L[below, below]) L[below, j] inv(D_j).
+// 12 + 8 block-level barriers instead of 2 per column.
+constexpr int SB = 32;
+constexpr int TLD = SB + 1;
+constexpr int POTF2_THREADS = 512;
+constexpr size_t POTF2_SMEM = sizeof(double) * (NB * NBLD + (NB - SB) * TLD + NB);
+
+__global__ void __launch_bounds__(POTF2_THREADS, 1)
 potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, int jb,
                    double* __restrict__ dinv, long long stride_dinv, int* __restrict__ info,
                    int k0) {
-  extern __shared__ double L[];  // [NB][NBLD]
+  extern __shared__ double sm[];
+  double* L = sm;                      // [NB][NBLD]
+  double* T = sm + NB * NBLD;          // [NB-SB][TLD]
+  double* rdiag = T + (NB - SB) * TLD; // [NB] reciprocals of the diagonal of L
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
+  constexpr unsigned FULL = 0xffffffffu;
   A += (long long)blockIdx.x * stride_a;
   dinv += (long long)blockIdx.x * stride_dinv;
   info += blockIdx.x;
 
-  for (int idx = tid; idx < jb * jb; idx += 1024) {
-    const int r = idx / jb, c = idx - r * jb;
-    L[r * NBLD + c] = (c <= r) ? A[(long long)r * lda + c] : 0.0;
-  }
-
-  for (int j = 0; j < jb; ++j) {
-    __syncthreads();
-    const double d = L[j * NBLD + j];
-    if (!(d > 0.0)) {
-      if (tid == 0 && *info == 0) *info = k0 + j + 1;
-    }
-    const double ljj = sqrt(d);
-    for (int i = j + 1 + tid; i < jb; i += 1024) L[i * NBLD + j] /= ljj;
-    __syncthreads();
-    if (tid == 0) L[j * NBLD + j] = ljj;
-    for (int i = j + 1 + warp; i < jb; i += 32) {
-      const double lij = L[i * NBLD + j];
-      for (int k = j + 1 + lane; k <= i; k += 32) L[i * NBLD + k] -= lij * L[k * NBLD + j];
-    }
+  for (int idx = tid; idx < NB * NB; idx += POTF2_THREADS) {
+    const int r = idx >> 7, c = idx & (NB - 1);
+    double v = (r == c) ? 1.0 : 0.0;
+    if (r < jb && c <= r) v = A[(long long)r * lda + c];
+    L[r * NBLD + c] = v;
   }
   __syncthreads();
 
-  for (int idx = tid; idx < jb * jb; idx += 1024) {
-    const int r = idx / jb, c = idx - r * jb;
-    if (c <= r) A[(long long)r * lda + c] = L[r * NBLD + c];
+  // ------------------------------------------------------------------ factorisation
+  for (int kb = 0; kb < NB / SB; ++kb) {
+    const int c0 = kb * SB;
+    if (warp == 0) {
+      double a[SB];
+#pragma unroll
+      for (int k = 0; k < SB; ++k) a[k] = L[(c0 + lane) * NBLD + c0 + k];
+      int bad = 0;
+#pragma unroll
+      for (int j = 0; j < SB; ++j) {
+        const double d = __shfl_sync(FULL, a[j], j);
+        if (!(d > 0.0) && bad == 0) bad = c0 + j + 1;
+        const double ljj = sqrt(d);
+        const double rl = 1.0 / ljj;
+        a[j] = (lane == j) ? ljj : a[j] * rl;
+        if (lane == j) rdiag[c0 + j] = rl;
+#pragma unroll
+        for (int k = j + 1; k < SB; ++k) {
+          const double vk = __shfl_sync(FULL, a[j], k);  // L[k][j]
+          a[k] -= a[j] * vk;                              // meaningful for lane >= k only
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < SB; ++k) L[(c0 + lane) * NBLD + c0 + k] = (k <= lane) ? a[k] : 0.0;
+      if (lane == 0 && bad != 0 && *info == 0) *info = k0 + bad;
+    }
+    __syncthreads();
+    const int r0 = c0 + SB;
+    const int nrows = NB - r0;
+    if (tid < nrows) {
+      // X D^T = P for one row of the panel below the diagonal block (right-looking substitution)
+      const int r = r0 + tid;
+      double s[SB];
+#pragma unroll
+      for (int c = 0; c < SB; ++c) s[c] = L[r * NBLD + c0 + c];
+#pragma unroll
+      for (int c = 0; c < SB; ++c) {
+        const double x = s[c] * rdiag[c0 + c];
+        s[c] = x;
+#pragma unroll
+        for (int c2 = c + 1; c2 < SB; ++c2) s[c2] -= x * L[(c0 + c2) * NBLD + c0 + c];
+      }
+#pragma unroll
+      for (int c = 0; c < SB; ++c) L[r * NBLD + c0 + c] = s[c];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nrows * nrows; idx += POTF2_THREADS) {
+      const int rr = idx / nrows, cc = idx - rr * nrows;
+      if (cc > rr) continue;
+      const double* xr = L + (r0 + rr) * NBLD + c0;
+      const double* xc = L + (r0 + cc) * NBLD + c0;
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int q = 0; q < SB; q += 2) {
+        s0 += xr[q] * xc[q];
+        s1 += xr[q + 1] * xc[q + 1];
+      }
+      L[(r0 + rr) * NBLD + r0 + cc] -= (s0 + s1);
+    }
+    __syncthreads();
   }
 
-  // inv(L): warp w solves L x = e_c for columns c = w, w+32, ...; lane owns x[k], k = lane (mod 32)
-  for (int c = warp; c < jb; c += 32) {
-    double xr[NB / 32];
+  for (int idx = tid; idx < NB * NB; idx += POTF2_THREADS) {
+    const int r = idx >> 7, c = idx & (NB - 1);
+    if (r < jb && c <= r) A[(long long)r * lda + c] = L[r * NBLD + c];
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ inverse of L, in place
+  if (warp < NB / SB) {
+    const int c0 = warp * SB;
+    double s[SB];  // column `lane` of inv(D)
 #pragma unroll
-    for (int q = 0; q < NB / 32; ++q) xr[q] = 0.0;
-    for (int i = c; i < jb; ++i) {
-      double s = 0.0;
+    for (int r = 0; r < SB; ++r) s[r] = (r == lane) ? 1.0 : 0.0;
 #pragma unroll
-      for (int q = 0; q < NB / 32; ++q) {
-        const int k = q * 32 + lane;
-        if (k >= c && k < i) s += L[i * NBLD + k] * xr[q];
-      }
-      s = warp_sum(s);
-      const double xi = ((i == c ? 1.0 : 0.0) - s) / L[i * NBLD + i];
+    for (int q = 0; q < SB; ++q) {
+      const double x = s[q] * rdiag[c0 + q];
+      s[q] = x;
 #pragma unroll
-      for (int q = 0; q < NB / 32; ++q)
-        if (q == (i >> 5) && lane == (i & 31)) xr[q] = xi;
-      if (lane == 0) dinv[(long long)i * NB + c] = xi;
+      for (int r = q + 1; r < SB; ++r) s[r] -= L[(c0 + r) * NBLD + c0 + q] * x;
     }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < SB; ++r) L[(c0 + r) * NBLD + c0 + lane] = s[r];
+  }
+  __syncthreads();
+  for (int j = NB / SB - 2; j >= 0; --j) {
+    const int c0 = j * SB, r0 = c0 + SB, nb = NB - r0;
+    for (int idx = tid; idx < nb * SB; idx += POTF2_THREADS) {
+      const int rr = idx >> 5, c = idx & 31;
+      const int r = r0 + rr;
+      double acc = 0.0;
+      for (int q = r0; q <= r; ++q) acc += L[r * NBLD + q] * L[q * NBLD + c0 + c];
+      T[rr * TLD + c] = acc;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nb * SB; idx += POTF2_THREADS) {
+      const int rr = idx >> 5, c = idx & 31;
+      double acc = 0.0;
+      for (int q = c; q < SB; ++q) acc += T[rr * TLD + q] * L[(c0 + q) * NBLD + c0 + c];
+      L[(r0 + rr) * NBLD + c0 + c] = -acc;
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < NB * NB; idx += POTF2_THREADS) {
+    const int r = idx >> 7, c = idx & (NB - 1);
+    if (r < jb && c <= r) dinv[(long long)r * NB + c] = L[r * NBLD + c];
   }
 }
 
@@ -268,28 +355,48 @@ extern "C" int pmr_potrf(double* A, int N, long long lda, int batch, long long s
   if (N == 0) return 0;
   PMR_CHECK_CUDA(cudaMemsetAsync(dinv, 0, sizeof(double) * dstride * batch, st));
   static thread_local bool configured = false;
-  const size_t smem = sizeof(double) * NB * NBLD;
+  const size_t smem = POTF2_SMEM;
   if (!configured) {
     PMR_CHECK_CUDA(cudaFuncSetAttribute(potf2_trtri_kernel,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  const int nblk = (N + NB - 1) / NB;
-  for (int kb = 0; kb < nblk; ++kb) {
-    const int k0 = kb * NB;
-    const int jb = std::min(NB, N - k0);
-    const int rest = N - k0 - jb;
-    double* Akk = A + (long long)k0 * lda + k0;
-    double* dk = dinv + (long long)kb * NB * NB;
-    potf2_trtri_kernel<<<batch, 1024, smem, st>>>(Akk, lda, stride_a, jb, dk, dstride, info, k0);
-    PMR_CHECK_LAUNCH("potf2_trtri_kernel");
+  // Two-level blocking: 128-wide panels are factorised and applied inside an outer block of
+  // NBO columns only; the rest of the matrix sees ONE rank-NBO update per outer block, so the
+  // large trailing GEMMs run with K = 512 (C tile read/written once per 512 columns, not per 128).
+  constexpr int NBO = 512;
+  for (int j0 = 0; j0 < N; j0 += NBO) {
+    const int jend = std::min(N, j0 + NBO);
+    for (int k0 = j0; k0 < jend; k0 += NB) {
+      const int kb = k0 / NB;
+      const int jb = std::min(NB, N - k0);
+      const int rest = N - k0 - jb;
+      double* Akk = A + (long long)k0 * lda + k0;
+      double* dk = dinv + (long long)kb * NB * NB;
+      potf2_trtri_kernel<<<batch, POTF2_THREADS, smem, st>>>(Akk, lda, stride_a, jb, dk, dstride,
+                                                             info, k0);
+      PMR_CHECK_LAUNCH("potf2_trtri_kernel");
+      if (rest > 0) {
+        double* A21 = A + (long long)(k0 + jb) * lda + k0;
+        pmr_gemm_t g = make_gemm(rest, jb, jb, 1.0, A21, lda, 1, dk, 1, NB, 0.0, A21, lda, 1);
+        g.batch1 = batch; g.a_b1 = stride_a; g.b_b1 = dstride; g.c_b1 = stride_a;
+        PMR_TRY(gemm(g, st));
+        const int ncols = jend - (k0 + jb);  // columns of the outer block still to be updated
+        if (ncols > 0) {
+          double* A22 = A + (long long)(k0 + jb) * lda + (k0 + jb);
+          pmr_gemm_t t = make_gemm(rest, ncols, jb, -1.0, A21, lda, 1, A21, 1, lda, 1.0, A22, lda, 1);
+          t.batch1 = batch; t.a_b1 = stride_a; t.b_b1 = stride_a; t.c_b1 = stride_a;
+          t.flags = PMR_GEMM_LOWER;
+          PMR_TRY(gemm(t, st));
+        }
+      }
+    }
+    const int rest = N - jend;
     if (rest > 0) {
-      double* A21 = A + (long long)(k0 + jb) * lda + k0;
-      pmr_gemm_t g = make_gemm(rest, jb, jb, 1.0, A21, lda, 1, dk, 1, NB, 0.0, A21, lda, 1);
-      g.batch1 = batch; g.a_b1 = stride_a; g.b_b1 = dstride; g.c_b1 = stride_a;
-      PMR_TRY(gemm(g, st));
-      double* A22 = A + (long long)(k0 + jb) * lda + (k0 + jb);
-      pmr_gemm_t t = make_gemm(rest, rest, jb, -1.0, A21, lda, 1, A21, 1, lda, 1.0, A22, lda, 1);
+      const int kw = jend - j0;
+      double* P = A + (long long)jend * lda + j0;
+      double* A22 = A + (long long)jend * lda + jend;
+      pmr_gemm_t t = make_gemm(rest, rest, kw, -1.0, P, lda, 1, P, 1, lda, 1.0, A22, lda, 1);
       t.batch1 = batch; t.a_b1 = stride_a; t.b_b1 = stride_a; t.c_b1 = stride_a;
       t.flags = PMR_GEMM_LOWER;
       PMR_TRY(gemm(t, st));

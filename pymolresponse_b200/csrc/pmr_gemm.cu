@@ -15,10 +15,18 @@
 //     epilogues (ov packing of operators.py:94, quarter-transform output orders) are free.
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
+#include <vector>
 
 #include "pmr_common.cuh"
 
 namespace pmr {
+
+// ---- optional per-launch CUDA-event timing (bench.py roofline pass; off by default) ----
+struct ProfRecord { cudaEvent_t e0, e1; int cls; double flops; double bytes; };
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfRecord> g_prof;
+
 namespace {
 
 constexpr int BK = 16;
@@ -75,40 +83,77 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
       : "d"(a), "d"(b));
 }
 
-// Copy one operand tile global -> shared.  XT = tile extent along the m/n ("x") dimension.
-// KC: element (x,k) at g[x*ld + k], smem [x][LD];  !KC: element at g[k*ld + x], smem [k][LD].
-// Out-of-range elements are zero-filled by the copy engine (src-size < cp-size).
+// Per-thread state for copying one operand tile global -> shared with cp.async.  XT = tile extent
+// along the m/n ("x") dimension.  KC: element (x,k) at g[x*ld + k], smem [x][LD]; otherwise element
+// at g[k*ld + x], smem [k][LD].  All address arithmetic that does not depend on the k-tile is done
+// once here; issuing a stage is then ITER cp.async per thread with one add each, and
+// out-of-range elements are zero-filled by the copy engine (src-size < cp-size).
 template <int XT, bool KC, int LD, int NT, int VEC>
-__device__ __forceinline__ void load_tile_v(double* s, const double* __restrict__ g, long long ld,
-                                            int x0, int k0, int X, int K, int tid) {
-  if (KC) {
-    constexpr int CPR = BK / VEC;
-    constexpr int TOTAL = XT * CPR;
+struct TileLoader {
+  static constexpr int CPR = KC ? (BK / VEC) : (XT / VEC);  // chunks per smem row
+  static constexpr int TOTAL = KC ? XT * CPR : BK * CPR;
+  static constexpr int ITER = (TOTAL + NT - 1) / NT;
+  static_assert(NT % CPR == 0, "a thread keeps the same column chunk across its rows");
+  static_assert(TOTAL % NT == 0, "every thread copies the same number of chunks");
+  static constexpr int ROWS_PER_ITER = NT / CPR;
+
+  const double* g;      // operand base (any valid address for fully masked copies)
+  const double* src0;   // source of this thread's first chunk in k-tile 0
+  long long step_i;     // source stride between this thread's successive chunks
+  long long step_kt;    // source stride between k-tiles
+  int dst0;             // smem offset (elements) of the first chunk
+  unsigned rowmask;     // KC: bit i <=> row of chunk i is inside the matrix
+  int col;              // KC: k offset of the chunk inside the tile; !KC: first k row of the thread
+  int xbytes;           // !KC: valid bytes of this thread's x chunk (0, 8 or 16)
+  int K;
+
+  __device__ __forceinline__ void init(const double* gbase, long long ld, int x0, int X, int K_,
+                                       int kbase, int tid) {
+    g = gbase;
+    K = K_;
+    const int r = tid / CPR;
+    const int cc = (tid % CPR) * VEC;
+    if (KC) {
+      col = cc;
+      dst0 = r * LD + cc;
+      src0 = gbase + (long long)(x0 + r) * ld + kbase + cc;
+      step_i = (long long)ROWS_PER_ITER * ld;
+      step_kt = BK;
+      rowmask = 0;
 #pragma unroll
-    for (int c = tid; c < TOTAL; c += NT) {
-      const int x = c / CPR;
-      const int kc = (c % CPR) * VEC;
-      const int gx = x0 + x, gk = k0 + kc;
-      int valid = (gx < X) ? min(max(K - gk, 0), VEC) : 0;
-      const double* src = valid ? (g + (long long)gx * ld + gk) : g;
-      if (VEC == 2) cp_async16(s + x * LD + kc, src, valid * 8);
-      else cp_async8(s + x * LD + kc, src, valid * 8);
-    }
-  } else {
-    constexpr int CPR = XT / VEC;
-    constexpr int TOTAL = BK * CPR;
-#pragma unroll
-    for (int c = tid; c < TOTAL; c += NT) {
-      const int k = c / CPR;
-      const int xc = (c % CPR) * VEC;
-      const int gk = k0 + k, gx = x0 + xc;
-      int valid = (gk < K) ? min(max(X - gx, 0), VEC) : 0;
-      const double* src = valid ? (g + (long long)gk * ld + gx) : g;
-      if (VEC == 2) cp_async16(s + k * LD + xc, src, valid * 8);
-      else cp_async8(s + k * LD + xc, src, valid * 8);
+      for (int i = 0; i < ITER; ++i)
+        if (x0 + r + i * ROWS_PER_ITER < X) rowmask |= (1u << i);
+      xbytes = 0;
+    } else {
+      col = r;
+      dst0 = r * LD + cc;
+      src0 = gbase + (long long)(kbase + r) * ld + x0 + cc;
+      step_i = (long long)ROWS_PER_ITER * ld;
+      step_kt = (long long)BK * ld;
+      rowmask = ~0u;
+      xbytes = min(max(X - (x0 + cc), 0), VEC) * 8;
     }
   }
-}
+
+  // kt: k-tile index relative to kbase; k0 = absolute k of the tile
+  __device__ __forceinline__ void issue(double* s, int kt, int k0) const {
+    const double* src = src0 + (long long)kt * step_kt;
+    const bool kfull = (k0 + BK <= K);
+#pragma unroll
+    for (int i = 0; i < ITER; ++i) {
+      int bytes;
+      if (KC) {
+        bytes = ((rowmask >> i) & 1u) ? (kfull ? VEC * 8 : min(max(K - (k0 + col), 0), VEC) * 8) : 0;
+      } else {
+        bytes = (kfull || k0 + col + i * ROWS_PER_ITER < K) ? xbytes : 0;
+      }
+      const double* p = bytes ? (src + i * step_i) : g;
+      double* d = s + dst0 + i * ROWS_PER_ITER * LD;
+      if (VEC == 2) cp_async16(d, p, bytes);
+      else cp_async8(d, p, bytes);
+    }
+  }
+};
 
 template <int BM, int BN, int WM, int WN, bool AKC, bool BKC>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) dgemm_dmma_kernel(const GemmArgs p) {
@@ -125,15 +170,16 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) dgemm_dmma_kern
   if (lower && bn0 > bm0 + BM - 1) return;
 
   const long long b1 = blockIdx.z, b2 = blockIdx.y;
-  const double* __restrict__ Ab = p.A + b1 * p.a_b1 + b2 * p.a_b2;
-  const double* __restrict__ Bb = p.B + b1 * p.b_b1 + b2 * p.b_b2;
-  double* __restrict__ Cb = p.C + b1 * p.c_b1 + b2 * p.c_b2;
+  const double* Ab = p.A + b1 * p.a_b1 + b2 * p.a_b2;
+  const double* Bb = p.B + b1 * p.b_b1 + b2 * p.b_b2;
+  double* Cb = p.C + b1 * p.c_b1 + b2 * p.c_b2;
 
   int kt_begin = 0;
   int kt_end = (p.K + BK - 1) / BK;
   if (p.flags & PMR_GEMM_KSTART_M) kt_begin = bm0 / BK;
   if (p.flags & PMR_GEMM_KEND_M) kt_end = min(kt_end, (min(p.K, bm0 + BM) + BK - 1) / BK);
   const int KT = max(kt_end - kt_begin, 0);
+  const int kbase = kt_begin * BK;
 
   const int wm0 = (warp % C_::WARPS_M) * WM;
   const int wn0 = (warp / C_::WARPS_M) * WN;
@@ -144,14 +190,24 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) dgemm_dmma_kern
 #pragma unroll
     for (int ni = 0; ni < NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
+  // The copy loops are instantiated for 16-byte and 8-byte granularity; the choice is uniform.
+  TileLoader<BM, AKC, LDA, NT, 2> la2;
+  TileLoader<BM, AKC, LDA, NT, 1> la1;
+  TileLoader<BN, BKC, LDB, NT, 2> lb2;
+  TileLoader<BN, BKC, LDB, NT, 1> lb1;
+  if (p.a_vec2) la2.init(Ab, p.a_ld, bm0, p.M, p.K, kbase, tid);
+  else la1.init(Ab, p.a_ld, bm0, p.M, p.K, kbase, tid);
+  if (p.b_vec2) lb2.init(Bb, p.b_ld, bn0, p.N, p.K, kbase, tid);
+  else lb1.init(Bb, p.b_ld, bn0, p.N, p.K, kbase, tid);
+
   auto load_stage = [&](int slot, int kt) {
     double* As = smem + slot * C_::STAGE_ELEMS;
     double* Bs = As + C_::A_ELEMS;
-    const int k0 = (kt_begin + kt) * BK;
-    if (p.a_vec2) load_tile_v<BM, AKC, LDA, NT, 2>(As, Ab, p.a_ld, bm0, k0, p.M, p.K, tid);
-    else load_tile_v<BM, AKC, LDA, NT, 1>(As, Ab, p.a_ld, bm0, k0, p.M, p.K, tid);
-    if (p.b_vec2) load_tile_v<BN, BKC, LDB, NT, 2>(Bs, Bb, p.b_ld, bn0, k0, p.N, p.K, tid);
-    else load_tile_v<BN, BKC, LDB, NT, 1>(Bs, Bb, p.b_ld, bn0, k0, p.N, p.K, tid);
+    const int k0 = kbase + kt * BK;
+    if (p.a_vec2) la2.issue(As, kt, k0);
+    else la1.issue(As, kt, k0);
+    if (p.b_vec2) lb2.issue(Bs, kt, k0);
+    else lb1.issue(Bs, kt, k0);
   };
 
 #pragma unroll
@@ -163,11 +219,6 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) dgemm_dmma_kern
   for (int kt = 0; kt < KT; ++kt) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
-    {
-      const int nk = kt + STAGES - 1;
-      if (nk < KT) load_stage(nk % STAGES, nk);
-      cp_async_commit();
-    }
     const double* As = smem + (kt % STAGES) * C_::STAGE_ELEMS;
     const double* Bs = As + C_::A_ELEMS;
 #pragma unroll
@@ -185,6 +236,14 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) dgemm_dmma_kern
       for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
         for (int ni = 0; ni < NI; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
+      if (kk == 0) {
+        // Refill the slot consumed in the previous iteration AFTER the first block of DMMAs is
+        // queued: while this warp generates addresses the other warps of the SMSP own the tensor
+        // pipe, so copy issue and math overlap instead of alternating in lock step.
+        const int nk = kt + STAGES - 1;
+        if (nk < KT) load_stage(nk % STAGES, nk);
+        cp_async_commit();
+      }
     }
   }
   cp_async_wait<0>();
@@ -240,7 +299,25 @@ int launch_cfg(const GemmArgs& a, int tiles_n, int batch1, int batch2, cudaStrea
     configured = true;
   }
   dim3 grid((unsigned)(a.tiles_m * (long long)tiles_n), (unsigned)batch2, (unsigned)batch1);
+  ProfRecord rec{};
+  if (g_prof_on) {
+    cudaEventCreate(&rec.e0);
+    cudaEventCreate(&rec.e1);
+    const bool lower = (a.flags & PMR_GEMM_LOWER) != 0;
+    const double nb = (double)batch1 * batch2;
+    const double mn = lower ? 0.5 * (double)a.M * ((double)a.M + 1.0) : (double)a.M * a.N;
+    double kk = a.K;
+    if (a.flags & PMR_GEMM_KSTART_M) kk = 0.5 * a.K;  // triangular k range (K^-1 = Z^T Z)
+    rec.flops = 2.0 * mn * kk * nb;
+    rec.bytes = 8.0 * nb * (mn * (a.beta != 0.0 ? 2.0 : 1.0) + (double)a.M * a.K + (double)a.N * a.K);
+    rec.cls = (BN == 128 ? 0 : (BN == 64 ? 2 : 4)) + (lower ? 1 : 0);
+    cudaEventRecord(rec.e0, st);
+  }
   kern<<<grid, C_::NT, C_::SMEM, st>>>(a);
+  if (g_prof_on) {
+    cudaEventRecord(rec.e1, st);
+    g_prof.push_back(rec);
+  }
   PMR_CHECK_LAUNCH("dgemm_dmma_kernel");
   return 0;
 }
@@ -305,12 +382,41 @@ int gemm(const pmr_gemm_t& g0, cudaStream_t st) {
   int bn = (g.N > 64) ? 128 : (g.N > 32 ? 64 : 32);
   const long long tiles_n = (g.N + bn - 1) / bn;
   PMR_REQUIRE((long long)a.tiles_m * tiles_n < (1LL << 31), "dgemm: too many tiles");
+  static const int warps16 = [] { const char* e = getenv("PMR_GEMM_WARPS"); return e ? atoi(e) : 16; }();
+  if (bn == 128 && warps16 == 16)
+    return launch_layout<128, 128, 32, 32>(a, akc, bkc, (int)tiles_n, g.batch1, g.batch2, st);
   if (bn == 128) return launch_layout<128, 128, 64, 32>(a, akc, bkc, (int)tiles_n, g.batch1, g.batch2, st);
   if (bn == 64) return launch_layout<128, 64, 32, 32>(a, akc, bkc, (int)tiles_n, g.batch1, g.batch2, st);
   return launch_layout<128, 32, 32, 32>(a, akc, bkc, (int)tiles_n, g.batch1, g.batch2, st);
 }
 
 }  // namespace pmr
+
+extern "C" void pmr_profile_enable(int on) {
+  pmr::g_prof_on = on != 0;
+  if (!on) {
+    for (auto& r : pmr::g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    pmr::g_prof.clear();
+  }
+}
+
+// out[cls*4 + {0,1,2,3}] = {launches, total ms, total flops, total algorithmic bytes}, cls < 6:
+// 0/1 = 128x128 tile (plain / lower-triangular update), 2/3 = 128x64, 4/5 = 128x32
+extern "C" int pmr_profile_fetch(double* out_host, int ncls) {
+  for (int k = 0; k < ncls * 4; ++k) out_host[k] = 0.0;
+  for (auto& r : pmr::g_prof) {
+    if (cudaEventSynchronize(r.e1) != cudaSuccess) return pmr::set_error(PMR_ERR_CUDA, "profile sync");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    if (r.cls < ncls) {
+      out_host[r.cls * 4 + 0] += 1.0;
+      out_host[r.cls * 4 + 1] += ms;
+      out_host[r.cls * 4 + 2] += r.flops;
+      out_host[r.cls * 4 + 3] += r.bytes;
+    }
+  }
+  return 0;
+}
 
 extern "C" int pmr_dgemm(const pmr_gemm_t* g, void* stream) {
   if (!g) return pmr::set_error(PMR_ERR_ARG, "pmr_dgemm: null descriptor");

@@ -50,7 +50,6 @@ extern "C" int pmr_ao2mo_transform(const double* I, int n, const double* C1, int
               "ao2mo_transform: workspace too small");
   const long long n2 = (long long)n * n, n3 = n2 * n;
   PMR_REQUIRE(n3 < (1LL << 31) && (long long)d1 * d2 * d3 < (1LL << 31), "ao2mo_transform: too large");
-  PMR_REQUIRE(d1 <= 65535 && d2 <= 65535, "ao2mo_transform: batch dimension above 65535");
   double* T1 = workspace;                      // (d1, n, n, n), later reused as T3 (d1,d2,d3,n)
   double* T2 = workspace + (long long)d1 * n3; // (d1, d2, n, n)
   // Q1 (ao2mo.py:45): T1[A, nu la si] = sum_mu C1[mu,A] I[mu, nu la si]
@@ -104,7 +103,6 @@ extern "C" int pmr_ao2mo_partial(const double* I_slab, int n, int nu_lo, int nu_
   PMR_REQUIRE(o1 >= 0 && v1 >= 0 && n_ket >= 0, "ao2mo_partial: bad dims");
   if (o1 == 0 || nu_cnt == 0) return 0;
   PMR_REQUIRE(I_slab && Co1 && Cv1 && workspace, "ao2mo_partial: null pointer");
-  PMR_REQUIRE(o1 <= 65535, "ao2mo_partial: more than 65535 occupied orbitals");
   const int want_oovv = oovv != nullptr;
   PMR_REQUIRE(workspace_doubles >=
                   pmr_ao2mo_partial_workspace(n, nu_cnt, o1, v1, n_ket, kets, want_oovv, nu_block),
@@ -137,7 +135,6 @@ extern "C" int pmr_ao2mo_partial(const double* I_slab, int n, int nu_lo, int nu_
     for (int k = 0; k < n_ket; ++k) {
       const pmr_ao2mo_ket_t& kt = kets[k];
       if (kt.o2 == 0 || kt.v2 == 0 || v1 == 0) continue;
-      PMR_REQUIRE(cnt <= 65535, "ao2mo_partial: nu block above 65535");
       // X[i,nu',j,si] = sum_la Co2[la,j] H1[i,nu',la,si]
       pmr_gemm_t g2 = make_gemm(kt.o2, n, n, 1.0, kt.Co2, 1, kt.ldc2, H1, n, 1, 0.0, X, n, 1);
       g2.batch1 = o1; g2.batch2 = cnt;

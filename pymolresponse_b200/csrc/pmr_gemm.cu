@@ -30,7 +30,6 @@ static thread_local std::vector<ProfRecord> g_prof;
 namespace {
 
 constexpr int BK = 16;
-constexpr int STAGES = 4;
 constexpr int PAD = 4;
 
 struct GemmArgs {
@@ -43,12 +42,12 @@ struct GemmArgs {
   double* C;
   long long c_sm, c_sn;
   long long a_b1, a_b2, b_b1, b_b2, c_b1, c_b2;
-  int tiles_m;
+  int tiles_m, tiles_n;
   int flags;
   int a_vec2, b_vec2, c_vec2;
 };
 
-template <int BM, int BN, int WM, int WN, bool AKC, bool BKC>
+template <int BM, int BN, int WM, int WN, bool AKC, bool BKC, int NSTAGE>
 struct Cfg {
   static constexpr int WARPS_M = BM / WM;
   static constexpr int WARPS_N = BN / WN;
@@ -60,7 +59,7 @@ struct Cfg {
   static constexpr int LDB = BKC ? (BK + PAD) : (BN + PAD);
   static constexpr int B_ELEMS = BKC ? BN * LDB : BK * LDB;
   static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
-  static constexpr size_t SMEM = size_t(STAGES) * STAGE_ELEMS * sizeof(double);
+  static constexpr size_t SMEM = size_t(NSTAGE) * STAGE_ELEMS * sizeof(double);
 };
 
 __device__ __forceinline__ void cp_async16(double* smem, const double* gmem, int src_bytes) {
@@ -97,67 +96,55 @@ struct TileLoader {
   static_assert(TOTAL % NT == 0, "every thread copies the same number of chunks");
   static constexpr int ROWS_PER_ITER = NT / CPR;
 
-  const double* g;      // operand base (any valid address for fully masked copies)
-  const double* src0;   // source of this thread's first chunk in k-tile 0
-  long long step_i;     // source stride between this thread's successive chunks
-  long long step_kt;    // source stride between k-tiles
+  const double* src0;   // source of this thread's first chunk in k-tile 0 of the current tile
   int dst0;             // smem offset (elements) of the first chunk
-  unsigned rowmask;     // KC: bit i <=> row of chunk i is inside the matrix
+  unsigned mask;        // KC: bit i <=> row of chunk i is inside the matrix; !KC: valid x bytes
   int col;              // KC: k offset of the chunk inside the tile; !KC: first k row of the thread
-  int xbytes;           // !KC: valid bytes of this thread's x chunk (0, 8 or 16)
-  int K;
 
-  __device__ __forceinline__ void init(const double* gbase, long long ld, int x0, int X, int K_,
-                                       int kbase, int tid) {
-    g = gbase;
-    K = K_;
+  __device__ __forceinline__ void init(const double* gbase, long long ld, int x0, int X, int kbase,
+                                       int tid) {
     const int r = tid / CPR;
     const int cc = (tid % CPR) * VEC;
+    dst0 = r * LD + cc;
     if (KC) {
       col = cc;
-      dst0 = r * LD + cc;
       src0 = gbase + (long long)(x0 + r) * ld + kbase + cc;
-      step_i = (long long)ROWS_PER_ITER * ld;
-      step_kt = BK;
-      rowmask = 0;
+      mask = 0;
 #pragma unroll
       for (int i = 0; i < ITER; ++i)
-        if (x0 + r + i * ROWS_PER_ITER < X) rowmask |= (1u << i);
-      xbytes = 0;
+        if (x0 + r + i * ROWS_PER_ITER < X) mask |= (1u << i);
     } else {
       col = r;
-      dst0 = r * LD + cc;
       src0 = gbase + (long long)(kbase + r) * ld + x0 + cc;
-      step_i = (long long)ROWS_PER_ITER * ld;
-      step_kt = (long long)BK * ld;
-      rowmask = ~0u;
-      xbytes = min(max(X - (x0 + cc), 0), VEC) * 8;
+      mask = (unsigned)(min(max(X - (x0 + cc), 0), VEC) * 8);
     }
   }
 
-  // kt: k-tile index relative to kbase; k0 = absolute k of the tile
-  __device__ __forceinline__ void issue(double* s, int kt, int k0) const {
-    const double* src = src0 + (long long)kt * step_kt;
+  // kt: k-tile index relative to kbase; k0 = absolute k of the tile; gsafe: any valid address
+  __device__ __forceinline__ void issue(double* s, int kt, int k0, int K, long long ld,
+                                        const double* gsafe) const {
+    const long long step_i = (long long)ROWS_PER_ITER * ld;
+    const double* src = src0 + (KC ? (long long)kt * BK : (long long)kt * BK * ld);
     const bool kfull = (k0 + BK <= K);
 #pragma unroll
     for (int i = 0; i < ITER; ++i) {
       int bytes;
       if (KC) {
-        bytes = ((rowmask >> i) & 1u) ? (kfull ? VEC * 8 : min(max(K - (k0 + col), 0), VEC) * 8) : 0;
+        bytes = ((mask >> i) & 1u) ? (kfull ? VEC * 8 : min(max(K - (k0 + col), 0), VEC) * 8) : 0;
       } else {
-        bytes = (kfull || k0 + col + i * ROWS_PER_ITER < K) ? xbytes : 0;
+        bytes = (kfull || k0 + col + i * ROWS_PER_ITER < K) ? (int)mask : 0;
       }
-      const double* p = bytes ? (src + i * step_i) : g;
+      const double* ptr = bytes ? (src + i * step_i) : gsafe;
       double* d = s + dst0 + i * ROWS_PER_ITER * LD;
-      if (VEC == 2) cp_async16(d, p, bytes);
-      else cp_async8(d, p, bytes);
+      if (VEC == 2) cp_async16(d, ptr, bytes);
+      else cp_async8(d, ptr, bytes);
     }
   }
 };
 
-template <int BM, int BN, int WM, int WN, bool AKC, bool BKC>
-__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) dgemm_dmma_kernel(const GemmArgs p) {
-  using C_ = Cfg<BM, BN, WM, WN, AKC, BKC>;
+template <int BM, int BN, int WM, int WN, bool AKC, bool BKC, int VEC, int NSTAGE, int MINB>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) dgemm_dmma_kernel(const GemmArgs p) {
+  using C_ = Cfg<BM, BN, WM, WN, AKC, BKC, NSTAGE>;
   constexpr int NT = C_::NT, MI = C_::MI, NI = C_::NI, LDA = C_::LDA, LDB = C_::LDB;
   extern __shared__ __align__(16) double smem[];
 
@@ -184,43 +171,63 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) dgemm_dmma_kern
   const int wm0 = (warp % C_::WARPS_M) * WM;
   const int wn0 = (warp / C_::WARPS_M) * WN;
 
-  double acc[MI][NI][2];
-#pragma unroll
-  for (int mi = 0; mi < MI; ++mi)
-#pragma unroll
-    for (int ni = 0; ni < NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-
-  // The copy loops are instantiated for 16-byte and 8-byte granularity; the choice is uniform.
-  TileLoader<BM, AKC, LDA, NT, 2> la2;
-  TileLoader<BM, AKC, LDA, NT, 1> la1;
-  TileLoader<BN, BKC, LDB, NT, 2> lb2;
-  TileLoader<BN, BKC, LDB, NT, 1> lb1;
-  if (p.a_vec2) la2.init(Ab, p.a_ld, bm0, p.M, p.K, kbase, tid);
-  else la1.init(Ab, p.a_ld, bm0, p.M, p.K, kbase, tid);
-  if (p.b_vec2) lb2.init(Bb, p.b_ld, bn0, p.N, p.K, kbase, tid);
-  else lb1.init(Bb, p.b_ld, bn0, p.N, p.K, kbase, tid);
+  TileLoader<BM, AKC, LDA, NT, VEC> la;  // VEC = 2: 16-byte copies (both operands 16-byte aligned)
+  TileLoader<BN, BKC, LDB, NT, VEC> lb;  // VEC = 1: 8-byte copies (odd strides / offsets)
+  la.init(Ab, p.a_ld, bm0, p.M, kbase, tid);
+  lb.init(Bb, p.b_ld, bn0, p.N, kbase, tid);
 
   auto load_stage = [&](int slot, int kt) {
     double* As = smem + slot * C_::STAGE_ELEMS;
     double* Bs = As + C_::A_ELEMS;
     const int k0 = kbase + kt * BK;
-    if (p.a_vec2) la2.issue(As, kt, k0);
-    else la1.issue(As, kt, k0);
-    if (p.b_vec2) lb2.issue(Bs, kt, k0);
-    else lb1.issue(Bs, kt, k0);
+    la.issue(As, kt, k0, p.K, p.a_ld, p.A);
+    lb.issue(Bs, kt, k0, p.K, p.b_ld, p.B);
   };
 
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
+  for (int s = 0; s < NSTAGE - 1; ++s) {
     if (s < KT) load_stage(s, s);
     cp_async_commit();
   }
 
+  // beta != 0: the old C tile goes INTO the accumulators (scaled by beta/alpha) while the first
+  // stages are in flight, so the epilogue is a pure store: no global-load latency at the tile end.
+  const double alpha = p.alpha;
+  const bool use_beta = (p.beta != 0.0);
+  const double ratio = use_beta ? p.beta / alpha : 0.0;
+  double acc[MI][NI][2];
+#pragma unroll
+  for (int mi = 0; mi < MI; ++mi) {
+    const int m = bm0 + wm0 + mi * 8 + g;
+#pragma unroll
+    for (int ni = 0; ni < NI; ++ni) {
+      acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+      if (use_beta) {
+        const int n = bn0 + wn0 + ni * 8 + 2 * t;
+        if (m < p.M && n < p.N) {
+          const bool ok1 = (n + 1 < p.N) && (!lower || n + 1 <= m);
+          const bool ok0 = (!lower || n <= m);
+          const double* c = Cb + (long long)m * p.c_sm + (long long)n * p.c_sn;
+          if (p.c_vec2 && ok0 && ok1) {
+            const double2 o = *reinterpret_cast<const double2*>(c);
+            acc[mi][ni][0] = ratio * o.x;
+            acc[mi][ni][1] = ratio * o.y;
+          } else {
+            if (ok0) acc[mi][ni][0] = ratio * c[0];
+            if (ok1) acc[mi][ni][1] = ratio * c[p.c_sn];
+          }
+        }
+      }
+    }
+  }
+
+  int slot = 0;
   for (int kt = 0; kt < KT; ++kt) {
-    cp_async_wait<STAGES - 2>();
+    cp_async_wait<NSTAGE - 2>();
     __syncthreads();
-    const double* As = smem + (kt % STAGES) * C_::STAGE_ELEMS;
+    const double* As = smem + slot * C_::STAGE_ELEMS;
     const double* Bs = As + C_::A_ELEMS;
+    slot = (slot + 1 == NSTAGE) ? 0 : slot + 1;
 #pragma unroll
     for (int kk = 0; kk < BK / 4; ++kk) {
       double a[MI], b[NI];
@@ -240,17 +247,15 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) dgemm_dmma_kern
         // Refill the slot consumed in the previous iteration AFTER the first block of DMMAs is
         // queued: while this warp generates addresses the other warps of the SMSP own the tensor
         // pipe, so copy issue and math overlap instead of alternating in lock step.
-        const int nk = kt + STAGES - 1;
-        if (nk < KT) load_stage(nk % STAGES, nk);
+        const int nk = kt + NSTAGE - 1;
+        if (nk < KT) load_stage((slot + NSTAGE - 2) % NSTAGE, nk);
         cp_async_commit();
       }
     }
   }
   cp_async_wait<0>();
 
-  // epilogue: thread owns C(m = ..+g, n = ..+2t, 2t+1) of every 8x8 tile
-  const double alpha = p.alpha, beta = p.beta;
-  const bool use_beta = (beta != 0.0);
+  // epilogue: thread owns C(m = ..+g, n = ..+2t, 2t+1) of every 8x8 tile; pure store
 #pragma unroll
   for (int mi = 0; mi < MI; ++mi) {
     const int m = bm0 + wm0 + mi * 8 + g;
@@ -266,46 +271,38 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) dgemm_dmma_kern
         double2 v;
         v.x = alpha * acc[mi][ni][0];
         v.y = alpha * acc[mi][ni][1];
-        if (use_beta) {
-          const double2 o = *reinterpret_cast<const double2*>(c);
-          v.x += beta * o.x;
-          v.y += beta * o.y;
-        }
         *reinterpret_cast<double2*>(c) = v;
       } else {
-        if (ok0) {
-          double v = alpha * acc[mi][ni][0];
-          if (use_beta) v += beta * c[0];
-          c[0] = v;
-        }
-        if (ok1) {
-          double v = alpha * acc[mi][ni][1];
-          if (use_beta) v += beta * c[p.c_sn];
-          c[p.c_sn] = v;
-        }
+        if (ok0) c[0] = alpha * acc[mi][ni][0];
+        if (ok1) c[p.c_sn] = alpha * acc[mi][ni][1];
       }
     }
   }
 }
 
-template <int BM, int BN, int WM, int WN, bool AKC, bool BKC>
-int launch_cfg(const GemmArgs& a, int tiles_n, int batch1, int batch2, cudaStream_t st) {
-  using C_ = Cfg<BM, BN, WM, WN, AKC, BKC>;
-  auto kern = dgemm_dmma_kernel<BM, BN, WM, WN, AKC, BKC>;
+template <int BM, int BN, int WM, int WN, bool AKC, bool BKC, int VEC, int NSTAGE, int MINB>
+int launch_cfg(GemmArgs a, int batch1, int batch2, cudaStream_t st) {
+  using C_ = Cfg<BM, BN, WM, WN, AKC, BKC, NSTAGE>;
+  auto kern = dgemm_dmma_kernel<BM, BN, WM, WN, AKC, BKC, VEC, NSTAGE, MINB>;
   static thread_local bool configured = false;
   if (!configured) {
     PMR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)C_::SMEM));
     configured = true;
   }
-  dim3 grid((unsigned)(a.tiles_m * (long long)tiles_n), (unsigned)batch2, (unsigned)batch1);
+  a.tiles_m = (a.M + BM - 1) / BM;
+  a.tiles_n = (a.N + BN - 1) / BN;
+  PMR_REQUIRE((long long)a.tiles_m * a.tiles_n < (1LL << 31), "dgemm: too many tiles");
+  PMR_REQUIRE(batch1 <= 65535 && batch2 <= 65535, "dgemm: batch count above 65535");
+  dim3 grid((unsigned)((long long)a.tiles_m * a.tiles_n), (unsigned)batch2, (unsigned)batch1);
   ProfRecord rec{};
   if (g_prof_on) {
     cudaEventCreate(&rec.e0);
     cudaEventCreate(&rec.e1);
     const bool lower = (a.flags & PMR_GEMM_LOWER) != 0;
     const double nb = (double)batch1 * batch2;
-    const double mn = lower ? 0.5 * (double)a.M * ((double)a.M + 1.0) : (double)a.M * a.N;
+    const double nn = std::min(a.M, a.N);
+    const double mn = lower ? 0.5 * nn * (nn + 1.0) + ((double)a.M - nn) * nn : (double)a.M * a.N;
     double kk = a.K;
     if (a.flags & PMR_GEMM_KSTART_M) kk = 0.5 * a.K;  // triangular k range (K^-1 = Z^T Z)
     rec.flops = 2.0 * mn * kk * nb;
@@ -322,13 +319,18 @@ int launch_cfg(const GemmArgs& a, int tiles_n, int batch1, int batch2, cudaStrea
   return 0;
 }
 
-template <int BM, int BN, int WM, int WN>
-int launch_layout(const GemmArgs& a, bool akc, bool bkc, int tiles_n, int b1, int b2,
-                  cudaStream_t st) {
-  if (akc && bkc) return launch_cfg<BM, BN, WM, WN, true, true>(a, tiles_n, b1, b2, st);
-  if (akc && !bkc) return launch_cfg<BM, BN, WM, WN, true, false>(a, tiles_n, b1, b2, st);
-  if (!akc && bkc) return launch_cfg<BM, BN, WM, WN, false, true>(a, tiles_n, b1, b2, st);
-  return launch_cfg<BM, BN, WM, WN, false, false>(a, tiles_n, b1, b2, st);
+template <int BM, int BN, int WM, int WN, int NSTAGE, int MINB>
+int launch_layout(const GemmArgs& a, bool akc, bool bkc, int b1, int b2, cudaStream_t st) {
+  if (a.a_vec2 && a.b_vec2) {
+    if (akc && bkc) return launch_cfg<BM, BN, WM, WN, true, true, 2, NSTAGE, MINB>(a, b1, b2, st);
+    if (akc && !bkc) return launch_cfg<BM, BN, WM, WN, true, false, 2, NSTAGE, MINB>(a, b1, b2, st);
+    if (!akc && bkc) return launch_cfg<BM, BN, WM, WN, false, true, 2, NSTAGE, MINB>(a, b1, b2, st);
+    return launch_cfg<BM, BN, WM, WN, false, false, 2, NSTAGE, MINB>(a, b1, b2, st);
+  }
+  if (akc && bkc) return launch_cfg<BM, BN, WM, WN, true, true, 1, NSTAGE, MINB>(a, b1, b2, st);
+  if (akc && !bkc) return launch_cfg<BM, BN, WM, WN, true, false, 1, NSTAGE, MINB>(a, b1, b2, st);
+  if (!akc && bkc) return launch_cfg<BM, BN, WM, WN, false, true, 1, NSTAGE, MINB>(a, b1, b2, st);
+  return launch_cfg<BM, BN, WM, WN, false, false, 1, NSTAGE, MINB>(a, b1, b2, st);
 }
 
 inline bool even(long long x) { return (x & 1LL) == 0; }
@@ -340,7 +342,6 @@ int gemm(const pmr_gemm_t& g0, cudaStream_t st) {
   pmr_gemm_t g = g0;
   PMR_REQUIRE(g.M >= 0 && g.N >= 0 && g.K >= 0, "dgemm: negative dimension");
   PMR_REQUIRE(g.batch1 >= 1 && g.batch2 >= 1, "dgemm: batch counts must be >= 1");
-  PMR_REQUIRE(g.batch1 <= 65535 && g.batch2 <= 65535, "dgemm: batch count above 65535");
   if (g.M == 0 || g.N == 0) return 0;
   PMR_REQUIRE(g.C != nullptr, "dgemm: null C");
   PMR_REQUIRE(g.K == 0 || (g.A != nullptr && g.B != nullptr), "dgemm: null operand");
@@ -348,6 +349,8 @@ int gemm(const pmr_gemm_t& g0, cudaStream_t st) {
               g.a_sm, g.a_sk);
   PMR_REQUIRE(g.b_sk == 1 || g.b_sn == 1, "dgemm: B needs a unit stride (b_sk=%lld b_sn=%lld)",
               g.b_sk, g.b_sn);
+
+  if (g.alpha == 0.0) { g.K = 0; g.alpha = 1.0; }  // C = beta*C through the accumulator path
 
   // Put the long dimension on M (the 128-row tile): C^T = B^T A^T with C's strides swapped.
   if (g.N > g.M && g.flags == 0) {
@@ -377,17 +380,14 @@ int gemm(const pmr_gemm_t& g0, cudaStream_t st) {
   a.b_vec2 = aligned16(g.B) && even(a.b_ld) && even(g.b_b1) && even(g.b_b2);
   a.c_vec2 = (g.c_sn == 1) && aligned16(g.C) && even(g.c_sm) && even(g.c_b1) && even(g.c_b2);
 
-  constexpr int BM = 128;
-  a.tiles_m = (g.M + BM - 1) / BM;
-  int bn = (g.N > 64) ? 128 : (g.N > 32 ? 64 : 32);
-  const long long tiles_n = (g.N + bn - 1) / bn;
-  PMR_REQUIRE((long long)a.tiles_m * tiles_n < (1LL << 31), "dgemm: too many tiles");
-  static const int warps16 = [] { const char* e = getenv("PMR_GEMM_WARPS"); return e ? atoi(e) : 16; }();
-  if (bn == 128 && warps16 == 16)
-    return launch_layout<128, 128, 32, 32>(a, akc, bkc, (int)tiles_n, g.batch1, g.batch2, st);
-  if (bn == 128) return launch_layout<128, 128, 64, 32>(a, akc, bkc, (int)tiles_n, g.batch1, g.batch2, st);
-  if (bn == 64) return launch_layout<128, 64, 32, 32>(a, akc, bkc, (int)tiles_n, g.batch1, g.batch2, st);
-  return launch_layout<128, 32, 32, 32>(a, akc, bkc, (int)tiles_n, g.batch1, g.batch2, st);
+  // Tile choice.  128x64 with 3 stages keeps TWO CTAs (2 x 8 warps) resident per SM, so one CTA's
+  // store epilogue / pipeline fill overlaps the other's DMMA stream; 128x128 (16 warps, 4 stages)
+  // has one CTA per SM.  PMR_GEMM_TILE selects for experiments.
+  static const int tile_pref = [] { const char* e = getenv("PMR_GEMM_TILE"); return e ? atoi(e) : 64; }();
+  const int bn = (g.N > 64) ? tile_pref : (g.N > 32 ? 64 : 32);
+  if (bn == 128) return launch_layout<128, 128, 32, 32, 4, 1>(a, akc, bkc, g.batch1, g.batch2, st);
+  if (bn == 64) return launch_layout<128, 64, 32, 32, 3, 2>(a, akc, bkc, g.batch1, g.batch2, st);
+  return launch_layout<128, 32, 32, 32, 4, 2>(a, akc, bkc, g.batch1, g.batch2, st);
 }
 
 }  // namespace pmr

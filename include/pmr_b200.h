@@ -48,6 +48,7 @@ void pmr_reset_launch_count(void);
 #define PMR_GEMM_LOWER 1      /* write only C(m,n) with n <= m; tiles above the diagonal skipped */
 #define PMR_GEMM_KSTART_M 2   /* operands vanish for k < m-tile origin: start the k loop there  */
 #define PMR_GEMM_KEND_M 4     /* operands vanish for k >= m-tile end: stop the k loop there     */
+#define PMR_GEMM_C_ALIASES_A 8 /* C is A (in-place A <- alpha A B, beta = 0); needs N <= 128       */
 
 typedef struct {
   int M, N, K;

@@ -69,6 +69,7 @@ class AssembleDesc(C.Structure):
 GEMM_LOWER = 1
 GEMM_KSTART_M = 2
 GEMM_KEND_M = 4
+GEMM_C_ALIASES_A = 8
 
 # name -> (restype, argtypes); must list every symbol include/pmr_b200.h declares
 SYMBOLS = {

@@ -361,47 +361,104 @@ extern "C" int pmr_potrf(double* A, int N, long long lda, int batch, long long s
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  // Two-level blocking: 128-wide panels are factorised and applied inside an outer block of
-  // NBO columns only; the rest of the matrix sees ONE rank-NBO update per outer block, so the
-  // large trailing GEMMs run with K = 512 (C tile read/written once per 512 columns, not per 128).
+  // Two-level blocking + look-ahead.  128-wide panels are factorised and applied inside an outer
+  // block of NBO = 512 columns only; the rest of the matrix sees ONE rank-512 update per outer
+  // block (C tile read/written once per 512 columns, K = 512 GEMMs).  That update is split in two:
+  //   U1: the columns of the NEXT outer block  -> auxiliary high-priority stream `sa`
+  //   U2: everything to the right of it        -> caller's stream `st`
+  // so the latency-bound panel work of block J+1 (potf2 + panel TRSM + inner updates, all on `sa`)
+  // runs underneath the big U2 of block J instead of between two of them.
   constexpr int NBO = 512;
+  static thread_local cudaStream_t sa = nullptr;
+  if (!sa) {
+    int lo = 0, hi = 0;
+    PMR_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    PMR_CHECK_CUDA(cudaStreamCreateWithPriority(&sa, cudaStreamNonBlocking, hi));
+  }
+  std::vector<cudaEvent_t> events;
+  auto new_event = [&](cudaStream_t on) -> cudaEvent_t {
+    cudaEvent_t e = nullptr;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventRecord(e, on);
+    events.push_back(e);
+    return e;
+  };
+  const bool lookahead = N > 2 * NBO;
+  cudaStream_t sp = lookahead ? sa : st;  // stream of the panel work
+  if (lookahead) PMR_CHECK_CUDA(cudaStreamWaitEvent(sa, new_event(st), 0));
+  cudaEvent_t u2_done_prev = nullptr;  // U2 of block J-1 finished (on st)
+
+  auto batched = [&](pmr_gemm_t& t) {
+    t.batch1 = batch; t.a_b1 = stride_a; t.b_b1 = stride_a; t.c_b1 = stride_a;
+  };
+
   for (int j0 = 0; j0 < N; j0 += NBO) {
     const int jend = std::min(N, j0 + NBO);
+    // ---- panel work of this outer block (stream sp)
     for (int k0 = j0; k0 < jend; k0 += NB) {
       const int kb = k0 / NB;
       const int jb = std::min(NB, N - k0);
       const int rest = N - k0 - jb;
       double* Akk = A + (long long)k0 * lda + k0;
       double* dk = dinv + (long long)kb * NB * NB;
-      potf2_trtri_kernel<<<batch, POTF2_THREADS, smem, st>>>(Akk, lda, stride_a, jb, dk, dstride,
+      potf2_trtri_kernel<<<batch, POTF2_THREADS, smem, sp>>>(Akk, lda, stride_a, jb, dk, dstride,
                                                              info, k0);
       PMR_CHECK_LAUNCH("potf2_trtri_kernel");
       if (rest > 0) {
         double* A21 = A + (long long)(k0 + jb) * lda + k0;
         pmr_gemm_t g = make_gemm(rest, jb, jb, 1.0, A21, lda, 1, dk, 1, NB, 0.0, A21, lda, 1);
         g.batch1 = batch; g.a_b1 = stride_a; g.b_b1 = dstride; g.c_b1 = stride_a;
-        PMR_TRY(gemm(g, st));
+        g.flags = PMR_GEMM_C_ALIASES_A;
+        PMR_TRY(gemm(g, sp));
         const int ncols = jend - (k0 + jb);  // columns of the outer block still to be updated
         if (ncols > 0) {
           double* A22 = A + (long long)(k0 + jb) * lda + (k0 + jb);
           pmr_gemm_t t = make_gemm(rest, ncols, jb, -1.0, A21, lda, 1, A21, 1, lda, 1.0, A22, lda, 1);
-          t.batch1 = batch; t.a_b1 = stride_a; t.b_b1 = stride_a; t.c_b1 = stride_a;
+          batched(t);
           t.flags = PMR_GEMM_LOWER;
-          PMR_TRY(gemm(t, st));
+          PMR_TRY(gemm(t, sp));
         }
       }
     }
     const int rest = N - jend;
-    if (rest > 0) {
-      const int kw = jend - j0;
-      double* P = A + (long long)jend * lda + j0;
+    if (rest <= 0) break;
+    const int kw = jend - j0;
+    double* P = A + (long long)jend * lda + j0;  // (rest x kw) panel of L
+    if (!lookahead) {
       double* A22 = A + (long long)jend * lda + jend;
       pmr_gemm_t t = make_gemm(rest, rest, kw, -1.0, P, lda, 1, P, 1, lda, 1.0, A22, lda, 1);
-      t.batch1 = batch; t.a_b1 = stride_a; t.b_b1 = stride_a; t.c_b1 = stride_a;
+      batched(t);
+      t.flags = PMR_GEMM_LOWER;
+      PMR_TRY(gemm(t, st));
+      continue;
+    }
+    const int jnext = std::min(N, jend + NBO);
+    const int w1 = jnext - jend;  // width of the next outer block
+    cudaEvent_t panel_done = new_event(sa);
+    // U1 (sa): A[jend:, jend:jnext] -= P P[0:w1]^T, after U2 of the previous block (same region)
+    if (u2_done_prev) PMR_CHECK_CUDA(cudaStreamWaitEvent(sa, u2_done_prev, 0));
+    {
+      double* A22 = A + (long long)jend * lda + jend;
+      pmr_gemm_t t = make_gemm(rest, w1, kw, -1.0, P, lda, 1, P, 1, lda, 1.0, A22, lda, 1);
+      batched(t);
+      t.flags = PMR_GEMM_LOWER;
+      PMR_TRY(gemm(t, sa));
+    }
+    // U2 (st): A[jnext:, jnext:] -= P[w1:] P[w1:]^T, after the panel of this block
+    const int rest2 = N - jnext;
+    PMR_CHECK_CUDA(cudaStreamWaitEvent(st, panel_done, 0));
+    if (rest2 > 0) {
+      double* P2 = P + (long long)w1 * lda;
+      double* A33 = A + (long long)jnext * lda + jnext;
+      pmr_gemm_t t = make_gemm(rest2, rest2, kw, -1.0, P2, lda, 1, P2, 1, lda, 1.0, A33, lda, 1);
+      batched(t);
       t.flags = PMR_GEMM_LOWER;
       PMR_TRY(gemm(t, st));
     }
+    u2_done_prev = new_event(st);
   }
+  if (lookahead) PMR_CHECK_CUDA(cudaStreamWaitEvent(st, new_event(sa), 0));
+  for (cudaEvent_t e : events) cudaEventDestroy(e);
   return 0;
 }
 

@@ -353,7 +353,7 @@ int gemm(const pmr_gemm_t& g0, cudaStream_t st) {
   if (g.alpha == 0.0) { g.K = 0; g.alpha = 1.0; }  // C = beta*C through the accumulator path
 
   // Put the long dimension on M (the 128-row tile): C^T = B^T A^T with C's strides swapped.
-  if (g.N > g.M && g.flags == 0) {
+  if (g.N > g.M && g.flags == 0) {  // (flags != 0: LOWER / k-range / aliasing keep their roles)
     std::swap(g.M, g.N);
     const double* A = g.A;
     const long long a_sm = g.a_sm, a_sk = g.a_sk, a_b1 = g.a_b1, a_b2 = g.a_b2;
@@ -384,7 +384,12 @@ int gemm(const pmr_gemm_t& g0, cudaStream_t st) {
   // store epilogue / pipeline fill overlaps the other's DMMA stream; 128x128 (16 warps, 4 stages)
   // has one CTA per SM.  PMR_GEMM_TILE selects for experiments.
   static const int tile_pref = [] { const char* e = getenv("PMR_GEMM_TILE"); return e ? atoi(e) : 64; }();
-  const int bn = (g.N > 64) ? tile_pref : (g.N > 32 ? 64 : 32);
+  int bn = (g.N > 64) ? tile_pref : (g.N > 32 ? 64 : 32);
+  if (g.flags & PMR_GEMM_C_ALIASES_A) {
+    // in-place A <- A * B: every CTA must own complete rows, i.e. a single column tile
+    PMR_REQUIRE(g.N <= 128, "dgemm: C may alias A only for N <= 128");
+    if (g.N > bn) bn = 128;
+  }
   if (bn == 128) return launch_layout<128, 128, 32, 32, 4, 1>(a, akc, bkc, g.batch1, g.batch2, st);
   if (bn == 64) return launch_layout<128, 64, 32, 32, 3, 2>(a, akc, bkc, g.batch1, g.batch2, st);
   return launch_layout<128, 32, 32, 32, 4, 2>(a, akc, bkc, g.batch1, g.batch2, st);

@@ -141,6 +141,37 @@ def test_potrf_potrs_batched(n):
     assert np.abs(X - np.linalg.solve(A, rhs)).max() <= 1e-11 * max(1, n)
 
 
+@pytest.mark.parametrize("n,batch", [(1100, 2), (2177, 1), (2560, 3)])
+def test_potrf_lookahead_path(n, batch):
+    """N > 1024 takes the two-stream look-ahead path (outer blocks of 512, panels of 128,
+    in-place panel solves); residual check, since NumPy's factor is not needed at this size."""
+    from pymolresponse_b200 import _engine as eng
+
+    nv = _nv()
+    A = _spd(n, 21, batch)
+    Ad = nv.to_dev(A).clone()
+    dinv, info = eng.potrf(Ad, batch=batch)
+    assert (nv.to_host(info) == 0).all()
+    L = np.tril(nv.to_host(Ad))
+    resid = np.abs(L @ np.swapaxes(L, -1, -2) - A).max()
+    assert resid <= 1e-12 * n
+    rhs = _rng(22).standard_normal((batch, n, 2))
+    X = nv.to_host(eng.potrs(Ad, dinv, nv.to_dev(rhs).clone(), batch=batch))
+    assert np.abs(A @ X - rhs).max() <= 1e-10 * n
+
+
+def test_dgemm_in_place_panel_update():
+    """A <- A * B with the aliasing flag (used by the panel solve of the Cholesky)."""
+    nv = _nv()
+    r = _rng(23)
+    M, K = 1000, 128
+    A, B = r.standard_normal((M, K)), r.standard_normal((K, K))
+    Ad = nv.to_dev(A).clone()
+    Bd = nv.to_dev(B.T.copy())          # B stored [n][k]
+    nv.dgemm(M, K, K, 1.0, Ad, 0, K, 1, Bd, 0, 1, K, 0.0, Ad, 0, K, 1, flags=nv.GEMM_C_ALIASES_A)
+    assert np.abs(nv.to_host(Ad) - A @ B).max() <= 1e-11
+
+
 def test_potrf_reports_first_bad_pivot():
     from pymolresponse_b200 import _engine as eng
 

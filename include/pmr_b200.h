@@ -149,6 +149,10 @@ int pmr_energy_differences(const double* eps_occ, int no, const double* eps_virt
  * diagonal blocks of L (needed by the solves): pmr_potrf_dinv_doubles(N) doubles per matrix.
  * ---------------------------------------------------------------------------------------- */
 long long pmr_potrf_dinv_doubles(int N);
+/* pmr_potrf overlaps panel factorisations with trailing updates on a second, high-priority stream
+ * (look-ahead).  Switch it off to get serialised, individually timeable kernels (bench.py's
+ * roofline pass does); results are identical either way.  Per calling thread; default on. */
+void pmr_set_lookahead(int on);
 int pmr_potrf(double* A, int N, long long lda, int batch, long long stride_a, double* dinv,
               int* info /* device, batch ints */, void* stream);
 /* Solve A X = B in place of B (B is N x nrhs, row stride ldb); `work` has N*nrhs doubles/batch. */

@@ -92,6 +92,7 @@ SYMBOLS = {
     "pmr_assemble": (C.c_int, [C.POINTER(AssembleDesc), c_dp]),
     "pmr_energy_differences": (C.c_int, [c_dp, C.c_int, c_dp, C.c_int, c_dp, c_dp]),
     "pmr_potrf_dinv_doubles": (c_ll, [C.c_int]),
+    "pmr_set_lookahead": (None, [C.c_int]),
     "pmr_potrf": (C.c_int, [c_dp, C.c_int, c_ll, C.c_int, c_ll, c_dp, c_dp, c_dp]),
     "pmr_potrs": (C.c_int, [c_dp, C.c_int, c_ll, C.c_int, c_ll, c_dp, c_dp, C.c_int, c_ll, c_ll,
                             c_dp, c_dp]),

@@ -20,6 +20,7 @@ namespace {
 
 constexpr int NB = 128;
 constexpr int NBLD = NB + 1;
+static thread_local bool g_lookahead = true;
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -339,6 +340,8 @@ __global__ void lu_diag_solve_kernel(const double* __restrict__ LU, long long ld
 
 using namespace pmr;
 
+extern "C" void pmr_set_lookahead(int on) { g_lookahead = on != 0; }
+
 extern "C" long long pmr_potrf_dinv_doubles(int N) {
   const long long nblk = (N + NB - 1) / NB;
   return nblk * NB * NB;
@@ -383,7 +386,7 @@ extern "C" int pmr_potrf(double* A, int N, long long lda, int batch, long long s
     events.push_back(e);
     return e;
   };
-  const bool lookahead = N > 2 * NBO;
+  const bool lookahead = g_lookahead && N > 2 * NBO;
   cudaStream_t sp = lookahead ? sa : st;  // stream of the panel work
   if (lookahead) PMR_CHECK_CUDA(cudaStreamWaitEvent(sa, new_event(st), 0));
   cudaEvent_t u2_done_prev = nullptr;  // U2 of block J-1 finished (on st)

@@ -293,7 +293,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------- ours
@@ -435,12 +435,35 @@ def run_ours(args):
             "check": {"alpha_static_diag": [float(x) for x in np.diag(alpha0)],
                       "solve_stats": res.get("stats")},
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         pd.barrier()
+        pd.dist().destroy_process_group()
+
+
+def _claim_stdout():
+    """Route everything libraries print on fd 1 (NCCL banners ...) to stderr and keep a private
+    handle on the real stdout, so rank 0 prints exactly ONE JSON line there."""
+    real = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    return real
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    global _REAL_STDOUT
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+    _REAL_STDOUT = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

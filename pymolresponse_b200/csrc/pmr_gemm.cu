@@ -319,6 +319,258 @@ int launch_cfg(GemmArgs a, int batch1, int batch2, cudaStream_t st) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// TMA (bulk async copy) + mbarrier, warp-specialised variant for operands that are contiguous along
+// m / n (A stored [k][m], B stored [k][n]): every k row of a tile is ONE cp.async.bulk (UBLKCP) of up
+// to 1 KiB issued by a dedicated producer warp and tracked by the stage's mbarrier (complete_tx);
+// the 8/4 math warps never touch global memory or a CTA-wide barrier inside the main loop -- they
+// wait on the stage's "full" mbarrier and release the slot through its "empty" mbarrier.
+// Used by the first AO->MO quarter (the 34-550 GB AO tensor is the streamed A operand) and by the
+// Z^T Z product of the inverse; needs 16-byte aligned rows, even M/N and K % 16 == 0, otherwise the
+// cp.async kernel (hardware zero-fill) runs.  Shared-memory layout and fragment mapping are the
+// same as above, so are the results (bit-identical accumulation order).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(double* dst, const double* src, unsigned bytes,
+                                         unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int BM, int BN, int WM, int WN, bool AKC, bool BKC, int NSTAGE, int MINB>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32 + 32, MINB)
+dgemm_bulk_kernel(const GemmArgs p) {
+  using C_ = Cfg<BM, BN, WM, WN, AKC, BKC, NSTAGE>;
+  constexpr int NTC = C_::NT;  // consumer threads
+  constexpr int NWC = NTC / 32;
+  constexpr int MI = C_::MI, NI = C_::NI, LDA = C_::LDA, LDB = C_::LDB;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) unsigned long long full_bar[NSTAGE];
+  __shared__ __align__(8) unsigned long long empty_bar[NSTAGE];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int tm = blockIdx.x % p.tiles_m, tn = blockIdx.x / p.tiles_m;
+  const int bm0 = tm * BM, bn0 = tn * BN;
+  const bool lower = (p.flags & PMR_GEMM_LOWER) != 0;
+  if (lower && bn0 > bm0 + BM - 1) return;
+
+  const long long b1 = blockIdx.z, b2 = blockIdx.y;
+  const double* Ab = p.A + b1 * p.a_b1 + b2 * p.a_b2;
+  const double* Bb = p.B + b1 * p.b_b1 + b2 * p.b_b2;
+  double* Cb = p.C + b1 * p.c_b1 + b2 * p.c_b2;
+
+  int kt_begin = 0;
+  int kt_end = p.K / BK;  // K % BK == 0 on this path
+  if (p.flags & PMR_GEMM_KSTART_M) kt_begin = bm0 / BK;
+  if (p.flags & PMR_GEMM_KEND_M) kt_end = min(kt_end, (min(p.K, bm0 + BM) + BK - 1) / BK);
+  const int KT = max(kt_end - kt_begin, 0);
+  const int kbase = kt_begin * BK;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], NWC);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == NWC) {
+    // ===== producer warp =====
+    // mn-contiguous operand: one copy per k row (16 rows of up to BM*8 bytes);
+    // k-contiguous operand : one 128-byte copy per m/n row of the tile.
+    const int rows_a = min(BM, p.M - bm0), rows_b = min(BN, p.N - bn0);
+    const unsigned tx_a = AKC ? (unsigned)rows_a * (BK * 8) : (unsigned)BK * (rows_a * 8);
+    const unsigned tx_b = BKC ? (unsigned)rows_b * (BK * 8) : (unsigned)BK * (rows_b * 8);
+    const double* a_src = AKC ? Ab + (long long)bm0 * p.a_ld + kbase : Ab + (long long)kbase * p.a_ld + bm0;
+    const double* b_src = BKC ? Bb + (long long)bn0 * p.b_ld + kbase : Bb + (long long)kbase * p.b_ld + bn0;
+    const long long a_step = AKC ? (long long)BK : (long long)BK * p.a_ld;
+    const long long b_step = BKC ? (long long)BK : (long long)BK * p.b_ld;
+    for (int kt = 0; kt < KT; ++kt) {
+      const int slot = kt % NSTAGE;
+      if (kt >= NSTAGE) mbar_wait(&empty_bar[slot], ((kt / NSTAGE) - 1) & 1);
+      if (lane == 0) mbar_expect_tx(&full_bar[slot], tx_a + tx_b);
+      __syncwarp();
+      double* As = smem + slot * C_::STAGE_ELEMS;
+      double* Bs = As + C_::A_ELEMS;
+      const double* ak = a_src + kt * a_step;
+      const double* bk = b_src + kt * b_step;
+      if (AKC) {
+        for (int r = lane; r < rows_a; r += 32)
+          bulk_g2s(As + r * LDA, ak + (long long)r * p.a_ld, BK * 8, &full_bar[slot]);
+      } else if (lane < BK) {
+        bulk_g2s(As + lane * LDA, ak + (long long)lane * p.a_ld, rows_a * 8, &full_bar[slot]);
+      }
+      if (BKC) {
+        for (int r = lane; r < rows_b; r += 32)
+          bulk_g2s(Bs + r * LDB, bk + (long long)r * p.b_ld, BK * 8, &full_bar[slot]);
+      } else if (lane >= 32 - BK) {
+        const int kr = lane - (32 - BK);
+        bulk_g2s(Bs + kr * LDB, bk + (long long)kr * p.b_ld, rows_b * 8, &full_bar[slot]);
+      }
+    }
+    return;
+  }
+
+  // ===== math warps =====
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp % C_::WARPS_M) * WM;
+  const int wn0 = (warp / C_::WARPS_M) * WN;
+  const double alpha = p.alpha;
+  const bool use_beta = (p.beta != 0.0);
+  const double ratio = use_beta ? p.beta / alpha : 0.0;
+  double acc[MI][NI][2];
+#pragma unroll
+  for (int mi = 0; mi < MI; ++mi) {
+    const int m = bm0 + wm0 + mi * 8 + g;
+#pragma unroll
+    for (int ni = 0; ni < NI; ++ni) {
+      acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+      if (use_beta) {
+        const int n = bn0 + wn0 + ni * 8 + 2 * t;
+        if (m < p.M && n < p.N) {
+          const bool ok1 = (n + 1 < p.N) && (!lower || n + 1 <= m);
+          const bool ok0 = (!lower || n <= m);
+          const double* c = Cb + (long long)m * p.c_sm + (long long)n * p.c_sn;
+          if (p.c_vec2 && ok0 && ok1) {
+            const double2 o = *reinterpret_cast<const double2*>(c);
+            acc[mi][ni][0] = ratio * o.x;
+            acc[mi][ni][1] = ratio * o.y;
+          } else {
+            if (ok0) acc[mi][ni][0] = ratio * c[0];
+            if (ok1) acc[mi][ni][1] = ratio * c[p.c_sn];
+          }
+        }
+      }
+    }
+  }
+
+  for (int kt = 0; kt < KT; ++kt) {
+    const int slot = kt % NSTAGE;
+    mbar_wait(&full_bar[slot], (kt / NSTAGE) & 1);
+    const double* As = smem + slot * C_::STAGE_ELEMS;
+    const double* Bs = As + C_::A_ELEMS;
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; ++kk) {
+      double a[MI], b[NI];
+#pragma unroll
+      for (int mi = 0; mi < MI; ++mi)
+        a[mi] = AKC ? As[(wm0 + mi * 8 + g) * LDA + kk * 4 + t]
+                    : As[(kk * 4 + t) * LDA + wm0 + mi * 8 + g];
+#pragma unroll
+      for (int ni = 0; ni < NI; ++ni)
+        b[ni] = BKC ? Bs[(wn0 + ni * 8 + g) * LDB + kk * 4 + t]
+                    : Bs[(kk * 4 + t) * LDB + wn0 + ni * 8 + g];
+#pragma unroll
+      for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[slot]);  // this warp is done reading the slot
+  }
+
+#pragma unroll
+  for (int mi = 0; mi < MI; ++mi) {
+    const int m = bm0 + wm0 + mi * 8 + g;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int ni = 0; ni < NI; ++ni) {
+      const int n = bn0 + wn0 + ni * 8 + 2 * t;
+      if (n >= p.N) continue;
+      const bool ok1 = (n + 1 < p.N) && (!lower || n + 1 <= m);
+      const bool ok0 = (!lower || n <= m);
+      double* c = Cb + (long long)m * p.c_sm + (long long)n * p.c_sn;
+      if (p.c_vec2 && ok0 && ok1) {
+        double2 v;
+        v.x = alpha * acc[mi][ni][0];
+        v.y = alpha * acc[mi][ni][1];
+        *reinterpret_cast<double2*>(c) = v;
+      } else {
+        if (ok0) c[0] = alpha * acc[mi][ni][0];
+        if (ok1) c[p.c_sn] = alpha * acc[mi][ni][1];
+      }
+    }
+  }
+}
+
+template <int BM, int BN, int WM, int WN, bool AKC, bool BKC, int NSTAGE, int MINB>
+int launch_bulk_cfg(GemmArgs a, int batch1, int batch2, cudaStream_t st) {
+  using C_ = Cfg<BM, BN, WM, WN, AKC, BKC, NSTAGE>;
+  auto kern = dgemm_bulk_kernel<BM, BN, WM, WN, AKC, BKC, NSTAGE, MINB>;
+  static thread_local bool configured = false;
+  if (!configured) {
+    PMR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)C_::SMEM));
+    configured = true;
+  }
+  a.tiles_m = (a.M + BM - 1) / BM;
+  a.tiles_n = (a.N + BN - 1) / BN;
+  PMR_REQUIRE((long long)a.tiles_m * a.tiles_n < (1LL << 31), "dgemm: too many tiles");
+  PMR_REQUIRE(batch1 <= 65535 && batch2 <= 65535, "dgemm: batch count above 65535");
+  dim3 grid((unsigned)((long long)a.tiles_m * a.tiles_n), (unsigned)batch2, (unsigned)batch1);
+  ProfRecord rec{};
+  if (g_prof_on) {
+    cudaEventCreate(&rec.e0);
+    cudaEventCreate(&rec.e1);
+    const bool lower = (a.flags & PMR_GEMM_LOWER) != 0;
+    const double nb = (double)batch1 * batch2;
+    const double nn = std::min(a.M, a.N);
+    const double mn = lower ? 0.5 * nn * (nn + 1.0) + ((double)a.M - nn) * nn : (double)a.M * a.N;
+    double kk = a.K;
+    if (a.flags & PMR_GEMM_KSTART_M) kk = 0.5 * a.K;
+    rec.flops = 2.0 * mn * kk * nb;
+    rec.bytes = 8.0 * nb * (mn * (a.beta != 0.0 ? 2.0 : 1.0) + (double)a.M * a.K + (double)a.N * a.K);
+    rec.cls = (BN == 128 ? 0 : (BN == 64 ? 2 : 4)) + (lower ? 1 : 0);
+    cudaEventRecord(rec.e0, st);
+  }
+  kern<<<grid, C_::NT + 32, C_::SMEM, st>>>(a);
+  if (g_prof_on) {
+    cudaEventRecord(rec.e1, st);
+    g_prof.push_back(rec);
+  }
+  PMR_CHECK_LAUNCH("dgemm_bulk_kernel");
+  return 0;
+}
+
+template <int BM, int BN, int WM, int WN, int NSTAGE, int MINB>
+int launch_bulk(const GemmArgs& a, bool akc, bool bkc, int b1, int b2, cudaStream_t st) {
+  if (akc && bkc) return launch_bulk_cfg<BM, BN, WM, WN, true, true, NSTAGE, MINB>(a, b1, b2, st);
+  if (akc && !bkc) return launch_bulk_cfg<BM, BN, WM, WN, true, false, NSTAGE, MINB>(a, b1, b2, st);
+  if (!akc && bkc) return launch_bulk_cfg<BM, BN, WM, WN, false, true, NSTAGE, MINB>(a, b1, b2, st);
+  return launch_bulk_cfg<BM, BN, WM, WN, false, false, NSTAGE, MINB>(a, b1, b2, st);
+}
+
 template <int BM, int BN, int WM, int WN, int NSTAGE, int MINB>
 int launch_layout(const GemmArgs& a, bool akc, bool bkc, int b1, int b2, cudaStream_t st) {
   if (a.a_vec2 && a.b_vec2) {
@@ -389,6 +641,21 @@ int gemm(const pmr_gemm_t& g0, cudaStream_t st) {
     // in-place A <- A * B: every CTA must own complete rows, i.e. a single column tile
     PMR_REQUIRE(g.N <= 128, "dgemm: C may alias A only for N <= 128");
     if (g.N > bn) bn = 128;
+  }
+  // TMA-bulk producer/consumer variant for mn-contiguous operands (see dgemm_bulk_kernel)
+  static const bool allow_bulk = [] { const char* e = getenv("PMR_GEMM_NO_BULK"); return !(e && atoi(e)); }();
+  // mn-contiguous operands are copied in whole rows, so their extent must be even (16-byte rows)
+  const bool a_rows_ok = akc || (g.M % 2) == 0;
+  const bool b_rows_ok = bkc || (g.N % 2) == 0;
+  // Measured on B200: 1 KiB row copies reach 35.1 TFLOP/s (99 % of cuBLAS DGEMM), but the 128-byte
+  // copies a k-contiguous operand needs (one per tile row, 192 per stage) throttle the copy engine
+  // (12-17 TFLOP/s), so those layouts stay on the cp.async kernel unless PMR_GEMM_BULK_KC=1.
+  static const bool bulk_kc = [] { const char* e = getenv("PMR_GEMM_BULK_KC"); return e && atoi(e); }();
+  if (allow_bulk && a.a_vec2 && a.b_vec2 && g.K % BK == 0 && g.K > 0 && a_rows_ok && b_rows_ok &&
+      ((!akc && !bkc) || bulk_kc) && !(g.flags & PMR_GEMM_C_ALIASES_A)) {
+    if (bn == 128) return launch_bulk<128, 128, 32, 32, 4, 1>(a, akc, bkc, g.batch1, g.batch2, st);
+    if (bn == 64) return launch_bulk<128, 64, 32, 32, 3, 2>(a, akc, bkc, g.batch1, g.batch2, st);
+    return launch_bulk<128, 32, 32, 32, 4, 2>(a, akc, bkc, g.batch1, g.batch2, st);
   }
   if (bn == 128) return launch_layout<128, 128, 32, 32, 4, 1>(a, akc, bkc, g.batch1, g.batch2, st);
   if (bn == 64) return launch_layout<128, 64, 32, 32, 3, 2>(a, akc, bkc, g.batch1, g.batch2, st);

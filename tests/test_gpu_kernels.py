@@ -71,6 +71,22 @@ def test_dgemm_unaligned_strides(pads, offset):
             assert np.abs(got - want).max() <= 1e-12
 
 
+@pytest.mark.parametrize("a_kc", [True, False])
+@pytest.mark.parametrize("b_kc", [True, False])
+@pytest.mark.parametrize("shape", [(1000, 96, 256), (130, 34, 64), (4096, 32, 512), (258, 200, 16),
+                                   (131, 77, 48)])
+def test_dgemm_bulk_copy_path(a_kc, b_kc, shape, monkeypatch):
+    """Aligned rows and K % 16 == 0 take the cp.async.bulk + mbarrier (TMA bulk) producer/consumer
+    kernel; ragged M/N tiles included (odd extents only for k-contiguous operands)."""
+    M, N, K = shape
+    if (not a_kc and M % 2) or (not b_kc and N % 2):
+        pytest.skip("odd extent of an mn-contiguous operand uses the cp.async kernel (covered elsewhere)")
+    got, want, _ = _gemm_case(M, N, K, a_kc, b_kc, alpha=-1.0, beta=1.0, seed=31)
+    assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+    got, want, _ = _gemm_case(M, N, K, a_kc, b_kc, alpha=2.0, beta=0.0, seed=32)
+    assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+
+
 def test_dgemm_lower_flag_leaves_upper_untouched():
     nv = _nv()
     got, want, C0 = _gemm_case(260, 260, 48, True, True, alpha=-1.0, beta=1.0,

@@ -180,11 +180,6 @@ def b_singlet_os_partial(ovov_xxyy):
 # --------------------------------------------------------------------------------------
 
 
-def _g(TEI, idx):
-    """Gather TEI[p,q,r,s] for index grids broadcast to (i,a,j,b)."""
-    return TEI[idx]
-
-
 def _grids(ox, vx, oy, vy):
     i = np.arange(ox)[:, None, None, None]
     a = np.arange(vx)[None, :, None, None] + ox
@@ -208,7 +203,7 @@ def a_triplet_full(E_MO, TEI, nocc):
     n = E_MO.shape[0]
     v = n - nocc
     i, a, j, b = _grids(nocc, v, nocc, v)
-    A = (-TEI[a, b, j, i] + 0 * TEI[a, i, j, b]).reshape(nocc * v, nocc * v)
+    A = (-TEI[a, b, j, i]).reshape(nocc * v, nocc * v)
     A = A + np.diag(_ediff(E_MO, nocc))
     return A
 
@@ -226,7 +221,7 @@ def b_triplet_full(TEI, nocc):
     n = TEI.shape[0]
     v = n - nocc
     i, a, j, b = _grids(nocc, v, nocc, v)
-    return -((-TEI[a, j, b, i] + 0 * TEI[a, i, b, j]).reshape(nocc * v, nocc * v))
+    return -((-TEI[a, j, b, i]).reshape(nocc * v, nocc * v))
 
 
 def a_singlet_ss_full(E_MO, TEI, nocc):
@@ -244,7 +239,7 @@ def a_singlet_os_full(TEI_xxyy, nocc_x, nocc_y):
     vx = TEI_xxyy.shape[0] - nocc_x
     vy = TEI_xxyy.shape[2] - nocc_y
     i, a, j, b = _grids(nocc_x, vx, nocc_y, vy)
-    return (TEI_xxyy[a, i, j, b] + 0.0).reshape(nocc_x * vx, nocc_y * vy)
+    return np.array(TEI_xxyy[a, i, j, b]).reshape(nocc_x * vx, nocc_y * vy)
 
 
 def b_singlet_ss_full(TEI, nocc):
@@ -260,7 +255,7 @@ def b_singlet_os_full(TEI_xxyy, nocc_x, nocc_y):
     vx = TEI_xxyy.shape[0] - nocc_x
     vy = TEI_xxyy.shape[2] - nocc_y
     i, a, j, b = _grids(nocc_x, vx, nocc_y, vy)
-    return -((TEI_xxyy[a, i, b, j] + 0.0).reshape(nocc_x * vx, nocc_y * vy))
+    return -(np.array(TEI_xxyy[a, i, b, j]).reshape(nocc_x * vx, nocc_y * vy))
 
 
 # --------------------------------------------------------------------------------------

@@ -166,21 +166,43 @@ class HalfSizeSystem:
         per = max(1, self.N * self.N * 8)
         return int(max(1, min(nf, (free * self.memory_fraction) // per)))
 
-    def solve(self, g_rows, signs, frequencies, allow_fallback=True):
+    def _kinv_distributed(self, Kfac, dinvK):
+        """K^-1 with the work split over the ranks: every rank solves K X = E_J for its own block of
+        N/world identity columns (two triangular solves against the shared factor, 0.75 u instead of
+        2 u) and the column blocks are all-gathered (N^2 * 8 bytes in total over NVLink)."""
+        from pymolresponse_b200 import distributed as pd
+
+        rank, world = pd.rank_world()
+        lo, hi = pd.shard_range(self.N, rank, world)
+        w = hi - lo
+        rhs = nv.zeros(self.N, max(w, 1))
+        if w > 0:
+            shift_diagonal(rhs, w, 1.0, offset=lo * int(rhs.stride(0)))
+            potrs(Kfac, dinvK, rhs)
+        return pd.allgather_columns(rhs[:, :w].contiguous() if w != rhs.shape[1] else rhs, self.N)
+
+    def solve(self, g_rows, signs, frequencies, allow_fallback=True, distributed=False,
+              global_frequencies=None):
         """g_rows: (ncols, N) CUDA tensor of property gradients g (first half of the supervector);
         signs[c] = -1 (real) / +1 (imaginary).  Returns xy: (nf, ncols, 2N) CUDA tensor of
         supervector solutions [X; Y] of G(w) [X;Y] = [g; s g]."""
         N = self.N
         nf, ncols = len(frequencies), int(g_rows.shape[0])
         xy = nv.zeros(nf, ncols, 2 * N)
-        if N == 0 or ncols == 0 or nf == 0:
+        if N == 0 or ncols == 0:
             return xy
         signs = [int(s) for s in signs]
         real_cols = [c for c, s in enumerate(signs) if s < 0]
         imag_cols = [c for c, s in enumerate(signs) if s > 0]
         freqs = [float(w) for w in frequencies]
+        # with frequencies dealt out to ranks, K^-1 is a collective job: every rank takes part as soon
+        # as ANY rank has a dynamic frequency, whatever its own share looks like
+        all_freqs = [float(w) for w in (global_frequencies if global_frequencies is not None else freqs)]
+        share_kinv = distributed and any(w != 0.0 for w in all_freqs)
         any_dyn = any(w != 0.0 for w in freqs)
-        need_K = any_dyn or bool(imag_cols)
+        need_K = any_dyn or bool(imag_cols) or share_kinv
+        if nf == 0 and not share_kinv:
+            return xy
         G = g_rows.t().contiguous()  # (N, ncols)
 
         Kfac = dinvK = Kinv = T = None
@@ -191,9 +213,14 @@ class HalfSizeSystem:
             self.stats["potrf"] += 1
             if int(infoK.item()) != 0:
                 bad = set(range(nf))  # K itself is not SPD: everything goes to LU
-        if not bad and any_dyn:
+        if not bad and share_kinv:
+            Kinv = self._kinv_distributed(Kfac, dinvK)
+            self.stats["potri_shared"] = self.stats.get("potri_shared", 0) + 1
+        elif not bad and any_dyn:
             Kinv = potri_lower(Kfac, dinvK)
             self.stats["potri"] += 1
+        if nf == 0:
+            return xy
         if not bad and any_dyn and imag_cols:
             T = G[:, imag_cols].contiguous()
             potrs(Kfac, dinvK, T)  # T = K^-1 g for the imaginary columns

@@ -70,13 +70,24 @@ def owner_of(item: int, world: int) -> int:
     return item % world
 
 
+def _host_staged() -> bool:
+    """gloo moves CUDA tensors only for a few collectives: stage through the host with it (tests that
+    run two ranks on one GPU); NCCL works on device memory directly."""
+    return dist().get_backend() == "gloo"
+
+
 def allreduce_blocks(tensors) -> None:
     """In-place sum over ranks of the partial MO-integral blocks."""
     if not is_initialized():
         return
     d = dist()
     for t in tensors:
-        d.all_reduce(t, op=d.ReduceOp.SUM)
+        if t.is_cuda and _host_staged():
+            h = t.cpu()
+            d.all_reduce(h, op=d.ReduceOp.SUM)
+            t.copy_(h)
+        else:
+            d.all_reduce(t, op=d.ReduceOp.SUM)
 
 
 def gather_round_robin(local_items: list, n_items: int):
@@ -95,7 +106,8 @@ def gather_round_robin(local_items: list, n_items: int):
         break
     if proto is not None:
         dev = proto.device
-    elif d.get_backend() == "nccl":
+    elif torch.cuda.is_available():
+        # a rank that owns no item still returns tensors where the others live (the device)
         dev = torch.device("cuda", torch.cuda.current_device())
     else:
         dev = torch.device("cpu")
@@ -104,18 +116,47 @@ def gather_round_robin(local_items: list, n_items: int):
         shape_t[0] = proto.dim()
         for k, s in enumerate(proto.shape):
             shape_t[1 + k] = s
-    d.all_reduce(shape_t, op=d.ReduceOp.MAX)
+    if dev.type == "cuda" and _host_staged():
+        h = shape_t.cpu()
+        d.all_reduce(h, op=d.ReduceOp.MAX)
+        shape_t.copy_(h)
+    else:
+        d.all_reduce(shape_t, op=d.ReduceOp.MAX)
     ndim = int(shape_t[0].item())
     shape = [int(shape_t[1 + k].item()) for k in range(ndim)]
     device = shape_t.device
-    buf = torch.zeros([per_rank_max] + shape, dtype=torch.float64, device=device)
+    coll_dev = torch.device("cpu") if (device.type == "cuda" and _host_staged()) else device
+    buf = torch.zeros([per_rank_max] + shape, dtype=torch.float64, device=coll_dev)
     for k, t in enumerate(local_items):
         buf[k].copy_(t)
     gathered = [torch.zeros_like(buf) for _ in range(world)]
     d.all_gather(gathered, buf)
     out = []
     for item in range(n_items):
-        out.append(gathered[owner_of(item, world)][item // world].clone())
+        out.append(gathered[owner_of(item, world)][item // world].to(device).clone())
+    return out
+
+
+def allgather_columns(X, n_cols_total: int):
+    """Every rank holds the column block ``shard_range(n_cols_total, rank, world)`` of a matrix as a
+    contiguous (rows, width) tensor; returns the full (rows, n_cols_total) matrix on every rank."""
+    rank, world = rank_world()
+    if world == 1:
+        return X
+    import torch
+
+    d = dist()
+    rows = int(X.shape[0])
+    wmax = (n_cols_total + world - 1) // world
+    coll_dev = torch.device("cpu") if (X.is_cuda and _host_staged()) else X.device
+    buf = torch.zeros(rows, wmax, dtype=X.dtype, device=coll_dev)
+    buf[:, : X.shape[1]].copy_(X)
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    d.all_gather(parts, buf)
+    out = torch.empty(rows, n_cols_total, dtype=X.dtype, device=X.device)
+    for r in range(world):
+        lo, hi = shard_range(n_cols_total, r, world)
+        out[:, lo:hi].copy_(parts[r][:, : hi - lo])
     return out
 
 

@@ -404,7 +404,7 @@ class ExactLineqSolver(LineqSolver, ABC):
             return None, signs
         return nv.torch_mod().cat(rows, dim=0).contiguous(), signs
 
-    def _solve_xy(self, hamiltonian, spin, frequencies):
+    def _solve_xy(self, hamiltonian, spin, frequencies, distributed=False, global_frequencies=None):
         """(nf, ncols, 2N) CUDA tensor of [X;Y] for the given frequencies (this rank's share)."""
         if getattr(self, "_prepared_for", None) != (hamiltonian, spin):
             self._prepare(hamiltonian, spin, want_ab=False)
@@ -413,7 +413,8 @@ class ExactLineqSolver(LineqSolver, ABC):
         if g_rows is None:
             return None
         try:
-            xy = system.solve(g_rows, signs, frequencies, allow_fallback=False)
+            xy = system.solve(g_rows, signs, frequencies, allow_fallback=False,
+                              distributed=distributed, global_frequencies=global_frequencies)
         except eng.LinAlgError:
             if not self._allow_lu_fallback:
                 raise
@@ -452,7 +453,8 @@ class ExactLineqSolver(LineqSolver, ABC):
         rank, world = pd.rank_world()
         if world > 1 and getattr(self, "distribute_frequencies", False):
             mine = pd.round_robin(len(frequencies), rank, world)
-            xy_local = self._solve_xy(hamiltonian, spin, [frequencies[i] for i in mine])
+            xy_local = self._solve_xy(hamiltonian, spin, [frequencies[i] for i in mine],
+                                      distributed=True, global_frequencies=list(frequencies))
             if xy_local is None:
                 return
             xy = pd.gather_round_robin([xy_local[k] for k in range(len(mine))], len(frequencies))

@@ -8,7 +8,6 @@ the rest is shape/IO plumbing with no arithmetic.
 
 from __future__ import annotations
 
-import ctypes as C
 from pathlib import Path
 
 import numpy as np
@@ -170,7 +169,3 @@ def read_file_3(filename):
 
 def read_file_4(filename):
     return _read_dims_then_values(filename, 4)
-
-
-def _unused():  # keep ctypes import referenced for type checkers
-    return C.c_void_p

@@ -1,0 +1,85 @@
+"""GPU: the N > 1 path with two ranks.  Both ranks use cuda:0 and exchange through gloo (host
+staged), so it runs on the single-GPU box too; on multi-GPU boxes bench.py exercises NCCL.
+Covers: nu-sharded AO2MO + block all-reduce, frequencies dealt to ranks, the shared K^-1
+(column blocks solved per rank + all-gather), a rank without any frequency, gather of response
+vectors -- compared with the oracle."""
+
+import os
+import socket
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+REPO = Path(__file__).resolve().parent.parent
+
+_WORKER = r"""
+import sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[3])
+from oracle import pmr_oracle as orc
+from pymolresponse_b200 import cphf, distributed as pd, operators, solvers, synthetic
+from pymolresponse_b200.ao2mo import AO2MO
+from pymolresponse_b200.core import Hamiltonian, Spin
+
+rank, world = int(sys.argv[1]), 2
+torch.cuda.set_device(0)
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=rank, world_size=world)
+n, o = 30, 4
+case = synthetic.rhf_case(n, o)
+lo, hi = pd.shard_range(n, rank, world)
+a = AO2MO(case["C"], case["occupations"], I=np.ascontiguousarray(case["I"][:, lo:hi]),
+          nu_range=(lo, hi), device_results=True)
+a.perform_rhf_partial()
+pd.allreduce_blocks(a.tei_mo)
+tei_ref = orc.ao2mo_rhf_partial(case["I"], case["C"], o)
+for got, ref in zip(a.tei_mo, tei_ref):
+    assert np.abs(got.cpu().numpy() - ref).max() <= 1e-12 * np.abs(ref).max()
+Or = synthetic.operator_integrals(n, 3, False)
+Oi = synthetic.operator_integrals(n, 2, True)
+for freqs in ([0.0, 0.1, 0.2], [0.3], [0.0]):
+    solver = solvers.ExactInv(case["C"], case["E"], case["occupations"])
+    solver.distribute_frequencies = True
+    solver.tei_mo = a.tei_mo
+    driver = cphf.CPHF(solver)
+    ops = [operators.Operator(label="dipole", is_imaginary=False, ao_integrals=Or),
+           operators.Operator(label="angmom", is_imaginary=True, ao_integrals=Oi)]
+    for op in ops:
+        driver.add_operator(op)
+    driver.set_frequencies(freqs)
+    driver.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet, program=None, program_obj=None)
+    ref = orc.run_cphf(case["C"], case["E"], case["occupations"], tei_ref, "partial",
+                       [{"ao_integrals": Or, "is_imaginary": False}, {"ao_integrals": Oi, "is_imaginary": True}],
+                       freqs)
+    for f in range(len(freqs)):
+        assert np.abs(driver.results[f] - ref["results"][f]).max() <= 1e-9, (freqs, f)
+        for k in range(2):
+            assert np.abs(ops[k].rspvecs_alph[f] - ref["rspvecs_alph"][k][f]).max() <= 1e-9
+    if any(w != 0.0 for w in freqs):
+        assert solver.solve_stats.get("potri_shared", 0) == 1 and solver.solve_stats["potri"] == 0
+pd.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_two_ranks_sharded_ao2mo_and_distributed_frequencies(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), str(port), str(REPO)],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+             for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    report = "\n".join(f"--- rank {r} (rc={p.returncode}) ---\n{o[-3000:]}" for r, (p, o) in enumerate(zip(procs, outs)))
+    for r, p in enumerate(procs):
+        assert p.returncode == 0, report
+        assert f"ok {r}" in outs[r]

@@ -626,3 +626,59 @@ def test_larger_rhf_size_independent_properties():
     xy_lu = nv.to_host(sysm.solve_lu(g_rows, [-1, -1, -1], 0.2))
     assert np.abs(xy_lu - op.rspvecs_alph[1][:, :, 0]).max() <= 1e-10
     del eng
+
+
+# ------------------------------------------------------------------------- BASELINE configs 2 and 4
+def test_config2_shaped_cholesky_sweep():
+    """BASELINE config 2 needs pyscf for H2O/aug-cc-pVTZ integrals (absent); same shape with the
+    synthetic generator: nbasis=92, nocc=5, 8 frequencies, ExactInvCholesky, from AO integrals."""
+    from pymolresponse_b200 import cphf, operators, solvers, synthetic
+    from pymolresponse_b200.core import Hamiltonian, Program, Spin
+
+    n, o = 92, 5
+    case = synthetic.rhf_case(n, o)
+    Or = synthetic.operator_integrals(n, 3, False)
+    freqs = [float(w) for w in np.linspace(0.0, 0.35, 8)]
+    tei = orc.ao2mo_rhf_partial(case["I"], case["C"], o)
+    ref = orc.run_cphf(case["C"], case["E"], case["occupations"], tei, "partial",
+                       [{"ao_integrals": Or, "is_imaginary": False}], freqs, cholesky=True)
+    solver = solvers.ExactInvCholesky(case["C"], case["E"], case["occupations"])
+    driver = cphf.CPHF(solver)
+    op = operators.Operator(label="dipole", is_imaginary=False, ao_integrals=Or)
+    driver.add_operator(op)
+    driver.set_frequencies(freqs)
+    driver.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet, program=Program.Arrays,
+               program_obj=case["I"])
+    for k in range(2):
+        assert np.abs(solver.tei_mo[k] - tei[k]).max() <= 1e-12 * np.abs(tei[k]).max()
+    for f in range(8):
+        np.testing.assert_allclose(driver.results[f], ref["results"][f], rtol=0, atol=1e-9)
+        assert np.abs(op.rspvecs_alph[f] - ref["rspvecs_alph"][0][f]).max() <= 1e-9
+        np.testing.assert_allclose(driver.uncoupled_results[f], ref["uncoupled_results"][f], rtol=0,
+                                   atol=1e-11)
+
+
+def test_config4_shaped_uhf_static():
+    """BASELINE config 4 shape at 1/8 scale: UHF nbasis=48 (6 alpha, 5 beta), odd beta dimensions
+    (8-byte-aligned copy paths, generic assembly kernel), static polarizability, joint Cholesky."""
+    from pymolresponse_b200 import cphf, operators, solvers, synthetic
+    from pymolresponse_b200.core import Hamiltonian, Program, Spin
+
+    n, na, nb = 48, 6, 5
+    case = synthetic.uhf_case(n, na, nb)
+    Or = synthetic.operator_integrals(n, 3, False)
+    tei = orc.ao2mo_uhf_partial(case["I"], case["C"], case["occupations"])
+    ref = orc.run_cphf(case["C"], case["E"], case["occupations"], tei, "partial",
+                       [{"ao_integrals": Or, "is_imaginary": False}], [0.0])
+    for cls in (solvers.ExactInv, solvers.ExactInvCholesky):
+        solver = cls(case["C"], case["E"], case["occupations"])
+        driver = cphf.CPHF(solver)
+        op = operators.Operator(label="dipole", is_imaginary=False, ao_integrals=Or)
+        driver.add_operator(op)
+        driver.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet, program=Program.Arrays,
+                   program_obj=case["I"])
+        for k in range(6):
+            assert np.abs(solver.tei_mo[k] - tei[k]).max() <= 1e-12 * np.abs(tei[k]).max(), k
+        np.testing.assert_allclose(driver.results[0], ref["results"][0], rtol=0, atol=1e-9)
+        assert np.abs(op.rspvecs_alph[0] - ref["rspvecs_alph"][0][0]).max() <= 1e-9
+        assert np.abs(op.rspvecs_beta[0] - ref["rspvecs_beta"][0][0]).max() <= 1e-9

@@ -202,11 +202,9 @@ def one_step(w, inp, I, device_resident: bool, world: int):
     from pymolresponse_b200.properties.magnetic import Magnetizability
 
     nu_range = inp["nu_range"] if world > 1 else None
-    a = AO2MO(inp["C"], inp["occ"], I=I, device_results=True, nu_range=nu_range)
+    a = AO2MO(inp["C"], inp["occ"], I=I, device_results=True, nu_range=nu_range, reduce=world > 1)
     a.perform_rhf_partial()
     tei = a.tei_mo
-    if world > 1:
-        pd.allreduce_blocks(tei)
     gen = integrals.IntegralsArrays({"dipole": inp["O_real"], "angmom_common_gauge": inp["O_imag"]})
     out = {}
     if w["magnetizability"]:

@@ -101,10 +101,20 @@ typedef struct {
 
 long long pmr_ao2mo_partial_workspace(int n, int nu_cnt, int o1, int v1, int n_ket,
                                       const pmr_ao2mo_ket_t* kets, int want_oovv, int nu_block);
+/* accumulate: bit 0 = add into ovov/oovv; bit 1 = stop the (ij|ab) chain after its two occupied
+ * quarters and return the half-transformed (i j|la si) in `oovv` (then o1*o1*n*n doubles): ranks
+ * reduce-scatter that over i and finish only their own rows with pmr_ao2mo_oovv_tail. */
 int pmr_ao2mo_partial(const double* I_slab, int n, int nu_lo, int nu_cnt, const double* Co1,
                       const double* Cv1, int ldc1, int o1, int v1, int n_ket,
                       const pmr_ao2mo_ket_t* kets, double* oovv, int accumulate, int nu_block,
                       double* workspace, long long workspace_doubles, void* stream);
+
+/* Last two (virtual) quarters of (ij|ab) for `rows` leading occupied indices:
+ * Y is (rows, o1, n, n), oovv is (rows, o1, v1, v1); workspace from the _workspace function. */
+long long pmr_ao2mo_oovv_tail_workspace(int n, int rows, int o1, int v1);
+int pmr_ao2mo_oovv_tail(const double* Y, int n, const double* Cv1, int ldc1, int rows, int o1,
+                        int v1, double* oovv, int accumulate, double* workspace,
+                        long long workspace_doubles, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Orbital-Hessian block assembly (explicit_equations_partial.py:8-214,

@@ -89,6 +89,9 @@ SYMBOLS = {
     "pmr_ao2mo_partial": (C.c_int, [c_dp, C.c_int, C.c_int, C.c_int, c_dp, c_dp, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.POINTER(KetDesc), c_dp, C.c_int, C.c_int,
                                     c_dp, c_ll, c_dp]),
+    "pmr_ao2mo_oovv_tail_workspace": (c_ll, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "pmr_ao2mo_oovv_tail": (C.c_int, [c_dp, C.c_int, c_dp, C.c_int, C.c_int, C.c_int, C.c_int, c_dp,
+                                      C.c_int, c_dp, c_ll, c_dp]),
     "pmr_assemble": (C.c_int, [C.POINTER(AssembleDesc), c_dp]),
     "pmr_energy_differences": (C.c_int, [c_dp, C.c_int, c_dp, C.c_int, c_dp, c_dp]),
     "pmr_potrf_dinv_doubles": (c_ll, [C.c_int]),

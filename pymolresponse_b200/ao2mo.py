@@ -12,8 +12,9 @@ same length, order, shapes and C-order layout.  Differences, all additive:
 * ``I`` may be a NumPy array or a CUDA tensor; with ``device_results=True`` the MO blocks stay in
   HBM as torch tensors (what the solvers consume directly).
 * ``nu_range=(lo, hi)`` marks ``I`` as the slab ``I[:, lo:hi, :, :]`` of a tensor sharded over the
-  second index of the first AO pair; the blocks are then partial sums that
-  ``pymolresponse_b200.distributed.allreduce_blocks`` completes across ranks.
+  second index of the first AO pair; with ``reduce=True`` the blocks are completed across the
+  ``torch.distributed`` ranks (all-reduce of (ia|jb); reduce-scatter / finish / all-gather for
+  (ij|ab)), otherwise they are this slab's partial sums.
 """
 
 from __future__ import annotations
@@ -44,12 +45,19 @@ def _transform_dev(I, C1, C2, C3, C4):
     return out
 
 
-def partial_blocks_dev(I_slab, nu_lo, Cbra, nocc_bra, kets, want_oovv, nu_block=0):
+def partial_blocks_dev(I_slab, nu_lo, Cbra, nocc_bra, kets, want_oovv, nu_block=0, reduce=False):
     """Occupied-first partial transform for one bra spin.
 
     I_slab: (n, nu_cnt, n, n) CUDA tensor; Cbra: (n, norb) CUDA tensor; kets: list of
     (Cket (n,norb), nocc_ket).  Returns ([ovov_k ...], oovv or None) as CUDA tensors.
+
+    ``reduce=True`` (ranks hold different nu slabs): the (ia|jb) partial sums are all-reduced; the
+    (ij|ab) chain stops after its two occupied quarters, the half-transformed (ij|la si) is
+    reduce-scattered over i, every rank finishes the two virtual quarters for its own i only and the
+    rows are all-gathered -- the o^2 n^2 (v + v^2/n) tail flops are not repeated on every rank.
     """
+    from pymolresponse_b200 import distributed as pd
+
     L = nv.lib()
     n, nu_cnt = int(I_slab.shape[0]), int(I_slab.shape[1])
     norb = int(Cbra.shape[1])
@@ -68,14 +76,34 @@ def partial_blocks_dev(I_slab, nu_lo, Cbra, nocc_bra, kets, want_oovv, nu_block=
         kd[k].ldc2 = int(Ck.stride(0))
         kd[k].o2, kd[k].v2 = o2, v2
         kd[k].ovov = nv.ptr(out)
-    oovv = nv.zeros(o1, o1, v1, v1) if want_oovv else None
+    split_tail = bool(reduce and want_oovv and pd.rank_world()[1] > 1)
+    if split_tail:
+        oovv = nv.zeros(o1, o1, n, n)       # receives the half-transformed (i j|la si)
+    else:
+        oovv = nv.zeros(o1, o1, v1, v1) if want_oovv else None
     ws_n = int(L.pmr_ao2mo_partial_workspace(n, nu_cnt, o1, v1, len(kets), kd, int(want_oovv),
                                              int(nu_block)))
     ws = nv.empty(ws_n)
     nv.check(L.pmr_ao2mo_partial(
         nv.ptr(I_slab), n, int(nu_lo), nu_cnt, nv.ptr(Cbra), nv.ptr(Cbra, o1), ldc1, o1, v1,
-        len(kets), kd, nv.ptr(oovv) if want_oovv else C.c_void_p(0), 0, int(nu_block),
-        nv.ptr(ws), ws_n, nv.stream_ptr()))
+        len(kets), kd, nv.ptr(oovv) if want_oovv else C.c_void_p(0), 2 if split_tail else 0,
+        int(nu_block), nv.ptr(ws), ws_n, nv.stream_ptr()))
+    del ws
+    if reduce:
+        pd.allreduce_blocks(outs)
+        if split_tail:
+            Y_loc = pd.reduce_scatter_rows(oovv, o1)            # (rows, o1, n, n), summed over ranks
+            del oovv
+            rows = int(Y_loc.shape[0])
+            loc = nv.zeros(rows, o1, v1, v1)
+            if rows > 0 and v1 > 0:
+                tw = int(L.pmr_ao2mo_oovv_tail_workspace(n, rows, o1, v1))
+                tws = nv.empty(tw)
+                nv.check(L.pmr_ao2mo_oovv_tail(nv.ptr(Y_loc), n, nv.ptr(Cbra, o1), ldc1, rows, o1, v1,
+                                               nv.ptr(loc), 0, nv.ptr(tws), tw, nv.stream_ptr()))
+            oovv = pd.allgather_rows(loc, o1)
+        elif want_oovv:
+            pd.allreduce_blocks([oovv])
     return outs, oovv
 
 
@@ -83,7 +111,8 @@ class AO2MO:
     """Interface for AO-to-MO transformations of two-electron integrals (reference ao2mo.py:15-78)."""
 
     def __init__(self, C, occupations, I=None, *, device_results: bool = False,  # noqa: E741
-                 nu_range: tuple[int, int] | None = None, nu_block: int = 0) -> None:
+                 nu_range: tuple[int, int] | None = None, nu_block: int = 0,
+                 reduce: bool = False) -> None:
         self.C = fix_mocoeffs_shape(C) if not nv.is_device_array(C) else (C if C.dim() == 3 else C[None])
         self.occupations = occupations
         self.I = I
@@ -92,6 +121,7 @@ class AO2MO:
         self.device_results = device_results
         self.nu_range = nu_range
         self.nu_block = nu_block
+        self.reduce = reduce  # complete the blocks over torch.distributed ranks (nu-sharded I)
 
     # ------------------------------------------------------------------ helpers
     def _out(self, tensors):
@@ -139,7 +169,7 @@ class AO2MO:
         I, lo = self._slab()
         Ca = self._C_dev(0)
         (ovov,), oovv = partial_blocks_dev(I, lo, Ca, self.nocc_alph, [(Ca, self.nocc_alph)], True,
-                                           self.nu_block)
+                                           self.nu_block, self.reduce)
         self.tei_mo = self._out((ovov, oovv))
 
     def perform_uhf_full(self) -> None:
@@ -161,9 +191,9 @@ class AO2MO:
         Ca, Cb = self._C_dev(0), self._C_dev(1)
         na, nb = self.nocc_alph, self.nocc_beta
         (aaaa, aabb), oovv_a = partial_blocks_dev(I, lo, Ca, na, [(Ca, na), (Cb, nb)], True,
-                                                  self.nu_block)
+                                                  self.nu_block, self.reduce)
         (bbaa, bbbb), oovv_b = partial_blocks_dev(I, lo, Cb, nb, [(Ca, na), (Cb, nb)], True,
-                                                  self.nu_block)
+                                                  self.nu_block, self.reduce)
         self.tei_mo = self._out((aaaa, aabb, bbaa, bbbb, oovv_a, oovv_b))
 
 

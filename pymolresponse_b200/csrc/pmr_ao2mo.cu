@@ -104,6 +104,7 @@ extern "C" int pmr_ao2mo_partial(const double* I_slab, int n, int nu_lo, int nu_
   if (o1 == 0 || nu_cnt == 0) return 0;
   PMR_REQUIRE(I_slab && Co1 && Cv1 && workspace, "ao2mo_partial: null pointer");
   const int want_oovv = oovv != nullptr;
+  const bool half_only = (accumulate & 2) != 0;
   PMR_REQUIRE(workspace_doubles >=
                   pmr_ao2mo_partial_workspace(n, nu_cnt, o1, v1, n_ket, kets, want_oovv, nu_block),
               "ao2mo_partial: workspace too small");
@@ -127,7 +128,7 @@ extern "C" int pmr_ao2mo_partial(const double* I_slab, int n, int nu_lo, int nu_
   for (int nu0 = 0; nu0 < nu_cnt; nu0 += nb) {
     const int cnt = std::min(nb, nu_cnt - nu0);
     const long long cn2 = (long long)cnt * n2;
-    const double beta_blk = (accumulate || nu0 > 0) ? 1.0 : 0.0;
+    const double beta_blk = ((accumulate & 1) || nu0 > 0) ? 1.0 : 0.0;
     // first quarter, shared: H1[i, nu', la si] = sum_mu Co1[mu,i] I[mu, nu0+nu', la si]
     pmr_gemm_t h = make_gemm(o1, (int)cn2, n, 1.0, Co1, 1, ldc1, I_slab + (long long)nu0 * n2,
                              slab_ld, 1, 0.0, H1, cn2, 1);
@@ -163,19 +164,43 @@ extern "C" int pmr_ao2mo_partial(const double* I_slab, int n, int nu_lo, int nu_
       PMR_TRY(gemm(y, st));
     }
   }
-  if (want_oovv && v1 > 0) {
-    // Y2[i,j,la,b] = sum_si Y[i,j,la,si] Cv1[si,b]
-    const long long rows = (long long)o1 * o1 * n;
-    PMR_REQUIRE(rows < (1LL << 31), "ao2mo_partial: too many rows");
-    pmr_gemm_t g3 = make_gemm((int)rows, v1, n, 1.0, Y, n, 1, Cv1, ldc1, 1, 0.0, Y2, v1, 1);
-    PMR_TRY(gemm(g3, st));
-    // oovv[i,j,a,b] (+)= sum_la Cv1[la,a] Y2[i,j,la,b]
-    pmr_gemm_t g4 = make_gemm(v1, v1, n, 1.0, Cv1, 1, ldc1, Y2, v1, 1, accumulate ? 1.0 : 0.0, oovv,
-                              v1, 1);
-    g4.batch1 = o1; g4.batch2 = o1;
-    g4.b_b1 = (long long)o1 * n * v1; g4.b_b2 = (long long)n * v1;
-    g4.c_b1 = (long long)o1 * v1 * v1; g4.c_b2 = (long long)v1 * v1;
-    PMR_TRY(gemm(g4, st));
+  if (want_oovv && half_only) {
+    // hand the half-transformed (i j|la si) back: the caller reduces it over ranks and finishes
+    // only its own rows with pmr_ao2mo_oovv_tail
+    PMR_CHECK_CUDA(cudaMemcpyAsync(oovv, Y, sizeof(double) * (size_t)o1 * o1 * n2,
+                                   cudaMemcpyDeviceToDevice, st));
+  } else if (want_oovv && v1 > 0) {
+    PMR_TRY(pmr_ao2mo_oovv_tail(Y, n, Cv1, ldc1, o1, o1, v1, oovv, (accumulate & 1), Y2,
+                                (long long)o1 * o1 * n * v1, stream));
   }
+  return 0;
+}
+
+extern "C" long long pmr_ao2mo_oovv_tail_workspace(int n, int rows, int o1, int v1) {
+  return (long long)rows * o1 * n * v1;
+}
+
+extern "C" int pmr_ao2mo_oovv_tail(const double* Y, int n, const double* Cv1, int ldc1, int rows,
+                                   int o1, int v1, double* oovv, int accumulate, double* workspace,
+                                   long long workspace_doubles, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  PMR_REQUIRE(n >= 1 && rows >= 0 && o1 >= 0 && v1 >= 0, "ao2mo_oovv_tail: bad dims");
+  if (rows == 0 || o1 == 0 || v1 == 0) return 0;
+  PMR_REQUIRE(Y && Cv1 && oovv && workspace, "ao2mo_oovv_tail: null pointer");
+  PMR_REQUIRE(workspace_doubles >= pmr_ao2mo_oovv_tail_workspace(n, rows, o1, v1),
+              "ao2mo_oovv_tail: workspace too small");
+  double* Y2 = workspace;
+  // Y2[i,j,la,b] = sum_si Y[i,j,la,si] Cv1[si,b]
+  const long long m = (long long)rows * o1 * n;
+  PMR_REQUIRE(m < (1LL << 31), "ao2mo_oovv_tail: too many rows");
+  pmr_gemm_t g3 = make_gemm((int)m, v1, n, 1.0, Y, n, 1, Cv1, ldc1, 1, 0.0, Y2, v1, 1);
+  PMR_TRY(gemm(g3, st));
+  // oovv[i,j,a,b] (+)= sum_la Cv1[la,a] Y2[i,j,la,b]
+  pmr_gemm_t g4 = make_gemm(v1, v1, n, 1.0, Cv1, 1, ldc1, Y2, v1, 1, accumulate ? 1.0 : 0.0, oovv,
+                            v1, 1);
+  g4.batch1 = rows; g4.batch2 = o1;
+  g4.b_b1 = (long long)o1 * n * v1; g4.b_b2 = (long long)n * v1;
+  g4.c_b1 = (long long)o1 * v1 * v1; g4.c_b2 = (long long)v1 * v1;
+  PMR_TRY(gemm(g4, st));
   return 0;
 }

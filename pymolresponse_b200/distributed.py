@@ -137,6 +137,49 @@ def gather_round_robin(local_items: list, n_items: int):
     return out
 
 
+def reduce_scatter_rows(T, n_rows_total: int):
+    """Sum T (n_rows_total, ...) over ranks and return this rank's row block
+    ``shard_range(n_rows_total, rank, world)`` of the sum."""
+    rank, world = rank_world()
+    if world == 1:
+        return T
+    import torch
+
+    d = dist()
+    lo, hi = shard_range(n_rows_total, rank, world)
+    if T.is_cuda and not _host_staged() and n_rows_total % world == 0:
+        out = torch.empty((hi - lo,) + tuple(T.shape[1:]), dtype=T.dtype, device=T.device)
+        d.reduce_scatter_tensor(out, T.contiguous(), op=d.ReduceOp.SUM)
+        return out
+    allreduce_blocks([T])
+    return T[lo:hi].contiguous()
+
+
+def allgather_rows(X, n_rows_total: int):
+    """Inverse of the row sharding: every rank contributes its row block, all get the whole."""
+    rank, world = rank_world()
+    if world == 1:
+        return X
+    import torch
+
+    d = dist()
+    rmax = (n_rows_total + world - 1) // world
+    coll_dev = torch.device("cpu") if (X.is_cuda and _host_staged()) else X.device
+    buf = torch.zeros((rmax,) + tuple(X.shape[1:]), dtype=X.dtype, device=coll_dev)
+    buf[: X.shape[0]].copy_(X)
+    if coll_dev == X.device and n_rows_total % world == 0:
+        out = torch.empty((n_rows_total,) + tuple(X.shape[1:]), dtype=X.dtype, device=X.device)
+        d.all_gather_into_tensor(out, buf)
+        return out
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    d.all_gather(parts, buf)
+    out = torch.empty((n_rows_total,) + tuple(X.shape[1:]), dtype=X.dtype, device=X.device)
+    for r in range(world):
+        lo, hi = shard_range(n_rows_total, r, world)
+        out[lo:hi].copy_(parts[r][: hi - lo])
+    return out
+
+
 def allgather_columns(X, n_cols_total: int):
     """Every rank holds the column block ``shard_range(n_cols_total, rank, world)`` of a matrix as a
     contiguous (rows, width) tensor; returns the full (rows, n_cols_total) matrix on every rank."""

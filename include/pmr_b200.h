@@ -62,6 +62,10 @@ typedef struct {
   int batch1, batch2;                           /* >= 1 each */
   long long a_b1, a_b2, b_b1, b_b2, c_b1, c_b2; /* element strides per batch index */
   int flags;
+  /* optional second copy of the result with its own strides (e.g. transposed); NULL = none.
+   * Honoured by the cp.async kernels (always used with PMR_GEMM_C_ALIASES_A). */
+  double* C2;
+  long long c2_sm, c2_sn, c2_b1, c2_b2;
 } pmr_gemm_t;
 
 int pmr_dgemm(const pmr_gemm_t* g, void* stream);
@@ -163,6 +167,9 @@ long long pmr_potrf_dinv_doubles(int N);
  * (look-ahead).  Switch it off to get serialised, individually timeable kernels (bench.py's
  * roofline pass does); results are identical either way.  Per calling thread; default on. */
 void pmr_set_lookahead(int on);
+/* pmr_potrf keeps a transposed copy of the current 512-column panel so its rank-k updates run on the
+ * TMA-bulk GEMM; switch off to use the in-place row-major panel with the cp.async GEMM (A/B test). */
+void pmr_set_transposed_panels(int on);
 int pmr_potrf(double* A, int N, long long lda, int batch, long long stride_a, double* dinv,
               int* info /* device, batch ints */, void* stream);
 /* Solve A X = B in place of B (B is N x nrhs, row stride ldb); `work` has N*nrhs doubles/batch. */

@@ -40,6 +40,7 @@ class GemmDesc(C.Structure):
         ("a_b1", c_ll), ("a_b2", c_ll), ("b_b1", c_ll), ("b_b2", c_ll),
         ("c_b1", c_ll), ("c_b2", c_ll),
         ("flags", C.c_int),
+        ("C2", c_dp), ("c2_sm", c_ll), ("c2_sn", c_ll), ("c2_b1", c_ll), ("c2_b2", c_ll),
     ]
 
 
@@ -96,6 +97,7 @@ SYMBOLS = {
     "pmr_energy_differences": (C.c_int, [c_dp, C.c_int, c_dp, C.c_int, c_dp, c_dp]),
     "pmr_potrf_dinv_doubles": (c_ll, [C.c_int]),
     "pmr_set_lookahead": (None, [C.c_int]),
+    "pmr_set_transposed_panels": (None, [C.c_int]),
     "pmr_potrf": (C.c_int, [c_dp, C.c_int, c_ll, C.c_int, c_ll, c_dp, c_dp, c_dp]),
     "pmr_potrs": (C.c_int, [c_dp, C.c_int, c_ll, C.c_int, c_ll, c_dp, c_dp, C.c_int, c_ll, c_ll,
                             c_dp, c_dp]),

@@ -21,6 +21,7 @@ namespace {
 constexpr int NB = 128;
 constexpr int NBLD = NB + 1;
 static thread_local bool g_lookahead = true;
+static thread_local bool g_transposed_panels = false;
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -341,6 +342,7 @@ __global__ void lu_diag_solve_kernel(const double* __restrict__ LU, long long ld
 using namespace pmr;
 
 extern "C" void pmr_set_lookahead(int on) { g_lookahead = on != 0; }
+extern "C" void pmr_set_transposed_panels(int on) { g_transposed_panels = on != 0; }
 
 extern "C" long long pmr_potrf_dinv_doubles(int N) {
   const long long nblk = (N + NB - 1) / NB;
@@ -388,14 +390,57 @@ extern "C" int pmr_potrf(double* A, int N, long long lda, int batch, long long s
   };
   const bool lookahead = g_lookahead && N > 2 * NBO;
   cudaStream_t sp = lookahead ? sa : st;  // stream of the panel work
+
+  // EXPERIMENT, off by default (pmr_set_transposed_panels): transposed panel store
+  // PT[J%2][k][row] (k < 512) written by the panel solve next to the in-place result, so that the
+  // rank-128 / rank-512 updates read both operands contiguous along m/n and run on the TMA-bulk +
+  // mbarrier GEMM.  Measured on B200 it does not pay: at K = 512 the per-tile costs dominate and the
+  // bulk kernel reaches 29.5 TFLOP/s on these lower-triangular updates against 31 for the
+  // k-contiguous cp.async kernel (the bulk kernel's 35 TFLOP/s needs long k loops).
+  const long long ldp = ((long long)N + 15) & ~15LL;
+  const long long pt_one = (long long)NBO * ldp;   // one buffer of one matrix
+  const long long pt_mat = 2 * pt_one;             // double-buffered (look-ahead)
+  double* PT = nullptr;
+  const bool use_pt = g_transposed_panels && N > NB;
+  if (use_pt) {
+    static thread_local bool pool_kept = false;
+    if (!pool_kept) {  // keep freed blocks in the stream-ordered pool instead of returning them to the OS
+      int dev = 0;
+      cudaMemPool_t pool;
+      unsigned long long keep = ~0ULL;
+      PMR_CHECK_CUDA(cudaGetDevice(&dev));
+      PMR_CHECK_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+      PMR_CHECK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+      pool_kept = true;
+    }
+    PMR_CHECK_CUDA(cudaMallocAsync(&PT, sizeof(double) * pt_mat * batch, st));
+  }
   if (lookahead) PMR_CHECK_CUDA(cudaStreamWaitEvent(sa, new_event(st), 0));
   cudaEvent_t u2_done_prev = nullptr;  // U2 of block J-1 finished (on st)
 
-  auto batched = [&](pmr_gemm_t& t) {
-    t.batch1 = batch; t.a_b1 = stride_a; t.b_b1 = stride_a; t.c_b1 = stride_a;
+  // C[r0.., c0..] (lower) -= P[r0.., :] P[c0.., :]^T with P = columns [j0, j0+kw) of L, K = kw,
+  // starting at panel column offset koff (rank-128 updates use a 128-wide slice of the block)
+  auto syrk = [&](int jblk, int j0, int koff, int kw, int r0, int nrows, int c0, int ncols,
+                  cudaStream_t s) -> int {
+    double* Cp = A + (long long)r0 * lda + c0;
+    pmr_gemm_t t;
+    if (use_pt) {
+      const double* pt = PT + (long long)(jblk & 1) * pt_one + (long long)koff * ldp;
+      t = make_gemm(nrows, ncols, kw, -1.0, pt + r0, 1, ldp, pt + c0, ldp, 1, 1.0, Cp, lda, 1);
+      t.a_b1 = pt_mat; t.b_b1 = pt_mat;
+    } else {
+      const double* Pr = A + (long long)r0 * lda + j0 + koff;
+      const double* Pc = A + (long long)c0 * lda + j0 + koff;
+      t = make_gemm(nrows, ncols, kw, -1.0, Pr, lda, 1, Pc, 1, lda, 1.0, Cp, lda, 1);
+      t.a_b1 = stride_a; t.b_b1 = stride_a;
+    }
+    t.batch1 = batch; t.c_b1 = stride_a;
+    t.flags = PMR_GEMM_LOWER;
+    return gemm(t, s);
   };
 
-  for (int j0 = 0; j0 < N; j0 += NBO) {
+  int jblk = 0;
+  for (int j0 = 0; j0 < N; j0 += NBO, ++jblk) {
     const int jend = std::min(N, j0 + NBO);
     // ---- panel work of this outer block (stream sp)
     for (int k0 = j0; k0 < jend; k0 += NB) {
@@ -412,55 +457,37 @@ extern "C" int pmr_potrf(double* A, int N, long long lda, int batch, long long s
         pmr_gemm_t g = make_gemm(rest, jb, jb, 1.0, A21, lda, 1, dk, 1, NB, 0.0, A21, lda, 1);
         g.batch1 = batch; g.a_b1 = stride_a; g.b_b1 = dstride; g.c_b1 = stride_a;
         g.flags = PMR_GEMM_C_ALIASES_A;
+        if (use_pt) {
+          g.C2 = PT + (long long)(jblk & 1) * pt_one + (long long)(k0 - j0) * ldp + (k0 + jb);
+          g.c2_sm = 1; g.c2_sn = ldp; g.c2_b1 = pt_mat;
+        }
         PMR_TRY(gemm(g, sp));
         const int ncols = jend - (k0 + jb);  // columns of the outer block still to be updated
-        if (ncols > 0) {
-          double* A22 = A + (long long)(k0 + jb) * lda + (k0 + jb);
-          pmr_gemm_t t = make_gemm(rest, ncols, jb, -1.0, A21, lda, 1, A21, 1, lda, 1.0, A22, lda, 1);
-          batched(t);
-          t.flags = PMR_GEMM_LOWER;
-          PMR_TRY(gemm(t, sp));
-        }
+        if (ncols > 0)
+          PMR_TRY(syrk(jblk, j0, k0 - j0, jb, k0 + jb, rest, k0 + jb, ncols, sp));
       }
     }
     const int rest = N - jend;
     if (rest <= 0) break;
     const int kw = jend - j0;
-    double* P = A + (long long)jend * lda + j0;  // (rest x kw) panel of L
     if (!lookahead) {
-      double* A22 = A + (long long)jend * lda + jend;
-      pmr_gemm_t t = make_gemm(rest, rest, kw, -1.0, P, lda, 1, P, 1, lda, 1.0, A22, lda, 1);
-      batched(t);
-      t.flags = PMR_GEMM_LOWER;
-      PMR_TRY(gemm(t, st));
+      PMR_TRY(syrk(jblk, j0, 0, kw, jend, rest, jend, rest, st));
       continue;
     }
     const int jnext = std::min(N, jend + NBO);
     const int w1 = jnext - jend;  // width of the next outer block
     cudaEvent_t panel_done = new_event(sa);
-    // U1 (sa): A[jend:, jend:jnext] -= P P[0:w1]^T, after U2 of the previous block (same region)
+    // U1 (sa): columns of the next outer block, after U2 of the previous block (same region)
     if (u2_done_prev) PMR_CHECK_CUDA(cudaStreamWaitEvent(sa, u2_done_prev, 0));
-    {
-      double* A22 = A + (long long)jend * lda + jend;
-      pmr_gemm_t t = make_gemm(rest, w1, kw, -1.0, P, lda, 1, P, 1, lda, 1.0, A22, lda, 1);
-      batched(t);
-      t.flags = PMR_GEMM_LOWER;
-      PMR_TRY(gemm(t, sa));
-    }
-    // U2 (st): A[jnext:, jnext:] -= P[w1:] P[w1:]^T, after the panel of this block
+    PMR_TRY(syrk(jblk, j0, 0, kw, jend, rest, jend, w1, sa));
+    // U2 (st): everything to the right of it, after the panel of this block
     const int rest2 = N - jnext;
     PMR_CHECK_CUDA(cudaStreamWaitEvent(st, panel_done, 0));
-    if (rest2 > 0) {
-      double* P2 = P + (long long)w1 * lda;
-      double* A33 = A + (long long)jnext * lda + jnext;
-      pmr_gemm_t t = make_gemm(rest2, rest2, kw, -1.0, P2, lda, 1, P2, 1, lda, 1.0, A33, lda, 1);
-      batched(t);
-      t.flags = PMR_GEMM_LOWER;
-      PMR_TRY(gemm(t, st));
-    }
+    if (rest2 > 0) PMR_TRY(syrk(jblk, j0, 0, kw, jnext, rest2, jnext, rest2, st));
     u2_done_prev = new_event(st);
   }
   if (lookahead) PMR_CHECK_CUDA(cudaStreamWaitEvent(st, new_event(sa), 0));
+  if (PT) PMR_CHECK_CUDA(cudaFreeAsync(PT, st));
   for (cudaEvent_t e : events) cudaEventDestroy(e);
   return 0;
 }

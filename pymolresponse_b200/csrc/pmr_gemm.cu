@@ -45,6 +45,8 @@ struct GemmArgs {
   int tiles_m, tiles_n;
   int flags;
   int a_vec2, b_vec2, c_vec2;
+  double* C2;  // optional second (differently strided) copy of the result
+  long long c2_sm, c2_sn, c2_b1, c2_b2;
 };
 
 template <int BM, int BN, int WM, int WN, bool AKC, bool BKC, int NSTAGE>
@@ -275,6 +277,11 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) dgemm_dmma_k
       } else {
         if (ok0) c[0] = alpha * acc[mi][ni][0];
         if (ok1) c[p.c_sn] = alpha * acc[mi][ni][1];
+      }
+      if (p.C2) {
+        double* c2 = p.C2 + b1 * p.c2_b1 + b2 * p.c2_b2 + (long long)m * p.c2_sm + (long long)n * p.c2_sn;
+        if (ok0) c2[0] = alpha * acc[mi][ni][0];
+        if (ok1) c2[p.c2_sn] = alpha * acc[mi][ni][1];
       }
     }
   }
@@ -605,7 +612,7 @@ int gemm(const pmr_gemm_t& g0, cudaStream_t st) {
   if (g.alpha == 0.0) { g.K = 0; g.alpha = 1.0; }  // C = beta*C through the accumulator path
 
   // Put the long dimension on M (the 128-row tile): C^T = B^T A^T with C's strides swapped.
-  if (g.N > g.M && g.flags == 0) {  // (flags != 0: LOWER / k-range / aliasing keep their roles)
+  if (g.N > g.M && g.flags == 0 && g.C2 == nullptr) {  // (flags != 0: LOWER / k-range / aliasing keep their roles)
     std::swap(g.M, g.N);
     const double* A = g.A;
     const long long a_sm = g.a_sm, a_sk = g.a_sk, a_b1 = g.a_b1, a_b2 = g.a_b2;
@@ -628,6 +635,7 @@ int gemm(const pmr_gemm_t& g0, cudaStream_t st) {
   a.a_b1 = g.a_b1; a.a_b2 = g.a_b2; a.b_b1 = g.b_b1; a.b_b2 = g.b_b2;
   a.c_b1 = g.c_b1; a.c_b2 = g.c_b2;
   a.flags = g.flags;
+  a.C2 = g.C2; a.c2_sm = g.c2_sm; a.c2_sn = g.c2_sn; a.c2_b1 = g.c2_b1; a.c2_b2 = g.c2_b2;
   a.a_vec2 = aligned16(g.A) && even(a.a_ld) && even(g.a_b1) && even(g.a_b2);
   a.b_vec2 = aligned16(g.B) && even(a.b_ld) && even(g.b_b1) && even(g.b_b2);
   a.c_vec2 = (g.c_sn == 1) && aligned16(g.C) && even(g.c_sm) && even(g.c_b1) && even(g.c_b2);
@@ -652,7 +660,7 @@ int gemm(const pmr_gemm_t& g0, cudaStream_t st) {
   // (12-17 TFLOP/s), so those layouts stay on the cp.async kernel unless PMR_GEMM_BULK_KC=1.
   static const bool bulk_kc = [] { const char* e = getenv("PMR_GEMM_BULK_KC"); return e && atoi(e); }();
   if (allow_bulk && a.a_vec2 && a.b_vec2 && g.K % BK == 0 && g.K > 0 && a_rows_ok && b_rows_ok &&
-      ((!akc && !bkc) || bulk_kc) && !(g.flags & PMR_GEMM_C_ALIASES_A)) {
+      ((!akc && !bkc) || bulk_kc) && !(g.flags & PMR_GEMM_C_ALIASES_A) && g.C2 == nullptr) {
     if (bn == 128) return launch_bulk<128, 128, 32, 32, 4, 1>(a, akc, bkc, g.batch1, g.batch2, st);
     if (bn == 64) return launch_bulk<128, 64, 32, 32, 3, 2>(a, akc, bkc, g.batch1, g.batch2, st);
     return launch_bulk<128, 32, 32, 32, 4, 2>(a, akc, bkc, g.batch1, g.batch2, st);

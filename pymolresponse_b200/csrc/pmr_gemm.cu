@@ -372,8 +372,12 @@ __device__ __forceinline__ void bulk_g2s(double* dst, const double* src, unsigne
       : "memory");
 }
 
-template <int BM, int BN, int WM, int WN, bool AKC, bool BKC, int NSTAGE, int MINB>
-__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32 + 32, MINB)
+// TMA = true : one producer warp, cp.async.bulk row copies (mn-contiguous operands only pay off);
+// TMA = false: two producer warps issue the ordinary 16/8-byte cp.async copies (with zero-fill, any
+//              layout / edge) and arrive on the stage's mbarrier with cp.async.mbarrier.arrive.noinc:
+//              same decoupled producer/consumer structure for the k-contiguous layouts.
+template <int BM, int BN, int WM, int WN, bool AKC, bool BKC, int NSTAGE, int MINB, bool TMA, int VEC>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32 + (TMA ? 32 : 64), MINB)
 dgemm_bulk_kernel(const GemmArgs p) {
   using C_ = Cfg<BM, BN, WM, WN, AKC, BKC, NSTAGE>;
   constexpr int NTC = C_::NT;  // consumer threads
@@ -395,8 +399,9 @@ dgemm_bulk_kernel(const GemmArgs p) {
   const double* Bb = p.B + b1 * p.b_b1 + b2 * p.b_b2;
   double* Cb = p.C + b1 * p.c_b1 + b2 * p.c_b2;
 
+  constexpr int NPROD = TMA ? 32 : 64;  // producer threads
   int kt_begin = 0;
-  int kt_end = p.K / BK;  // K % BK == 0 on this path
+  int kt_end = (p.K + BK - 1) / BK;  // (K % BK == 0 on the TMA path)
   if (p.flags & PMR_GEMM_KSTART_M) kt_begin = bm0 / BK;
   if (p.flags & PMR_GEMM_KEND_M) kt_end = min(kt_end, (min(p.K, bm0 + BM) + BK - 1) / BK);
   const int KT = max(kt_end - kt_begin, 0);
@@ -405,15 +410,38 @@ dgemm_bulk_kernel(const GemmArgs p) {
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], TMA ? 1 : NPROD);
       mbar_init(&empty_bar[s], NWC);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
 
-  if (warp == NWC) {
-    // ===== producer warp =====
+  if constexpr (!TMA) {
+  if (warp >= NWC) {
+    // ===== producer warps, cp.async flavour =====
+    const int ptid = tid - NTC;
+    TileLoader<BM, AKC, LDA, NPROD, VEC> la;
+    TileLoader<BN, BKC, LDB, NPROD, VEC> lb;
+    la.init(Ab, p.a_ld, bm0, p.M, kbase, ptid);
+    lb.init(Bb, p.b_ld, bn0, p.N, kbase, ptid);
+    for (int kt = 0; kt < KT; ++kt) {
+      const int slot = kt % NSTAGE;
+      if (kt >= NSTAGE) mbar_wait(&empty_bar[slot], ((kt / NSTAGE) - 1) & 1);
+      double* As = smem + slot * C_::STAGE_ELEMS;
+      double* Bs = As + C_::A_ELEMS;
+      const int k0 = kbase + kt * BK;
+      la.issue(As, kt, k0, p.K, p.a_ld, p.A);
+      lb.issue(Bs, kt, k0, p.K, p.b_ld, p.B);
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&full_bar[slot]))
+                   : "memory");
+    }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    return;
+  }
+  }
+  if (TMA && warp == NWC) {
+    // ===== producer warp, TMA bulk flavour =====
     // mn-contiguous operand: one copy per k row (16 rows of up to BM*8 bytes);
     // k-contiguous operand : one 128-byte copy per m/n row of the tile.
     const int rows_a = min(BM, p.M - bm0), rows_b = min(BN, p.N - bn0);
@@ -531,10 +559,10 @@ dgemm_bulk_kernel(const GemmArgs p) {
   }
 }
 
-template <int BM, int BN, int WM, int WN, bool AKC, bool BKC, int NSTAGE, int MINB>
+template <int BM, int BN, int WM, int WN, bool AKC, bool BKC, int NSTAGE, int MINB, bool TMA, int VEC>
 int launch_bulk_cfg(GemmArgs a, int batch1, int batch2, cudaStream_t st) {
   using C_ = Cfg<BM, BN, WM, WN, AKC, BKC, NSTAGE>;
-  auto kern = dgemm_bulk_kernel<BM, BN, WM, WN, AKC, BKC, NSTAGE, MINB>;
+  auto kern = dgemm_bulk_kernel<BM, BN, WM, WN, AKC, BKC, NSTAGE, MINB, TMA, VEC>;
   static thread_local bool configured = false;
   if (!configured) {
     PMR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -561,7 +589,7 @@ int launch_bulk_cfg(GemmArgs a, int batch1, int batch2, cudaStream_t st) {
     rec.cls = (BN == 128 ? 0 : (BN == 64 ? 2 : 4)) + (lower ? 1 : 0);
     cudaEventRecord(rec.e0, st);
   }
-  kern<<<grid, C_::NT + 32, C_::SMEM, st>>>(a);
+  kern<<<grid, C_::NT + (TMA ? 32 : 64), C_::SMEM, st>>>(a);
   if (g_prof_on) {
     cudaEventRecord(rec.e1, st);
     g_prof.push_back(rec);
@@ -572,10 +600,20 @@ int launch_bulk_cfg(GemmArgs a, int batch1, int batch2, cudaStream_t st) {
 
 template <int BM, int BN, int WM, int WN, int NSTAGE, int MINB>
 int launch_bulk(const GemmArgs& a, bool akc, bool bkc, int b1, int b2, cudaStream_t st) {
-  if (akc && bkc) return launch_bulk_cfg<BM, BN, WM, WN, true, true, NSTAGE, MINB>(a, b1, b2, st);
-  if (akc && !bkc) return launch_bulk_cfg<BM, BN, WM, WN, true, false, NSTAGE, MINB>(a, b1, b2, st);
-  if (!akc && bkc) return launch_bulk_cfg<BM, BN, WM, WN, false, true, NSTAGE, MINB>(a, b1, b2, st);
-  return launch_bulk_cfg<BM, BN, WM, WN, false, false, NSTAGE, MINB>(a, b1, b2, st);
+  if (akc && bkc) return launch_bulk_cfg<BM, BN, WM, WN, true, true, NSTAGE, MINB, true, 2>(a, b1, b2, st);
+  if (akc && !bkc) return launch_bulk_cfg<BM, BN, WM, WN, true, false, NSTAGE, MINB, true, 2>(a, b1, b2, st);
+  if (!akc && bkc) return launch_bulk_cfg<BM, BN, WM, WN, false, true, NSTAGE, MINB, true, 2>(a, b1, b2, st);
+  return launch_bulk_cfg<BM, BN, WM, WN, false, false, NSTAGE, MINB, true, 2>(a, b1, b2, st);
+}
+
+// warp-specialised cp.async producers (any layout; 16-byte copies only: the 8-byte variant stays on
+// the plain kernel)
+template <int BM, int BN, int WM, int WN, int NSTAGE, int MINB>
+int launch_ws(const GemmArgs& a, bool akc, bool bkc, int b1, int b2, cudaStream_t st) {
+  if (akc && bkc) return launch_bulk_cfg<BM, BN, WM, WN, true, true, NSTAGE, MINB, false, 2>(a, b1, b2, st);
+  if (akc && !bkc) return launch_bulk_cfg<BM, BN, WM, WN, true, false, NSTAGE, MINB, false, 2>(a, b1, b2, st);
+  if (!akc && bkc) return launch_bulk_cfg<BM, BN, WM, WN, false, true, NSTAGE, MINB, false, 2>(a, b1, b2, st);
+  return launch_bulk_cfg<BM, BN, WM, WN, false, false, NSTAGE, MINB, false, 2>(a, b1, b2, st);
 }
 
 template <int BM, int BN, int WM, int WN, int NSTAGE, int MINB>
@@ -665,6 +703,13 @@ int gemm(const pmr_gemm_t& g0, cudaStream_t st) {
     if (bn == 64) return launch_bulk<128, 64, 32, 32, 3, 2>(a, akc, bkc, g.batch1, g.batch2, st);
     return launch_bulk<128, 32, 32, 32, 4, 2>(a, akc, bkc, g.batch1, g.batch2, st);
   }
+  // EXPERIMENT (PMR_GEMM_WS=1): warp-specialised cp.async producers + mbarriers for the k-contiguous
+  // layouts.  Measured on B200 it is not faster than the plain ring (8192^3: 32.4 vs 33.7 TFLOP/s;
+  // K = 128: 28.2 vs 29.8; batched Cholesky 15.9 vs 15.5 ms), so it is off by default.
+  static const bool allow_ws = [] { const char* e = getenv("PMR_GEMM_WS"); return e && atoi(e); }();
+  if (allow_ws && bn == 64 && a.a_vec2 && a.b_vec2 && g.K > 0 && !(g.flags & PMR_GEMM_C_ALIASES_A) &&
+      g.C2 == nullptr)
+    return launch_ws<128, 64, 32, 32, 3, 2>(a, akc, bkc, g.batch1, g.batch2, st);
   if (bn == 128) return launch_layout<128, 128, 32, 32, 4, 1>(a, akc, bkc, g.batch1, g.batch2, st);
   if (bn == 64) return launch_layout<128, 64, 32, 32, 3, 2>(a, akc, bkc, g.batch1, g.batch2, st);
   return launch_layout<128, 32, 32, 32, 4, 2>(a, akc, bkc, g.batch1, g.batch2, st);

@@ -65,18 +65,22 @@ class CPHF(Driver):
             return dev[f]
         return nv.to_dev(host[f])[:, :, 0].contiguous()
 
-    def _block_matrix(self, get_p, get_r):
-        """results[rows(op1), cols(op2)] = sum_sigma P_op1,sigma . R_op2,sigma^T."""
+    def _block_matrices(self, get_p, get_r, nfreq):
+        """results[f][rows(op1), cols(op2)] = sum_sigma P_op1,sigma . R_op2,sigma[f]^T for every
+        frequency f: ONE contraction per spin with all operators and frequencies stacked."""
         ops = self.solver.operators
         tags = ("alph", "beta") if self.solver.is_uhf else ("alph",)
+        torch = nv.torch_mod()
         dims = [int(get_p(op, "alph").shape[0]) for op in ops]
         total = sum(dims)
-        out = np.zeros((total, total))
-        # stack all operators: one contraction per spin gives every block at once
+        out = np.zeros((nfreq, total, total))
+        if total == 0 or nfreq == 0:
+            return out
         for tag in tags:
-            P = nv.torch_mod().cat([get_p(op, tag) for op in ops], dim=0)
-            R = nv.torch_mod().cat([get_r(op, tag) for op in ops], dim=0)
-            out += nv.to_host(contract_rows(P, R))
+            P = torch.cat([get_p(op, tag) for op in ops], dim=0)
+            R = torch.cat([get_r(op, tag, f) for f in range(nfreq) for op in ops], dim=0)
+            full = nv.to_host(contract_rows(P, R))            # (total, nfreq * total)
+            out += full.reshape(total, nfreq, total).transpose(1, 0, 2)
         return out
 
     def form_uncoupled_results(self) -> None:
@@ -93,19 +97,19 @@ class CPHF(Driver):
                                               int(ev.shape[0]), nv.ptr(ed), nv.stream_ptr()))
             ediffs[tag] = ed
         self.uncoupled_results = []
-        for f in range(len(solver.frequencies)):
-            frequency = float(solver.frequencies[f])
+        freqs = [float(w) for w in solver.frequencies]
 
-            def divided(op, tag):
-                sv = op.supervector_dev(tag)
-                ncomp, two_nov = int(sv.shape[0]), int(sv.shape[1])
-                out = nv.empty(ncomp, two_nov)
-                nv.check(L.pmr_uncoupled_divide(nv.ptr(sv), ncomp, two_nov // 2,
-                                                nv.ptr(ediffs[tag]), frequency, nv.ptr(out),
-                                                nv.stream_ptr()))
-                return out
+        def divided(op, tag, f):
+            sv = op.supervector_dev(tag)
+            ncomp, two_nov = int(sv.shape[0]), int(sv.shape[1])
+            out = nv.empty(ncomp, two_nov)
+            nv.check(L.pmr_uncoupled_divide(nv.ptr(sv), ncomp, two_nov // 2, nv.ptr(ediffs[tag]),
+                                            freqs[f], nv.ptr(out), nv.stream_ptr()))
+            return out
 
-            results = self._block_matrix(lambda op, tag: op.supervector_dev(tag), divided)
+        allres = self._block_matrices(lambda op, tag: op.supervector_dev(tag), divided, len(freqs))
+        for f in range(len(freqs)):
+            results = allres[f]
             # the / 2 is because of the supervector part (reference cphf.py:158-162)
             if solver.is_uhf:
                 results = 2 * results / 2
@@ -130,11 +134,11 @@ class CPHF(Driver):
                 if solver.is_uhf:
                     assert tuple(op.rspvecs_beta[f].shape) == tuple(
                         op.mo_integrals_ai_supervector_beta.shape)
-        for f in range(len(solver.frequencies)):
-            results = self._block_matrix(
-                lambda op, tag: op.supervector_dev(tag),
-                lambda op, tag, f=f: self._rows(op, "rsp", tag, f),
-            )
+        nfreq = len(solver.frequencies)
+        allres = self._block_matrices(lambda op, tag: op.supervector_dev(tag),
+                                      lambda op, tag, f: self._rows(op, "rsp", tag, f), nfreq)
+        for f in range(nfreq):
+            results = allres[f]
             if solver.is_uhf:
                 results = 2 * results / 2
             else:

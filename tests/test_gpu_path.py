@@ -682,3 +682,72 @@ def test_config4_shaped_uhf_static():
         np.testing.assert_allclose(driver.results[0], ref["results"][0], rtol=0, atol=1e-9)
         assert np.abs(op.rspvecs_alph[0] - ref["rspvecs_alph"][0][0]).max() <= 1e-9
         assert np.abs(op.rspvecs_beta[0] - ref["rspvecs_beta"][0][0]).max() <= 1e-9
+
+
+def test_config5_full_size_properties():
+    """BASELINE config 5 at FULL size (nbasis=256, nocc=32: 34.4 GB AO tensor built on the device,
+    nov = 7168), checked through size-independent properties: pair symmetry of the MO integrals,
+    residual of G(w)[X;Y] = rhs with the bit-exact A/B blocks (torch is only the checker here),
+    symmetry of the polarizability, linearity in the operator, real/imaginary operator in one batch."""
+    import torch
+
+    from pymolresponse_b200 import _native as nv
+    from pymolresponse_b200 import cphf, operators, solvers, synthetic
+    from pymolresponse_b200 import explicit_equations_partial as eqp
+    from pymolresponse_b200.ao2mo import AO2MO
+    from pymolresponse_b200.core import Hamiltonian, Spin
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 80 * 2**30:
+        pytest.skip("needs ~80 GB of free HBM")
+    n, o = 256, 32
+    v, nov = n - o, o * (n - o)
+    case = synthetic.rhf_case(n, o, build_eri=False)
+    Bd = torch.from_numpy(case["B"]).cuda()
+    Bf = Bd.reshape(n, n * n)
+    I = torch.empty(n, n, n, n, dtype=torch.float64, device="cuda")
+    for mu in range(n):
+        I[mu] = (Bd[:, mu, :].t() @ Bf).reshape(n, n, n)
+    del Bd, Bf
+    a = AO2MO(case["C"], case["occupations"], I=I, device_results=True)
+    a.perform_rhf_partial()
+    ovov, oovv = a.tei_mo
+    del I, a
+    torch.cuda.empty_cache()
+    m = ovov.reshape(nov, nov)
+    assert float((m - m.t()).abs().max()) <= 1e-13
+    assert float((oovv - oovv.transpose(0, 1)).abs().max()) <= 1e-13
+    del m
+    Or = synthetic.operator_integrals(n, 3, False)
+    Oi = synthetic.operator_integrals(n, 3, True)
+    freqs = [0.0, 0.3, 0.63]
+    solver = solvers.ExactInv(case["C"], case["E"], case["occupations"])
+    solver.device_results = True
+    solver.tei_mo = (ovov, oovv)
+    driver = cphf.CPHF(solver)
+    ops = [operators.Operator(label="dipole", is_imaginary=False, ao_integrals=Or),
+           operators.Operator(label="angmom", is_imaginary=True, ao_integrals=Oi),
+           operators.Operator(label="dipole2", is_imaginary=False, ao_integrals=2.5 * Or)]
+    for op in ops:
+        driver.add_operator(op)
+    driver.set_frequencies(freqs)
+    driver.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet, program=None, program_obj=None)
+    assert solver.solve_stats["lu_fallback"] == 0
+    A = eqp.form_rpa_a_matrix_mo_singlet_partial(nv.to_dev(case["E"][0]), ovov, oovv)
+    Bm = eqp.form_rpa_b_matrix_mo_singlet_partial(ovov)
+    for f, w in enumerate(freqs):
+        for op in ops:
+            xy = op.rspvecs_alph[f][:, :, 0]              # (3, 2nov) on the device
+            rhs = op.supervector_dev("alph")
+            X, Y = xy[:, :nov], xy[:, nov:]
+            top = X @ A.t() + Y @ Bm.t() - w * X
+            bot = X @ Bm.t() + Y @ A.t() + w * Y
+            resid = torch.cat((top, bot), dim=1) - rhs
+            assert float(resid.abs().max()) <= 1e-11 * max(1.0, float(rhs.abs().max()))
+        res = driver.results[f]
+        assert res.shape == (9, 9)
+        alpha = res[:3, :3]
+        assert np.abs(alpha - alpha.T).max() <= 1e-10
+        # linearity: the third operator is 2.5 x the first
+        assert np.abs(res[6:, 6:] - 6.25 * alpha).max() <= 1e-9 * max(1.0, np.abs(alpha).max())
+        assert np.abs(res[6:, :3] - 2.5 * alpha).max() <= 1e-9 * max(1.0, np.abs(alpha).max())

@@ -159,6 +159,10 @@ class HalfSizeSystem:
         self.N = int(M.shape[0])
         self.memory_fraction = memory_fraction
         self.stats = {"potrf": 0, "potrf_batch": 0, "potri": 0, "lu_fallback": 0}
+        # factor of K and K^-1 are kept: later solve() calls and solvers that adopt this system
+        # (several properties on one reference wavefunction) reuse them
+        self._Kfac = self._dinvK = self._Kinv = None
+        self._K_bad = False
 
     def _chunk(self, nf):
         torch = nv.torch_mod()
@@ -208,17 +212,26 @@ class HalfSizeSystem:
         Kfac = dinvK = Kinv = T = None
         bad = set()
         if need_K:
-            Kfac = self.K.clone()
-            dinvK, infoK = potrf(Kfac)
-            self.stats["potrf"] += 1
-            if int(infoK.item()) != 0:
-                bad = set(range(nf))  # K itself is not SPD: everything goes to LU
-        if not bad and share_kinv:
-            Kinv = self._kinv_distributed(Kfac, dinvK)
-            self.stats["potri_shared"] = self.stats.get("potri_shared", 0) + 1
-        elif not bad and any_dyn:
-            Kinv = potri_lower(Kfac, dinvK)
-            self.stats["potri"] += 1
+            if self._Kfac is None and not self._K_bad:
+                Kf = self.K.clone()
+                dk, infoK = potrf(Kf)
+                self.stats["potrf"] += 1
+                if int(infoK.item()) != 0:
+                    self._K_bad = True  # K itself is not SPD: everything goes to LU
+                else:
+                    self._Kfac, self._dinvK = Kf, dk
+            if self._K_bad:
+                bad = set(range(nf))
+            Kfac, dinvK = self._Kfac, self._dinvK
+        if not bad and (share_kinv or any_dyn):
+            if self._Kinv is None:
+                if share_kinv:
+                    self._Kinv = self._kinv_distributed(Kfac, dinvK)
+                    self.stats["potri_shared"] = self.stats.get("potri_shared", 0) + 1
+                else:
+                    self._Kinv = potri_lower(Kfac, dinvK)
+                    self.stats["potri"] += 1
+            Kinv = self._Kinv
         if nf == 0:
             return xy
         if not bad and any_dyn and imag_cols:

@@ -277,6 +277,17 @@ class ExactLineqSolver(LineqSolver, ABC):
                 fill(A, B, 0)
         return M, K, A, B
 
+    def share_hessian_with(self, other: "ExactLineqSolver") -> None:
+        """Let ``other`` reuse this solver's assembled M / K matrices, the Cholesky factor of K and
+        K^-1 (all device resident) instead of rebuilding them: several properties computed for the
+        same reference wavefunction, Hamiltonian and spin need them only once.  Call it after this
+        solver has run (or at least been prepared); ``other`` must use the same MO integrals."""
+        assert getattr(self, "_system", None) is not None, "run or prepare this solver first"
+        assert self.occupations == other.occupations and self.is_uhf == other.is_uhf
+        other._system = self._system
+        other._prepared_for = self._prepared_for
+        other._hessian_shared = True
+
     def _prepare(self, hamiltonian: Hamiltonian, spin: Spin, want_ab: bool = False):
         assemble = self._assemble_uhf if self.is_uhf else self._assemble_rhf
         M, K, A, B = assemble(hamiltonian, spin, want_ab)
@@ -474,7 +485,8 @@ class ExactLineqSolver(LineqSolver, ABC):
         for frequency in self.frequencies:
             assert isinstance(frequency, float)
         freqs = [float(w) for w in self.frequencies]
-        self._prepared_for = None
+        if not getattr(self, "_hessian_shared", False):
+            self._prepared_for = None
         if getattr(self, "inv_func", None) is not None and self.inv_func is not np.linalg.inv:
             # caller-injected inversion routine (reference solvers.py:490-497): honour it literally
             for w in freqs:

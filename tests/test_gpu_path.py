@@ -751,3 +751,32 @@ def test_config5_full_size_properties():
         # linearity: the third operator is 2.5 x the first
         assert np.abs(res[6:, 6:] - 6.25 * alpha).max() <= 1e-9 * max(1.0, np.abs(alpha).max())
         assert np.abs(res[6:, :3] - 2.5 * alpha).max() <= 1e-9 * max(1.0, np.abs(alpha).max())
+
+
+def test_solvers_share_hessian(golden_dir):
+    """Two properties on one reference: the second solver adopts M, K, chol(K) of the first."""
+    from pymolresponse_b200 import cphf, operators, solvers, synthetic
+    from pymolresponse_b200.core import Hamiltonian, Spin
+
+    g = np.load(golden_dir / "synthetic_rhf_n10.npz")
+    n, o = int(g["n"]), int(g["nocc"])
+    case = synthetic.rhf_case(n, o, build_eri=False)
+    Or, Oi = synthetic.operator_integrals(n, 3, False), synthetic.operator_integrals(n, 3, True)
+    tei = (g["ovov"], g["oovv"])
+    s1 = solvers.ExactInvCholesky(case["C"], case["E"], case["occupations"])
+    s1.tei_mo = tei
+    d1 = cphf.CPHF(s1)
+    d1.add_operator(operators.Operator(label="angmom", is_imaginary=True, ao_integrals=Oi))
+    d1.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet, program=None, program_obj=None)
+    s2 = solvers.ExactInv(case["C"], case["E"], case["occupations"])
+    s2.tei_mo = tei
+    s1.share_hessian_with(s2)
+    d2 = cphf.CPHF(s2)
+    d2.add_operator(operators.Operator(label="dipole", is_imaginary=False, ao_integrals=Or))
+    d2.set_frequencies([float(w) for w in g["frequencies"]])
+    d2.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet, program=None, program_obj=None)
+    assert s2.solve_stats["potrf"] == 1          # factor of K came from the first solver
+    ref = g["results_rpa_singlet_partial"]
+    for f in range(len(g["frequencies"])):
+        np.testing.assert_allclose(d2.results[f], ref[f][:3, :3], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(d1.results[0], ref[0][3:, 3:], rtol=0, atol=1e-10)

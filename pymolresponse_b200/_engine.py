@@ -166,7 +166,10 @@ class HalfSizeSystem:
 
     def _chunk(self, nf):
         torch = nv.torch_mod()
-        free, _ = torch.cuda.mem_get_info()
+        # memory the caching allocator can still hand out, without a driver call
+        dev = torch.cuda.current_device()
+        total = torch.cuda.get_device_properties(dev).total_memory
+        free = total - torch.cuda.memory_allocated(dev) - (2 << 30)
         per = max(1, self.N * self.N * 8)
         return int(max(1, min(nf, (free * self.memory_fraction) // per)))
 

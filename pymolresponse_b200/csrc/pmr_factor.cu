@@ -176,18 +176,21 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, in
   }
 }
 
+constexpr int SHIFT_MAX = 64;  // frequencies per launch (shifts travel as kernel parameters)
+struct ShiftPack { double a[SHIFT_MAX]; double b[SHIFT_MAX]; };
+
 __global__ void shifted_combine_kernel(const double* __restrict__ M, const double* __restrict__ W,
                                        int N, long long ldm, long long ldw, int nf,
                                        double* __restrict__ S, long long lds, long long stride_s,
-                                       const double* __restrict__ shifts /* 2*nf on device */) {
+                                       const ShiftPack sh) {
   const int row = blockIdx.y;
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col > row || col >= N) return;
   const double m = M[(long long)row * ldm + col];
   const double w = W ? W[(long long)row * ldw + col] : 0.0;
   for (int f = 0; f < nf; ++f) {
-    double v = m + shifts[nf + f] * w;
-    if (col == row) v += shifts[f];
+    double v = m + sh.b[f] * w;
+    if (col == row) v += sh.a[f];
     S[(long long)f * stride_s + (long long)row * lds + col] = v;
   }
 }
@@ -584,17 +587,15 @@ extern "C" int pmr_shifted_combine(const double* M, const double* W, int N, long
   PMR_REQUIRE(N >= 0 && nf >= 0, "shifted_combine: bad sizes");
   if (N == 0 || nf == 0) return 0;
   PMR_REQUIRE(M && S && shift_a_host && shift_b_host, "shifted_combine: null pointer");
-  double* dshift = nullptr;
-  PMR_CHECK_CUDA(cudaMallocAsync(&dshift, sizeof(double) * 2 * nf, st));
-  std::vector<double> h(2 * (size_t)nf);
-  for (int f = 0; f < nf; ++f) { h[f] = shift_a_host[f]; h[nf + f] = shift_b_host[f]; }
-  // pageable host memory: the copy is staged by the runtime before the call returns
-  PMR_CHECK_CUDA(cudaMemcpyAsync(dshift, h.data(), sizeof(double) * 2 * nf,
-                                 cudaMemcpyHostToDevice, st));
   dim3 grid((N + 255) / 256, N);
-  shifted_combine_kernel<<<grid, 256, 0, st>>>(M, W, N, ldm, ldw, nf, S, lds, stride_s, dshift);
-  PMR_CHECK_LAUNCH("shifted_combine_kernel");
-  PMR_CHECK_CUDA(cudaFreeAsync(dshift, st));
+  for (int f0 = 0; f0 < nf; f0 += SHIFT_MAX) {
+    const int cnt = std::min(SHIFT_MAX, nf - f0);
+    ShiftPack sh{};
+    for (int f = 0; f < cnt; ++f) { sh.a[f] = shift_a_host[f0 + f]; sh.b[f] = shift_b_host[f0 + f]; }
+    shifted_combine_kernel<<<grid, 256, 0, st>>>(M, W, N, ldm, ldw, cnt, S + (long long)f0 * stride_s,
+                                                 lds, stride_s, sh);
+    PMR_CHECK_LAUNCH("shifted_combine_kernel");
+  }
   return 0;
 }
 

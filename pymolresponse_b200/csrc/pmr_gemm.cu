@@ -173,6 +173,11 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) dgemm_dmma_k
   const int wm0 = (warp % C_::WARPS_M) * WM;
   const int wn0 = (warp / C_::WARPS_M) * WN;
 
+  // lower-triangular updates: a warp whose whole WM x WN block lies above the diagonal produces
+  // nothing that is stored; it keeps copying and synchronising but issues no DMMA, which leaves the
+  // tensor pipe to the other CTA of the SM (diagonal tiles are ~2/T of all tiles of a T-row update)
+  const bool warp_active = !(lower && bn0 + wn0 > bm0 + wm0 + WM - 1);
+
   TileLoader<BM, AKC, LDA, NT, VEC> la;  // VEC = 2: 16-byte copies (both operands 16-byte aligned)
   TileLoader<BN, BKC, LDB, NT, VEC> lb;  // VEC = 1: 8-byte copies (odd strides / offsets)
   la.init(Ab, p.a_ld, bm0, p.M, kbase, tid);
@@ -232,19 +237,21 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) dgemm_dmma_k
     slot = (slot + 1 == NSTAGE) ? 0 : slot + 1;
 #pragma unroll
     for (int kk = 0; kk < BK / 4; ++kk) {
-      double a[MI], b[NI];
+      if (warp_active) {
+        double a[MI], b[NI];
 #pragma unroll
-      for (int mi = 0; mi < MI; ++mi)
-        a[mi] = AKC ? As[(wm0 + mi * 8 + g) * LDA + kk * 4 + t]
-                    : As[(kk * 4 + t) * LDA + wm0 + mi * 8 + g];
+        for (int mi = 0; mi < MI; ++mi)
+          a[mi] = AKC ? As[(wm0 + mi * 8 + g) * LDA + kk * 4 + t]
+                      : As[(kk * 4 + t) * LDA + wm0 + mi * 8 + g];
 #pragma unroll
-      for (int ni = 0; ni < NI; ++ni)
-        b[ni] = BKC ? Bs[(wn0 + ni * 8 + g) * LDB + kk * 4 + t]
-                    : Bs[(kk * 4 + t) * LDB + wn0 + ni * 8 + g];
+        for (int ni = 0; ni < NI; ++ni)
+          b[ni] = BKC ? Bs[(wn0 + ni * 8 + g) * LDB + kk * 4 + t]
+                      : Bs[(kk * 4 + t) * LDB + wn0 + ni * 8 + g];
 #pragma unroll
-      for (int mi = 0; mi < MI; ++mi)
+        for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < NI; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
+          for (int ni = 0; ni < NI; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
+      }
       if (kk == 0) {
         // Refill the slot consumed in the previous iteration AFTER the first block of DMMAs is
         // queued: while this warp generates addresses the other warps of the SMSP own the tensor
@@ -710,6 +717,8 @@ int gemm(const pmr_gemm_t& g0, cudaStream_t st) {
   if (allow_ws && bn == 64 && a.a_vec2 && a.b_vec2 && g.K > 0 && !(g.flags & PMR_GEMM_C_ALIASES_A) &&
       g.C2 == nullptr)
     return launch_ws<128, 64, 32, 32, 3, 2>(a, akc, bkc, g.batch1, g.batch2, st);
+  if (bn == 128 && (g.flags & PMR_GEMM_C_ALIASES_A))  // in-place panel solve: full rows per CTA,
+    return launch_layout<64, 128, 32, 32, 3, 2>(a, akc, bkc, g.batch1, g.batch2, st);  // 2 CTAs / SM
   if (bn == 128) return launch_layout<128, 128, 32, 32, 4, 1>(a, akc, bkc, g.batch1, g.batch2, st);
   if (bn == 64) return launch_layout<128, 64, 32, 32, 3, 2>(a, akc, bkc, g.batch1, g.batch2, st);
   return launch_layout<128, 32, 32, 32, 4, 2>(a, akc, bkc, g.batch1, g.batch2, st);

@@ -172,9 +172,14 @@ void pmr_set_lookahead(int on);
 void pmr_set_transposed_panels(int on);
 int pmr_potrf(double* A, int N, long long lda, int batch, long long stride_a, double* dinv,
               int* info /* device, batch ints */, void* stream);
+/* Factor ONE 512-wide block column (columns [j0, j0+512), j0 % 512 == 0) of a single matrix whose
+ * rows j0.. already carry the updates of the block columns to its left; `dinv` / `info` as in
+ * pmr_potrf (info must be zeroed by the caller once).  Multi-GPU building block. */
+int pmr_potrf_panel(double* A, int N, long long lda, int j0, double* dinv, int* info, void* stream);
 /* Solve A X = B in place of B (B is N x nrhs, row stride ldb); `work` has N*nrhs doubles/batch. */
 int pmr_potrs(const double* L, int N, long long lda, int batch, long long stride_l,
               const double* dinv, double* B, int nrhs, long long ldb, long long stride_b,
+              int first_row /* rows of B above it are zero on entry (0 = general) */,
               double* work, void* stream);
 /* Lower triangle of A^-1 from the Cholesky factor (out may not alias L); work: N*N doubles. */
 int pmr_potri_lower(const double* L, int N, long long lda, const double* dinv, double* out,

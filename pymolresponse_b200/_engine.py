@@ -47,8 +47,61 @@ def potrf(A, batch=1):
     return dinv, info
 
 
-def potrs(Lfac, dinv, B, batch=1):
-    """Solve in place: B is (batch, N, nrhs) or (N, nrhs), contiguous."""
+OUTER_BLOCK = 512  # outer block width of pmr_potrf / pmr_potrf_panel
+DISTRIBUTED_POTRF_MIN_N = 4 * OUTER_BLOCK  # below this the redundant single-rank factorisation wins
+
+
+def potrf_distributed(A):
+    """Cholesky of ONE replicated (N, N) matrix with the work split over the torch.distributed ranks:
+    512-wide block columns are dealt cyclically; the owner factors its block column
+    (pmr_potrf_panel) and broadcasts the panel (+ its diagonal-block inverses); every rank stores it
+    and applies the rank-512 update to the block columns it owns.  All ranks end up with the complete
+    factor, so the triangular solves that follow need no further exchange.  Per-rank flops: u/world
+    instead of u."""
+    from pymolresponse_b200 import distributed as pd
+
+    rank, world = pd.rank_world()
+    L = nv.lib()
+    torch = nv.torch_mod()
+    N = int(A.shape[0])
+    lda = int(A.stride(0))
+    nbd = int(L.pmr_potrf_dinv_doubles(N))
+    dinv = nv.zeros(1, max(1, nbd))
+    info = torch.zeros(1, dtype=torch.int32, device=nv.device())
+    nblk = (N + OUTER_BLOCK - 1) // OUTER_BLOCK
+    for J in range(nblk):
+        j0 = J * OUTER_BLOCK
+        jend = min(N, j0 + OUTER_BLOCK)
+        kw = jend - j0
+        owner = J % world
+        nd = ((kw + 127) // 128) * 128 * 128        # diagonal-block inverses of this panel
+        d0 = (j0 // 128) * 128 * 128
+        pack = nv.empty((N - j0) * kw + nd + 1)
+        if owner == rank:
+            nv.check(L.pmr_potrf_panel(nv.ptr(A), N, lda, j0, nv.ptr(dinv), nv.ptr(info),
+                                       nv.stream_ptr()))
+            pack[: (N - j0) * kw].view(N - j0, kw).copy_(A[j0:, j0:jend])
+            pack[(N - j0) * kw: (N - j0) * kw + nd].copy_(dinv[0, d0:d0 + nd])
+            pack[-1:].copy_(info.to(torch.float64))
+        pd.broadcast(pack, owner)
+        if owner != rank:
+            A[j0:, j0:jend].copy_(pack[: (N - j0) * kw].view(N - j0, kw))
+            dinv[0, d0:d0 + nd].copy_(pack[(N - j0) * kw: (N - j0) * kw + nd])
+            info.copy_(torch.maximum(info, pack[-1:].to(torch.int32)))
+        # rank-kw update of the block columns this rank owns to the right of J
+        for Jp in range(J + 1, nblk):
+            if Jp % world != rank:
+                continue
+            c0 = Jp * OUTER_BLOCK
+            c1 = min(N, c0 + OUTER_BLOCK)
+            nv.dgemm(N - c0, c1 - c0, kw, -1.0, A, c0 * lda + j0, lda, 1, A, c0 * lda + j0, 1, lda, 1.0,
+                     A, c0 * lda + c0, lda, 1, flags=nv.GEMM_LOWER)
+    return dinv, info
+
+
+def potrs(Lfac, dinv, B, batch=1, first_row=0):
+    """Solve in place: B is (batch, N, nrhs) or (N, nrhs), contiguous.  ``first_row``: rows of B above
+    it are known to be zero (identity columns), the forward substitution starts there."""
     L = nv.lib()
     N = int(Lfac.shape[-1])
     nrhs = int(B.shape[-1])
@@ -59,7 +112,7 @@ def potrs(Lfac, dinv, B, batch=1):
     sb = int(B.stride(0)) if B.dim() == 3 else 0
     work = nv.empty(batch, N, nrhs)
     nv.check(L.pmr_potrs(nv.ptr(Lfac), N, lda, batch, sl, nv.ptr(dinv), nv.ptr(B), nrhs,
-                         int(B.stride(-2)), sb, nv.ptr(work), nv.stream_ptr()))
+                         int(B.stride(-2)), sb, int(first_row), nv.ptr(work), nv.stream_ptr()))
     return B
 
 
@@ -174,19 +227,36 @@ class HalfSizeSystem:
         return int(max(1, min(nf, (free * self.memory_fraction) // per)))
 
     def _kinv_distributed(self, Kfac, dinvK):
-        """K^-1 with the work split over the ranks: every rank solves K X = E_J for its own block of
-        N/world identity columns (two triangular solves against the shared factor, 0.75 u instead of
-        2 u) and the column blocks are all-gathered (N^2 * 8 bytes in total over NVLink)."""
+        """K^-1 with the work split over the ranks: every rank solves K X = E_J for its own identity
+        columns against the shared factor and the column blocks are all-gathered (N^2 * 8 bytes in
+        total over NVLink).  The forward substitution of a column block starting at column c skips
+        the (zero) rows above c, so the columns are cut into 2*world blocks and rank r takes blocks r
+        and 2*world-1-r: the cheap late block balances the expensive early one."""
         from pymolresponse_b200 import distributed as pd
 
         rank, world = pd.rank_world()
-        lo, hi = pd.shard_range(self.N, rank, world)
-        w = hi - lo
-        rhs = nv.zeros(self.N, max(w, 1))
-        if w > 0:
-            shift_diagonal(rhs, w, 1.0, offset=lo * int(rhs.stride(0)))
-            potrs(Kfac, dinvK, rhs)
-        return pd.allgather_columns(rhs[:, :w].contiguous() if w != rhs.shape[1] else rhs, self.N)
+        N = self.N
+        nblocks = 2 * world
+        bounds = [pd.shard_range(N, b, nblocks) for b in range(nblocks)]
+        mine = [bounds[rank], bounds[nblocks - 1 - rank]]
+        wmax = max(hi - lo for lo, hi in bounds)
+        local = nv.zeros(N, 2 * wmax)
+        for k, (lo, hi) in enumerate(mine):
+            w = hi - lo
+            if w == 0:
+                continue
+            rhs = nv.zeros(N, w)
+            shift_diagonal(rhs, w, 1.0, offset=lo * w)
+            potrs(Kfac, dinvK, rhs, first_row=(lo // 128) * 128)
+            local[:, k * wmax:k * wmax + w].copy_(rhs)
+        gathered = pd.allgather_columns(local, 2 * wmax * world)   # equal widths per rank
+        Kinv = nv.empty(N, N)
+        for r in range(world):
+            for k, b in enumerate((r, nblocks - 1 - r)):
+                lo, hi = bounds[b]
+                src0 = r * 2 * wmax + k * wmax
+                Kinv[:, lo:hi].copy_(gathered[:, src0:src0 + (hi - lo)])
+        return Kinv
 
     def solve(self, g_rows, signs, frequencies, allow_fallback=True, distributed=False,
               global_frequencies=None):
@@ -217,7 +287,11 @@ class HalfSizeSystem:
         if need_K:
             if self._Kfac is None and not self._K_bad:
                 Kf = self.K.clone()
-                dk, infoK = potrf(Kf)
+                if share_kinv and self.N >= DISTRIBUTED_POTRF_MIN_N:
+                    dk, infoK = potrf_distributed(Kf)   # collective: every rank is here (share_kinv)
+                    self.stats["potrf_shared"] = self.stats.get("potrf_shared", 0) + 1
+                else:
+                    dk, infoK = potrf(Kf)
                 self.stats["potrf"] += 1
                 if int(infoK.item()) != 0:
                     self._K_bad = True  # K itself is not SPD: everything goes to LU

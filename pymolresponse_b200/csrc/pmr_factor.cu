@@ -495,9 +495,53 @@ extern "C" int pmr_potrf(double* A, int N, long long lda, int batch, long long s
   return 0;
 }
 
+// One outer block column of the blocked Cholesky, on its own: factor columns [j0, j0+512) of A
+// (rows j0..N-1 must already carry every update from the blocks to the left).  Building block of the
+// multi-GPU factorisation (block columns dealt cyclically to ranks, panels broadcast); the caller
+// applies the rank-512 update of the other block columns with pmr_dgemm + PMR_GEMM_LOWER.
+extern "C" int pmr_potrf_panel(double* A, int N, long long lda, int j0, double* dinv, int* info,
+                               void* stream) {
+  cudaStream_t st = as_stream(stream);
+  constexpr int NBO = 512;
+  PMR_REQUIRE(A && dinv && info, "potrf_panel: null pointer");
+  PMR_REQUIRE(N >= 0 && j0 >= 0 && j0 < N && j0 % NBO == 0 && lda >= N, "potrf_panel: bad block");
+  const long long dstride = pmr_potrf_dinv_doubles(N);
+  static thread_local bool configured = false;
+  const size_t smem = POTF2_SMEM;
+  if (!configured) {
+    PMR_CHECK_CUDA(cudaFuncSetAttribute(potf2_trtri_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int jend = std::min(N, j0 + NBO);
+  for (int k0 = j0; k0 < jend; k0 += NB) {
+    const int kb = k0 / NB;
+    const int jb = std::min(NB, N - k0);
+    const int rest = N - k0 - jb;
+    double* dk = dinv + (long long)kb * NB * NB;
+    potf2_trtri_kernel<<<1, POTF2_THREADS, smem, st>>>(A + (long long)k0 * lda + k0, lda, 0, jb, dk,
+                                                       dstride, info, k0);
+    PMR_CHECK_LAUNCH("potf2_trtri_kernel");
+    if (rest > 0) {
+      double* A21 = A + (long long)(k0 + jb) * lda + k0;
+      pmr_gemm_t g = make_gemm(rest, jb, jb, 1.0, A21, lda, 1, dk, 1, NB, 0.0, A21, lda, 1);
+      g.flags = PMR_GEMM_C_ALIASES_A;
+      PMR_TRY(gemm(g, st));
+      const int ncols = jend - (k0 + jb);
+      if (ncols > 0) {
+        double* A22 = A + (long long)(k0 + jb) * lda + (k0 + jb);
+        pmr_gemm_t t = make_gemm(rest, ncols, jb, -1.0, A21, lda, 1, A21, 1, lda, 1.0, A22, lda, 1);
+        t.flags = PMR_GEMM_LOWER;
+        PMR_TRY(gemm(t, st));
+      }
+    }
+  }
+  return 0;
+}
+
 extern "C" int pmr_potrs(const double* L, int N, long long lda, int batch, long long stride_l,
                          const double* dinv, double* B, int nrhs, long long ldb,
-                         long long stride_b, double* work, void* stream) {
+                         long long stride_b, int first_row, double* work, void* stream) {
   cudaStream_t st = as_stream(stream);
   PMR_REQUIRE(N >= 0 && nrhs >= 0 && batch >= 1 && batch <= 65535, "potrs: bad sizes");
   if (N == 0 || nrhs == 0) return 0;
@@ -506,8 +550,15 @@ extern "C" int pmr_potrs(const double* L, int N, long long lda, int batch, long 
   const long long dstride = pmr_potrf_dinv_doubles(N);
   const long long wstride = (long long)N * nrhs;
   const int nblk = (N + NB - 1) / NB;
-  // forward: L Y = B, Y -> work
-  for (int kb = 0; kb < nblk; ++kb) {
+  // forward: L Y = B, Y -> work.  Rows of B above first_row are zero on entry (columns of the
+  // identity): their block rows are skipped, only the matching part of `work` is cleared.
+  PMR_REQUIRE(first_row >= 0 && first_row <= N, "potrs: bad first_row");
+  const int kb0 = first_row / NB;
+  if (kb0 > 0)
+    for (int b = 0; b < batch; ++b)
+      PMR_CHECK_CUDA(cudaMemsetAsync(work + (long long)b * wstride, 0,
+                                     sizeof(double) * (size_t)kb0 * NB * nrhs, st));
+  for (int kb = kb0; kb < nblk; ++kb) {
     const int k0 = kb * NB, jb = std::min(NB, N - k0), rest = N - k0 - jb;
     const double* dk = dinv + (long long)kb * NB * NB;
     pmr_gemm_t g = make_gemm(jb, nrhs, jb, 1.0, dk, NB, 1, B + (long long)k0 * ldb, ldb, 1, 0.0,

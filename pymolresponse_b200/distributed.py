@@ -137,6 +137,20 @@ def gather_round_robin(local_items: list, n_items: int):
     return out
 
 
+def broadcast(t, src: int) -> None:
+    """In-place broadcast of a contiguous tensor from rank ``src``."""
+    if not is_initialized():
+        return
+    d = dist()
+    if t.is_cuda and _host_staged():
+        h = t.cpu()
+        d.broadcast(h, src=src)
+        if d.get_rank() != src:
+            t.copy_(h)
+    else:
+        d.broadcast(t, src=src)
+
+
 def reduce_scatter_rows(T, n_rows_total: int):
     """Sum T (n_rows_total, ...) over ranks and return this rank's row block
     ``shard_range(n_rows_total, rank, world)`` of the sum."""

@@ -22,6 +22,7 @@ import torch
 import torch.distributed as dist
 sys.path.insert(0, sys.argv[3])
 from oracle import pmr_oracle as orc
+from pymolresponse_b200 import _engine as eng, _native as nv
 from pymolresponse_b200 import cphf, distributed as pd, operators, solvers, synthetic
 from pymolresponse_b200.ao2mo import AO2MO
 from pymolresponse_b200.core import Hamiltonian, Spin
@@ -29,6 +30,23 @@ from pymolresponse_b200.core import Hamiltonian, Spin
 rank, world = int(sys.argv[1]), 2
 torch.cuda.set_device(0)
 dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=rank, world_size=world)
+# block-cyclic distributed Cholesky (panels broadcast) against the single-rank factorisation
+for N in (700, 1537):
+    r = np.random.default_rng(5)
+    X = r.standard_normal((N, N))
+    A = X @ X.T / N + 1.5 * np.eye(N)
+    Ad = nv.to_dev(A).clone()
+    dinv, info = eng.potrf_distributed(Ad)
+    assert int(info.item()) == 0
+    Lm = np.tril(Ad.cpu().numpy())
+    assert np.abs(Lm @ Lm.T - A).max() <= 1e-12 * N
+    rhs = r.standard_normal((N, 3))
+    Xs = eng.potrs(Ad, dinv, nv.to_dev(rhs).clone()).cpu().numpy()
+    assert np.abs(A @ Xs - rhs).max() <= 1e-10 * N
+A[900, 900] = -3.0
+_, info = eng.potrf_distributed(nv.to_dev(A).clone())
+assert int(info.item()) == 901
+eng.DISTRIBUTED_POTRF_MIN_N = 0      # let the small solver case below take the distributed path too
 n, o = 30, 4
 case = synthetic.rhf_case(n, o)
 lo, hi = pd.shard_range(n, rank, world)
@@ -60,6 +78,7 @@ for freqs in ([0.0, 0.1, 0.2], [0.3], [0.0]):
             assert np.abs(ops[k].rspvecs_alph[f] - ref["rspvecs_alph"][k][f]).max() <= 1e-9
     if any(w != 0.0 for w in freqs):
         assert solver.solve_stats.get("potri_shared", 0) == 1 and solver.solve_stats["potri"] == 0
+        assert solver.solve_stats.get("potrf_shared", 0) == 1
 pd.barrier()
 dist.destroy_process_group()
 print("ok", rank)

@@ -180,6 +180,7 @@ int pmr_potrf_panel(double* A, int N, long long lda, int j0, double* dinv, int* 
 int pmr_potrs(const double* L, int N, long long lda, int batch, long long stride_l,
               const double* dinv, double* B, int nrhs, long long ldb, long long stride_b,
               int first_row /* rows of B above it are zero on entry (0 = general) */,
+              int lower_only /* 1: rows of X above first_row are not computed (left zero) */,
               double* work, void* stream);
 /* Lower triangle of A^-1 from the Cholesky factor (out may not alias L); work: N*N doubles. */
 int pmr_potri_lower(const double* L, int N, long long lda, const double* dinv, double* out,

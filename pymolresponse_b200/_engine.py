@@ -51,13 +51,29 @@ OUTER_BLOCK = 512  # outer block width of pmr_potrf / pmr_potrf_panel
 DISTRIBUTED_POTRF_MIN_N = 4 * OUTER_BLOCK  # below this the redundant single-rank factorisation wins
 
 
+_comm_streams = {}
+
+
+def _comm_stream():
+    """One side stream per device for the panel broadcasts of :func:`potrf_distributed`."""
+    torch = nv.torch_mod()
+    dev = torch.cuda.current_device()
+    if dev not in _comm_streams:
+        _comm_streams[dev] = torch.cuda.Stream(device=dev)
+    return _comm_streams[dev]
+
+
 def potrf_distributed(A):
     """Cholesky of ONE replicated (N, N) matrix with the work split over the torch.distributed ranks:
     512-wide block columns are dealt cyclically; the owner factors its block column
     (pmr_potrf_panel) and broadcasts the panel (+ its diagonal-block inverses); every rank stores it
     and applies the rank-512 update to the block columns it owns.  All ranks end up with the complete
     factor, so the triangular solves that follow need no further exchange.  Per-rank flops: u/world
-    instead of u."""
+    instead of u.
+
+    Look-ahead: as soon as panel J has arrived, the owner of J+1 updates that one block column,
+    factors it and hands it to the broadcast on a side stream; the remaining rank-512 updates of step
+    J (the bulk of the flops) run on the main stream underneath the transfer."""
     from pymolresponse_b200 import distributed as pd
 
     rank, world = pd.rank_world()
@@ -69,39 +85,70 @@ def potrf_distributed(A):
     dinv = nv.zeros(1, max(1, nbd))
     info = torch.zeros(1, dtype=torch.int32, device=nv.device())
     nblk = (N + OUTER_BLOCK - 1) // OUTER_BLOCK
-    for J in range(nblk):
+    main = torch.cuda.current_stream()
+    comm = _comm_stream()
+    packs = {}
+
+    def geometry(J):
         j0 = J * OUTER_BLOCK
         jend = min(N, j0 + OUTER_BLOCK)
         kw = jend - j0
-        owner = J % world
         nd = ((kw + 127) // 128) * 128 * 128        # diagonal-block inverses of this panel
         d0 = (j0 // 128) * 128 * 128
+        return j0, jend, kw, nd, d0
+
+    def update(J, Jp):
+        j0, _, kw, _, _ = geometry(J)
+        c0 = Jp * OUTER_BLOCK
+        c1 = min(N, c0 + OUTER_BLOCK)
+        nv.dgemm(N - c0, c1 - c0, kw, -1.0, A, c0 * lda + j0, lda, 1, A, c0 * lda + j0, 1, lda, 1.0,
+                 A, c0 * lda + c0, lda, 1, flags=nv.GEMM_LOWER)
+
+    def post(J):
+        """Owner: factor block column J on the main stream; everyone: broadcast it on the side one."""
+        j0, jend, kw, nd, d0 = geometry(J)
+        owner = J % world
         pack = nv.empty((N - j0) * kw + nd + 1)
         if owner == rank:
             nv.check(L.pmr_potrf_panel(nv.ptr(A), N, lda, j0, nv.ptr(dinv), nv.ptr(info),
                                        nv.stream_ptr()))
-            pack[: (N - j0) * kw].view(N - j0, kw).copy_(A[j0:, j0:jend])
-            pack[(N - j0) * kw: (N - j0) * kw + nd].copy_(dinv[0, d0:d0 + nd])
-            pack[-1:].copy_(info.to(torch.float64))
-        pd.broadcast(pack, owner)
-        if owner != rank:
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(comm):
+            comm.wait_event(ready)
+            if owner == rank:
+                pack[: (N - j0) * kw].view(N - j0, kw).copy_(A[j0:, j0:jend])
+                pack[(N - j0) * kw: (N - j0) * kw + nd].copy_(dinv[0, d0:d0 + nd])
+                pack[-1:].copy_(info.to(torch.float64))
+            pd.broadcast(pack, owner)
+            done = torch.cuda.Event()
+            done.record(comm)
+        packs[J] = (pack, done)
+
+    post(0)
+    for J in range(nblk):
+        j0, jend, kw, nd, d0 = geometry(J)
+        pack, done = packs.pop(J)
+        main.wait_event(done)
+        if J % world != rank:
             A[j0:, j0:jend].copy_(pack[: (N - j0) * kw].view(N - j0, kw))
             dinv[0, d0:d0 + nd].copy_(pack[(N - j0) * kw: (N - j0) * kw + nd])
             info.copy_(torch.maximum(info, pack[-1:].to(torch.int32)))
-        # rank-kw update of the block columns this rank owns to the right of J
-        for Jp in range(J + 1, nblk):
-            if Jp % world != rank:
-                continue
-            c0 = Jp * OUTER_BLOCK
-            c1 = min(N, c0 + OUTER_BLOCK)
-            nv.dgemm(N - c0, c1 - c0, kw, -1.0, A, c0 * lda + j0, lda, 1, A, c0 * lda + j0, 1, lda, 1.0,
-                     A, c0 * lda + c0, lda, 1, flags=nv.GEMM_LOWER)
+        if J + 1 < nblk:
+            if (J + 1) % world == rank:
+                update(J, J + 1)
+            post(J + 1)
+        for Jp in range(J + 2, nblk):
+            if Jp % world == rank:
+                update(J, Jp)
+        del pack
     return dinv, info
 
 
-def potrs(Lfac, dinv, B, batch=1, first_row=0):
+def potrs(Lfac, dinv, B, batch=1, first_row=0, lower_only=False):
     """Solve in place: B is (batch, N, nrhs) or (N, nrhs), contiguous.  ``first_row``: rows of B above
-    it are known to be zero (identity columns), the forward substitution starts there."""
+    it are known to be zero (identity columns), the forward substitution starts there; with
+    ``lower_only`` the rows of the solution above ``first_row`` are not computed either (left zero)."""
     L = nv.lib()
     N = int(Lfac.shape[-1])
     nrhs = int(B.shape[-1])
@@ -112,7 +159,8 @@ def potrs(Lfac, dinv, B, batch=1, first_row=0):
     sb = int(B.stride(0)) if B.dim() == 3 else 0
     work = nv.empty(batch, N, nrhs)
     nv.check(L.pmr_potrs(nv.ptr(Lfac), N, lda, batch, sl, nv.ptr(dinv), nv.ptr(B), nrhs,
-                         int(B.stride(-2)), sb, int(first_row), nv.ptr(work), nv.stream_ptr()))
+                         int(B.stride(-2)), sb, int(first_row), int(bool(lower_only)), nv.ptr(work),
+                         nv.stream_ptr()))
     return B
 
 
@@ -229,9 +277,11 @@ class HalfSizeSystem:
     def _kinv_distributed(self, Kfac, dinvK):
         """K^-1 with the work split over the ranks: every rank solves K X = E_J for its own identity
         columns against the shared factor and the column blocks are all-gathered (N^2 * 8 bytes in
-        total over NVLink).  The forward substitution of a column block starting at column c skips
-        the (zero) rows above c, so the columns are cut into 2*world blocks and rank r takes blocks r
-        and 2*world-1-r: the cheap late block balances the expensive early one."""
+        total over NVLink).  Only the lower triangle of the result is filled (its one consumer, the
+        Cholesky of S(w) = M - w^2 K^-1, reads nothing else; the rest is zero): for a column block
+        starting at column c both substitutions skip the rows above c, costing (1-c/N)^2 + 1-(c/N)^2
+        in units of N^2 w flops, so the columns are cut into 2*world blocks and rank r takes blocks r
+        and 2*world-1-r, which sums to the same work on every rank."""
         from pymolresponse_b200 import distributed as pd
 
         rank, world = pd.rank_world()
@@ -247,7 +297,7 @@ class HalfSizeSystem:
                 continue
             rhs = nv.zeros(N, w)
             shift_diagonal(rhs, w, 1.0, offset=lo * w)
-            potrs(Kfac, dinvK, rhs, first_row=(lo // 128) * 128)
+            potrs(Kfac, dinvK, rhs, first_row=(lo // 128) * 128, lower_only=True)
             local[:, k * wmax:k * wmax + w].copy_(rhs)
         gathered = pd.allgather_columns(local, 2 * wmax * world)   # equal widths per rank
         Kinv = nv.empty(N, N)

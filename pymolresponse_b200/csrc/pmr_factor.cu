@@ -541,7 +541,8 @@ extern "C" int pmr_potrf_panel(double* A, int N, long long lda, int j0, double* 
 
 extern "C" int pmr_potrs(const double* L, int N, long long lda, int batch, long long stride_l,
                          const double* dinv, double* B, int nrhs, long long ldb,
-                         long long stride_b, int first_row, double* work, void* stream) {
+                         long long stride_b, int first_row, int lower_only, double* work,
+                         void* stream) {
   cudaStream_t st = as_stream(stream);
   PMR_REQUIRE(N >= 0 && nrhs >= 0 && batch >= 1 && batch <= 65535, "potrs: bad sizes");
   if (N == 0 || nrhs == 0) return 0;
@@ -558,32 +559,64 @@ extern "C" int pmr_potrs(const double* L, int N, long long lda, int batch, long 
     for (int b = 0; b < batch; ++b)
       PMR_CHECK_CUDA(cudaMemsetAsync(work + (long long)b * wstride, 0,
                                      sizeof(double) * (size_t)kb0 * NB * nrhs, st));
-  for (int kb = kb0; kb < nblk; ++kb) {
-    const int k0 = kb * NB, jb = std::min(NB, N - k0), rest = N - k0 - jb;
-    const double* dk = dinv + (long long)kb * NB * NB;
-    pmr_gemm_t g = make_gemm(jb, nrhs, jb, 1.0, dk, NB, 1, B + (long long)k0 * ldb, ldb, 1, 0.0,
-                             work + (long long)k0 * nrhs, nrhs, 1);
-    g.batch1 = batch; g.a_b1 = dstride; g.b_b1 = stride_b; g.c_b1 = wstride;
-    PMR_TRY(gemm(g, st));
-    if (rest > 0) {
-      pmr_gemm_t u = make_gemm(rest, nrhs, jb, -1.0, L + (long long)(k0 + jb) * lda + k0, lda, 1,
-                               work + (long long)k0 * nrhs, nrhs, 1, 1.0,
-                               B + (long long)(k0 + jb) * ldb, ldb, 1);
+  // Both substitutions run in chunks of NBO rows: inside a chunk the 128-row blocks are solved one
+  // after the other with small in-chunk updates, then ONE rank-NBO update carries the chunk into
+  // the rest of the right-hand side (k = 512 keeps the DMMA pipeline full; k = 128 did not).
+  constexpr int NBO = 512;
+  const int cb0 = (kb0 * NB) / NBO;
+  for (int c0 = cb0 * NBO; c0 < N; c0 += NBO) {
+    const int cend = std::min(N, c0 + NBO);
+    for (int k0 = std::max(c0, kb0 * NB); k0 < cend; k0 += NB) {
+      const int jb = std::min(NB, N - k0), inrest = cend - k0 - jb;
+      const double* dk = dinv + (long long)(k0 / NB) * NB * NB;
+      pmr_gemm_t g = make_gemm(jb, nrhs, jb, 1.0, dk, NB, 1, B + (long long)k0 * ldb, ldb, 1, 0.0,
+                               work + (long long)k0 * nrhs, nrhs, 1);
+      g.batch1 = batch; g.a_b1 = dstride; g.b_b1 = stride_b; g.c_b1 = wstride;
+      PMR_TRY(gemm(g, st));
+      if (inrest > 0) {
+        pmr_gemm_t u = make_gemm(inrest, nrhs, jb, -1.0, L + (long long)(k0 + jb) * lda + k0, lda, 1,
+                                 work + (long long)k0 * nrhs, nrhs, 1, 1.0,
+                                 B + (long long)(k0 + jb) * ldb, ldb, 1);
+        u.batch1 = batch; u.a_b1 = stride_l; u.b_b1 = wstride; u.c_b1 = stride_b;
+        PMR_TRY(gemm(u, st));
+      }
+    }
+    if (cend < N) {
+      const int kfirst = std::max(c0, kb0 * NB);   // rows of Y above it are zero
+      pmr_gemm_t u = make_gemm(N - cend, nrhs, cend - kfirst, -1.0,
+                               L + (long long)cend * lda + kfirst, lda, 1,
+                               work + (long long)kfirst * nrhs, nrhs, 1, 1.0,
+                               B + (long long)cend * ldb, ldb, 1);
       u.batch1 = batch; u.a_b1 = stride_l; u.b_b1 = wstride; u.c_b1 = stride_b;
       PMR_TRY(gemm(u, st));
     }
   }
-  // backward: L^T X = Y, X -> B
-  for (int kb = nblk - 1; kb >= 0; --kb) {
-    const int k0 = kb * NB, jb = std::min(NB, N - k0);
-    const double* dk = dinv + (long long)kb * NB * NB;
-    pmr_gemm_t g = make_gemm(jb, nrhs, jb, 1.0, dk, 1, NB, work + (long long)k0 * nrhs, nrhs, 1,
-                             0.0, B + (long long)k0 * ldb, ldb, 1);
-    g.batch1 = batch; g.a_b1 = dstride; g.b_b1 = wstride; g.c_b1 = stride_b;
-    PMR_TRY(gemm(g, st));
-    if (k0 > 0) {
-      pmr_gemm_t u = make_gemm(k0, nrhs, jb, -1.0, L + (long long)k0 * lda, 1, lda,
-                               B + (long long)k0 * ldb, ldb, 1, 1.0, work, nrhs, 1);
+  // backward: L^T X = Y, X -> B.  With lower_only the rows above first_row (rounded down to a
+  // block) are not wanted (a symmetric result whose upper part nobody reads) and stay zero.
+  const int r0 = lower_only ? kb0 * NB : 0;
+  const int nchunk = (N + NBO - 1) / NBO;
+  for (int cb = nchunk - 1; cb >= r0 / NBO; --cb) {
+    const int c0 = std::max(cb * NBO, r0), cend = std::min(N, cb * NBO + NBO);
+    const int klast = ((cend - 1) / NB) * NB;
+    for (int k0 = klast; k0 >= c0; k0 -= NB) {
+      const int jb = std::min(NB, N - k0);
+      const double* dk = dinv + (long long)(k0 / NB) * NB * NB;
+      pmr_gemm_t g = make_gemm(jb, nrhs, jb, 1.0, dk, 1, NB, work + (long long)k0 * nrhs, nrhs, 1,
+                               0.0, B + (long long)k0 * ldb, ldb, 1);
+      g.batch1 = batch; g.a_b1 = dstride; g.b_b1 = wstride; g.c_b1 = stride_b;
+      PMR_TRY(gemm(g, st));
+      if (k0 > c0) {
+        pmr_gemm_t u = make_gemm(k0 - c0, nrhs, jb, -1.0, L + (long long)k0 * lda + c0, 1, lda,
+                                 B + (long long)k0 * ldb, ldb, 1, 1.0,
+                                 work + (long long)c0 * nrhs, nrhs, 1);
+        u.batch1 = batch; u.a_b1 = stride_l; u.b_b1 = stride_b; u.c_b1 = wstride;
+        PMR_TRY(gemm(u, st));
+      }
+    }
+    if (c0 > r0) {
+      pmr_gemm_t u = make_gemm(c0 - r0, nrhs, cend - c0, -1.0, L + (long long)c0 * lda + r0, 1, lda,
+                               B + (long long)c0 * ldb, ldb, 1, 1.0,
+                               work + (long long)r0 * nrhs, nrhs, 1);
       u.batch1 = batch; u.a_b1 = stride_l; u.b_b1 = stride_b; u.c_b1 = wstride;
       PMR_TRY(gemm(u, st));
     }

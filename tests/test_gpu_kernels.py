@@ -193,6 +193,11 @@ def test_potrs_identity_columns_skip_zero_rows(n, lo, w):
     fast = nv.to_host(eng.potrs(Ad, dinv, nv.to_dev(E).clone(), first_row=(lo // 128) * 128))
     assert np.array_equal(full, fast)
     assert np.abs(fast - np.linalg.inv(A)[:, lo:lo + w]).max() <= 1e-11 * n
+    # lower_only: the rows above the block are left zero, the rest is unchanged
+    r0 = (lo // 128) * 128
+    low = nv.to_host(eng.potrs(Ad, dinv, nv.to_dev(E).clone(), first_row=r0, lower_only=True))
+    assert np.array_equal(low[r0:], full[r0:])
+    assert not low[:r0].any()
 
 
 def test_dgemm_in_place_panel_update():

@@ -241,6 +241,20 @@ int pmr_cphf_update(double* x, const double* x_old, const double* rhs, const dou
                     int init /* 1: x = uncoupled guess rhs/(+-(e_a-e_i-w)), solvers.py:606-611 */,
                     double* maxdiff /* device, ncomp */, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * AO ERI upload exploiting the 8-fold permutational symmetry (host buffer in, full tensor in HBM).
+ * Replaces the plain host->device copy of the (n,n,n,n) tensor the reference hands to
+ * AO2MO.__init__ (pymolresponse/ao2mo.py:18-33; the tensors come from pyscf int2e / psi4 ao_eri,
+ * solvers.py:86-127, and always carry this symmetry).
+ *   pmr_eri_s8_bytes     bytes that cross PCIe for basis size n (about n^4 * 8 / 3)
+ *   pmr_eri_upload_s8    for each mu: rows (mu, 0..mu), columns up to (mu, mu), one strided DMA;
+ *                        host: full C-order (n,n,n,n) array (pinned for an asynchronous copy)
+ *   pmr_eri_complete_s8  fills the rest of the tensor in place from the uploaded part
+ * ------------------------------------------------------------------------------------------ */
+long long pmr_eri_s8_bytes(int n);
+int pmr_eri_upload_s8(const double* host, double* dev, int n, void* stream);
+int pmr_eri_complete_s8(double* dev, int n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -108,6 +108,9 @@ SYMBOLS = {
     "pmr_shift_diagonal": (C.c_int, [c_dp, C.c_int, c_ll, C.c_double, c_dp]),
     "pmr_cphf_update": (C.c_int, [c_dp, c_dp, c_dp, c_dp, c_dp, C.c_double, C.c_int, C.c_int,
                                   C.c_int, C.c_int, c_dp, c_dp]),
+    "pmr_eri_s8_bytes": (c_ll, [C.c_int]),
+    "pmr_eri_upload_s8": (C.c_int, [c_dp, c_dp, C.c_int, c_dp]),
+    "pmr_eri_complete_s8": (C.c_int, [c_dp, C.c_int, c_dp]),
     "pmr_getrf": (C.c_int, [c_dp, C.c_int, c_ll, c_dp, c_dp, c_dp, c_dp]),
     "pmr_getrf_work_doubles": (c_ll, [C.c_int]),
     "pmr_getrs": (C.c_int, [c_dp, C.c_int, c_ll, c_dp, c_dp, C.c_int, c_ll, c_dp, c_dp]),
@@ -200,6 +203,22 @@ def to_dev(x, dtype=None):
         arr = np.ascontiguousarray(np.asarray(x))
         t = torch.from_numpy(arr).to(device=device(), dtype=dtype)
     return t.contiguous()
+
+
+def upload_eri_s8(I):  # noqa: E741
+    """Host (n,n,n,n) AO ERI tensor with 8-fold permutational symmetry -> full CUDA tensor; only the
+    unique part (about a third of the doubles) crosses PCIe, the rest is rebuilt in HBM
+    (pmr_eri_upload_s8 / pmr_eri_complete_s8).  The caller vouches for the symmetry."""
+    torch = torch_mod()
+    arr = np.ascontiguousarray(np.asarray(I), dtype=np.float64)
+    assert arr.ndim == 4 and len(set(arr.shape)) == 1, "the s8 upload needs the whole (n,n,n,n) tensor"
+    n = int(arr.shape[0])
+    dev = empty(n, n, n, n)
+    L = lib()
+    check(L.pmr_eri_upload_s8(C.c_void_p(arr.ctypes.data), ptr(dev), n, stream_ptr()))
+    check(L.pmr_eri_complete_s8(ptr(dev), n, stream_ptr()))
+    torch.cuda.current_stream().synchronize()   # the host buffer may be reused by the caller
+    return dev
 
 
 def to_host(t) -> np.ndarray:

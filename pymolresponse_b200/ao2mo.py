@@ -15,6 +15,10 @@ same length, order, shapes and C-order layout.  Differences, all additive:
   second index of the first AO pair; with ``reduce=True`` the blocks are completed across the
   ``torch.distributed`` ranks (all-reduce of (ia|jb); reduce-scatter / finish / all-gather for
   (ij|ab)), otherwise they are this slab's partial sums.
+* ``ao_symmetry="s8"``: the caller states that a host-side ``I`` has the 8-fold permutational
+  symmetry of real-orbital ERIs (what pyscf ``int2e`` and psi4 ``ao_eri`` return); only its unique
+  part is copied to the GPU and the tensor is completed in HBM.  The default ``"s1"`` copies the
+  whole array and assumes nothing.
 """
 
 from __future__ import annotations
@@ -112,7 +116,7 @@ class AO2MO:
 
     def __init__(self, C, occupations, I=None, *, device_results: bool = False,  # noqa: E741
                  nu_range: tuple[int, int] | None = None, nu_block: int = 0,
-                 reduce: bool = False) -> None:
+                 reduce: bool = False, ao_symmetry: str = "s1") -> None:
         self.C = fix_mocoeffs_shape(C) if not nv.is_device_array(C) else (C if C.dim() == 3 else C[None])
         self.occupations = occupations
         self.I = I
@@ -122,6 +126,8 @@ class AO2MO:
         self.nu_range = nu_range
         self.nu_block = nu_block
         self.reduce = reduce  # complete the blocks over torch.distributed ranks (nu-sharded I)
+        assert ao_symmetry in ("s1", "s8")
+        self.ao_symmetry = ao_symmetry
 
     # ------------------------------------------------------------------ helpers
     def _out(self, tensors):
@@ -131,6 +137,9 @@ class AO2MO:
 
     def _I_dev(self):
         assert self.I is not None
+        if (self.ao_symmetry == "s8" and self.nu_range is None
+                and not nv.is_device_array(self.I)):
+            return nv.upload_eri_s8(self.I)
         I = nv.to_dev(self.I)
         assert I.dim() == 4
         return I

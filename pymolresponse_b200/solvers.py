@@ -67,6 +67,8 @@ class Solver(ABC):
         self._lazy_hessian = None
         # keep response vectors on the device as torch tensors instead of NumPy arrays
         self.device_results = False
+        # "s8": form_tei_mo may assume the 8-fold symmetry of the AO ERI tensor (see ao2mo.py)
+        self.ao_symmetry = "s1"
 
     # ---------------------------------------------------------------- MO integrals
     explicit_hessian = None
@@ -114,7 +116,8 @@ class Solver(ABC):
             )
         else:
             raise RuntimeError
-        ao2mo = AO2MO(self.mocoeffs, self.occupations, I=I, device_results=True)
+        ao2mo = AO2MO(self.mocoeffs, self.occupations, I=I, device_results=True,
+                      ao_symmetry=self.ao_symmetry)
         if tei_mo_type == AO2MOTransformationType.partial and nden == 2:
             ao2mo.perform_uhf_partial()
         elif tei_mo_type == AO2MOTransformationType.partial and nden == 1:

@@ -190,7 +190,7 @@ def build_inputs(w, rank, world, torch):
         # (nu mu| independently), so that the resident and the end-to-end paths see the same tensor
         from pymolresponse_b200 import _native as nv
 
-        nv.check(nv.lib().pmr_eri_complete_s8(nv.ptr(I), n, nv.stream_ptr()))
+        nv.check(nv.lib().pmr_eri_complete_s8(nv.ptr(I), n, 0, nv.stream_ptr()))
         torch.cuda.synchronize()
     C = synthetic.mo_coefficients(n, synthetic.SEED_ALPHA)[None]
     E = np.diag(synthetic.orbital_energies(n, o, synthetic.SEED_ALPHA))[None]
@@ -471,10 +471,10 @@ def run_ours(args):
             # tensor crosses PCIe, the rest is rebuilt in HBM (pmr_eri_upload_s8/_complete_s8)
             ms_e = timed_e2e("s8")
             e2e = {"value": F / (ms_e * 1e-3) / 1e12, "unit": UNIT, "ms_per_step": ms_e,
-                   "h2d_bytes_per_step": int(lib.pmr_eri_s8_bytes(n)) + int(small),
+                   "h2d_bytes_per_step": int(lib.pmr_eri_s8_bytes(n, nv.ERI_S8_LAYOUT)) + int(small),
                    "d2h_bytes_per_step": int(d2h), "pinned_host_input": bool(I_host_t.is_pinned()),
-                   "upload": "8-fold-unique part of the AO ERI array (ao_symmetry='s8'), completed "
-                             "on the device",
+                   "upload": "permutationally unique part of the AO ERI array (ao_symmetry='s8': "
+                             "mu >= la >= si, a sixth of the tensor), completed on the device",
                    "whole_array_upload": full}
         else:
             e2e = full

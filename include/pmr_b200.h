@@ -246,14 +246,18 @@ int pmr_cphf_update(double* x, const double* x_old, const double* rhs, const dou
  * Replaces the plain host->device copy of the (n,n,n,n) tensor the reference hands to
  * AO2MO.__init__ (pymolresponse/ao2mo.py:18-33; the tensors come from pyscf int2e / psi4 ao_eri,
  * solvers.py:86-127, and always carry this symmetry).
- *   pmr_eri_s8_bytes     bytes that cross PCIe for basis size n (about n^4 * 8 / 3)
- *   pmr_eri_upload_s8    for each mu: rows (mu, 0..mu), columns up to (mu, mu), one strided DMA;
+ * layout 0 ("row prefix", ~n^4/3 doubles): for each mu the rows (mu, 0..mu), columns up to
+ *   (mu, mu) -- long contiguous runs;  layout 1 ("box", ~n^4/6 doubles): for each la the entries
+ *   (mu >= la, nu | la, si <= la) -- half the bytes in runs of (la+1) doubles.
+ *   pmr_eri_s8_bytes     bytes that cross PCIe for basis size n
+ *   pmr_eri_upload_s8    one strided DMA per mu (layout 0) / per la (layout 1);
  *                        host: full C-order (n,n,n,n) array (pinned for an asynchronous copy)
  *   pmr_eri_complete_s8  fills the rest of the tensor in place from the uploaded part
  * ------------------------------------------------------------------------------------------ */
-long long pmr_eri_s8_bytes(int n);
-int pmr_eri_upload_s8(const double* host, double* dev, int n, void* stream);
-int pmr_eri_complete_s8(double* dev, int n, void* stream);
+void pmr_set_upload_streams(int count); /* side streams the layout-1 DMAs are spread over (1..8) */
+long long pmr_eri_s8_bytes(int n, int layout);
+int pmr_eri_upload_s8(const double* host, double* dev, int n, int layout, void* stream);
+int pmr_eri_complete_s8(double* dev, int n, int layout, void* stream);
 
 #ifdef __cplusplus
 }

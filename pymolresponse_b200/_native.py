@@ -108,9 +108,10 @@ SYMBOLS = {
     "pmr_shift_diagonal": (C.c_int, [c_dp, C.c_int, c_ll, C.c_double, c_dp]),
     "pmr_cphf_update": (C.c_int, [c_dp, c_dp, c_dp, c_dp, c_dp, C.c_double, C.c_int, C.c_int,
                                   C.c_int, C.c_int, c_dp, c_dp]),
-    "pmr_eri_s8_bytes": (c_ll, [C.c_int]),
-    "pmr_eri_upload_s8": (C.c_int, [c_dp, c_dp, C.c_int, c_dp]),
-    "pmr_eri_complete_s8": (C.c_int, [c_dp, C.c_int, c_dp]),
+    "pmr_set_upload_streams": (None, [C.c_int]),
+    "pmr_eri_s8_bytes": (c_ll, [C.c_int, C.c_int]),
+    "pmr_eri_upload_s8": (C.c_int, [c_dp, c_dp, C.c_int, C.c_int, c_dp]),
+    "pmr_eri_complete_s8": (C.c_int, [c_dp, C.c_int, C.c_int, c_dp]),
     "pmr_getrf": (C.c_int, [c_dp, C.c_int, c_ll, c_dp, c_dp, c_dp, c_dp]),
     "pmr_getrf_work_doubles": (c_ll, [C.c_int]),
     "pmr_getrs": (C.c_int, [c_dp, C.c_int, c_ll, c_dp, c_dp, C.c_int, c_ll, c_dp, c_dp]),
@@ -205,18 +206,24 @@ def to_dev(x, dtype=None):
     return t.contiguous()
 
 
-def upload_eri_s8(I):  # noqa: E741
-    """Host (n,n,n,n) AO ERI tensor with 8-fold permutational symmetry -> full CUDA tensor; only the
-    unique part (about a third of the doubles) crosses PCIe, the rest is rebuilt in HBM
-    (pmr_eri_upload_s8 / pmr_eri_complete_s8).  The caller vouches for the symmetry."""
+# 1 ("box", a sixth of the tensor, 160 + 19 ms at n = 256) beats 0 ("row prefix", a third, 208 + 11 ms)
+ERI_S8_LAYOUT = int(os.environ.get("PMR_ERI_S8_LAYOUT", "1"))
+
+
+def upload_eri_s8(I, layout=None):  # noqa: E741
+    """Host (n,n,n,n) AO ERI tensor with 8-fold permutational symmetry -> full CUDA tensor; only a
+    unique part (a third or a sixth of the doubles, see include/pmr_b200.h) crosses PCIe, the rest
+    is rebuilt in HBM (pmr_eri_upload_s8 / pmr_eri_complete_s8).  The caller vouches for the
+    symmetry."""
     torch = torch_mod()
+    layout = ERI_S8_LAYOUT if layout is None else int(layout)
     arr = np.ascontiguousarray(np.asarray(I), dtype=np.float64)
     assert arr.ndim == 4 and len(set(arr.shape)) == 1, "the s8 upload needs the whole (n,n,n,n) tensor"
     n = int(arr.shape[0])
     dev = empty(n, n, n, n)
     L = lib()
-    check(L.pmr_eri_upload_s8(C.c_void_p(arr.ctypes.data), ptr(dev), n, stream_ptr()))
-    check(L.pmr_eri_complete_s8(ptr(dev), n, stream_ptr()))
+    check(L.pmr_eri_upload_s8(C.c_void_p(arr.ctypes.data), ptr(dev), n, layout, stream_ptr()))
+    check(L.pmr_eri_complete_s8(ptr(dev), n, layout, stream_ptr()))
     torch.cuda.current_stream().synchronize()   # the host buffer may be reused by the caller
     return dev
 

@@ -9,6 +9,13 @@
 //   A. row mirror:       row (nu, mu) <- row (mu, nu), nu < mu, over the uploaded prefix;
 //   B. transpose mirror: entry (Q, P) <- entry (P, Q), Q < P (64x64 tiles through shared memory).
 // After A every row P holds at least its columns Q <= P, so B reads only defined entries.
+//
+// layout 1 ("box", about a sixth of the doubles): for every la one strided DMA of the entries
+// (mu >= la, all nu | la, si <= la); completion in three passes, m(P) = max(mu, nu):
+//   1. in every uploaded row (mu, nu): (si, la) <- (la, si) for si < la <= mu;
+//   2. row (mu, nu), mu < nu  <-  row (nu, mu), columns (la, si) in [0, nu]^2;
+//      now every row P holds the columns Q with m(Q) <= m(P);
+//   3. entry (P, Q) with m(Q) > m(P)  <-  entry (Q, P)   (64x64 tiles through shared memory).
 #include <algorithm>
 
 #include "pmr_common.cuh"
@@ -55,20 +62,136 @@ __global__ void __launch_bounds__(256) eri_transpose_mirror_kernel(double* __res
   }
 }
 
+// ---- layout 1 -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) eri_box_pass1_kernel(double* __restrict__ I, int n) {
+  // one block per row (mu, nu): symmetrise the leading (mu+1)^2 block of its n x n matrix
+  const int mu = blockIdx.y, nu = blockIdx.x;
+  double* row = I + ((long long)mu * n + nu) * (long long)n * n;
+  const int m = mu + 1;
+  for (int idx = threadIdx.x; idx < m * m; idx += 256) {
+    const int si = idx / m, la = idx - si * m;       // destination (si, la): write coalesced in la
+    if (la > si) row[(long long)si * n + la] = row[(long long)la * n + si];
+  }
+}
+
+__global__ void __launch_bounds__(256) eri_box_pass2_kernel(double* __restrict__ I, int n) {
+  // row (mu, nu) with mu < nu  <-  row (nu, mu) on the block [0, nu]^2
+  const int mu = blockIdx.y, nu = blockIdx.x;
+  if (mu >= nu) return;
+  const long long n2 = (long long)n * n;
+  const double* src = I + ((long long)nu * n + mu) * n2;
+  double* dst = I + ((long long)mu * n + nu) * n2;
+  const int m = nu + 1;
+  for (int idx = threadIdx.x; idx < m * m; idx += 256) {
+    const int la = idx / m, si = idx - la * m;
+    dst[(long long)la * n + si] = src[(long long)la * n + si];
+  }
+}
+
+__device__ __forceinline__ int pair_max(long long P, int n) {
+  const int a = (int)(P / n), b = (int)(P - (long long)a * n);
+  return a > b ? a : b;
+}
+
+__global__ void __launch_bounds__(256) eri_box_pass3_kernel(double* __restrict__ I, int n,
+                                                            long long P) {
+  // destination tile (rows r0.., cols c0..): entries with m(col) > m(row) take the transposed one
+  __shared__ double tile[TT][TT + 1];
+  const long long r0 = (long long)blockIdx.y * TT, c0 = (long long)blockIdx.x * TT;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  // any work in this tile?  (the largest m over its columns against the smallest over its rows)
+  const long long cc = c0 + tx;
+  const int mcol = cc < P ? pair_max(cc, n) : -1;
+  int any = 0;
+#pragma unroll 4
+  for (int r = ty; r < TT; r += 4) {
+    const long long rr = r0 + r;
+    if (rr < P && mcol > pair_max(rr, n)) any = 1;
+  }
+  if (!__syncthreads_or(any)) return;
+#pragma unroll 4
+  for (int r = ty; r < TT; r += 4) {
+    const long long sr = c0 + r, sc = r0 + tx;       // source tile = transposed position
+    if (sr < P && sc < P) tile[r][tx] = I[sr * P + sc];
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (int r = ty; r < TT; r += 4) {
+    const long long rr = r0 + r;
+    if (rr < P && cc < P && mcol > pair_max(rr, n)) I[rr * P + cc] = tile[tx][r];
+  }
+}
+
 }  // namespace
 
-extern "C" long long pmr_eri_s8_bytes(int n) {
+extern "C" long long pmr_eri_s8_bytes(int n, int layout) {
   long long total = 0;
-  for (long long mu = 0; mu < n; ++mu) total += (mu + 1) * (mu * n + mu + 1) * 8;
+  if (layout == 1) {
+    for (long long la = 0; la < n; ++la) total += (n - la) * n * (la + 1) * 8;
+  } else {
+    for (long long mu = 0; mu < n; ++mu) total += (mu + 1) * (mu * n + mu + 1) * 8;
+  }
   return total;
 }
 
-extern "C" int pmr_eri_upload_s8(const double* host, double* dev, int n, void* stream) {
+// Narrow strided rows cost a fixed time per row on top of the bytes (measured on B200, n = 256:
+// 5.79 GB in 160 ms = 36 GB/s against 55 GB/s for long runs).  The DMAs can be spread over side
+// streams (pmr_set_upload_streams); measured 1..8 streams: no gain, the limit is the PCIe read
+// of short host rows, not the copy engine -- so the default is the caller's stream alone.
+constexpr int kMaxUploadStreams = 8;
+static int g_upload_streams = 1;
+
+struct UploadStreams {
+  cudaStream_t s[kMaxUploadStreams] = {};
+  cudaEvent_t fork = nullptr, join[kMaxUploadStreams] = {};
+  int device = -1;
+};
+static thread_local UploadStreams g_up;
+
+static int upload_streams_ready() {
+  int dev = 0;
+  PMR_CHECK_CUDA(cudaGetDevice(&dev));
+  if (g_up.device == dev) return 0;
+  for (int i = 0; i < kMaxUploadStreams; ++i) {
+    PMR_CHECK_CUDA(cudaStreamCreateWithFlags(&g_up.s[i], cudaStreamNonBlocking));
+    PMR_CHECK_CUDA(cudaEventCreateWithFlags(&g_up.join[i], cudaEventDisableTiming));
+  }
+  PMR_CHECK_CUDA(cudaEventCreateWithFlags(&g_up.fork, cudaEventDisableTiming));
+  g_up.device = dev;
+  return 0;
+}
+
+extern "C" void pmr_set_upload_streams(int count) {
+  g_upload_streams = std::max(1, std::min(kMaxUploadStreams, count));
+}
+
+extern "C" int pmr_eri_upload_s8(const double* host, double* dev, int n, int layout, void* stream) {
   cudaStream_t st = as_stream(stream);
-  PMR_REQUIRE(n >= 0, "eri_upload_s8: bad n");
+  PMR_REQUIRE(n >= 0 && (layout == 0 || layout == 1), "eri_upload_s8: bad n or layout");
   if (n == 0) return 0;
   PMR_REQUIRE(host && dev, "eri_upload_s8: null pointer");
   const size_t n2 = (size_t)n * n;
+  if (layout == 1) {
+    const int ns = g_upload_streams;
+    if (ns > 1) {
+      PMR_TRY(upload_streams_ready());
+      PMR_CHECK_CUDA(cudaEventRecord(g_up.fork, st));
+      for (int i = 0; i < ns; ++i) PMR_CHECK_CUDA(cudaStreamWaitEvent(g_up.s[i], g_up.fork, 0));
+    }
+    for (size_t la = 0; la < (size_t)n; ++la) {
+      const size_t off = la * n * n2 + la * n;        // row (la, 0), column (la, 0)
+      cudaStream_t cs = ns > 1 ? g_up.s[la % ns] : st;
+      PMR_CHECK_CUDA(cudaMemcpy2DAsync(dev + off, n2 * sizeof(double), host + off,
+                                       n2 * sizeof(double), (la + 1) * sizeof(double),
+                                       (n - la) * n, cudaMemcpyHostToDevice, cs));
+    }
+    if (ns > 1)
+      for (int i = 0; i < ns; ++i) {
+        PMR_CHECK_CUDA(cudaEventRecord(g_up.join[i], g_up.s[i]));
+        PMR_CHECK_CUDA(cudaStreamWaitEvent(st, g_up.join[i], 0));
+      }
+    return 0;
+  }
   for (size_t mu = 0; mu < (size_t)n; ++mu) {
     const size_t width = (mu * n + mu + 1) * sizeof(double);
     const size_t off = mu * n * n2;
@@ -78,19 +201,31 @@ extern "C" int pmr_eri_upload_s8(const double* host, double* dev, int n, void* s
   return 0;
 }
 
-extern "C" int pmr_eri_complete_s8(double* dev, int n, void* stream) {
+extern "C" int pmr_eri_complete_s8(double* dev, int n, int layout, void* stream) {
   cudaStream_t st = as_stream(stream);
-  PMR_REQUIRE(n >= 0 && n <= 2047, "eri_complete_s8: n out of range");
+  PMR_REQUIRE(n >= 0 && n <= 2047 && (layout == 0 || layout == 1),
+              "eri_complete_s8: n out of range or bad layout");
   if (n <= 0) return 0;
   PMR_REQUIRE(dev, "eri_complete_s8: null pointer");
   const long long P = (long long)n * n;
+  const unsigned nt = (unsigned)((P + TT - 1) / TT);
+  if (layout == 1) {
+    if (n > 1) {
+      eri_box_pass1_kernel<<<dim3(n, n), 256, 0, st>>>(dev, n);
+      PMR_CHECK_LAUNCH("eri_box_pass1_kernel");
+      eri_box_pass2_kernel<<<dim3(n, n), 256, 0, st>>>(dev, n);
+      PMR_CHECK_LAUNCH("eri_box_pass2_kernel");
+    }
+    eri_box_pass3_kernel<<<dim3(nt, nt), 256, 0, st>>>(dev, n, P);
+    PMR_CHECK_LAUNCH("eri_box_pass3_kernel");
+    return 0;
+  }
   if (n > 1) {
     const long long wmax = (long long)(n - 1) * n + n;
     dim3 grid((unsigned)((wmax + 2047) / 2048), (unsigned)n, (unsigned)n);
     eri_row_mirror_kernel<<<grid, 256, 0, st>>>(dev, n);
     PMR_CHECK_LAUNCH("eri_row_mirror_kernel");
   }
-  const unsigned nt = (unsigned)((P + TT - 1) / TT);
   eri_transpose_mirror_kernel<<<dim3(nt, nt), 256, 0, st>>>(dev, P);
   PMR_CHECK_LAUNCH("eri_transpose_mirror_kernel");
   return 0;

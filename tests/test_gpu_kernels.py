@@ -332,20 +332,23 @@ def _symmetric_eri(n, seed):
     return np.ascontiguousarray(T)
 
 
+@pytest.mark.parametrize("layout", [0, 1])
 @pytest.mark.parametrize("n", [1, 2, 7, 13, 32])
-def test_eri_upload_s8_rebuilds_the_full_tensor(n):
-    """Only rows (mu, nu <= mu), columns <= (mu, mu) are read from the host (everything else is
-    poisoned with NaN here); the completed tensor in HBM equals the symmetric original bit for bit."""
+def test_eri_upload_s8_rebuilds_the_full_tensor(n, layout):
+    """Only the documented unique part is read from the host (everything else is poisoned with NaN
+    here); the completed tensor in HBM equals the symmetric original bit for bit."""
     nv = _nv()
     T = _symmetric_eri(n, 41)
-    H = T.reshape(n, n, n * n).copy()
-    read = 0
-    for mu in range(n):
-        H[mu, mu + 1:, :] = np.nan
-        H[mu, :, mu * n + mu + 1:] = np.nan
-        read += (mu + 1) * (mu * n + mu + 1) * 8
-    assert int(nv.lib().pmr_eri_s8_bytes(n)) == read
-    got = nv.to_host(nv.upload_eri_s8(H.reshape(n, n, n, n)))
+    keep = np.zeros((n, n, n, n), dtype=bool)
+    if layout == 0:       # rows (mu, nu <= mu), columns up to (mu, mu)
+        for mu in range(n):
+            keep[mu, :mu + 1].reshape(mu + 1, n * n)[:, :mu * n + mu + 1] = True
+    else:                 # (mu >= la, nu | la, si <= la)
+        for la in range(n):
+            keep[la:, :, la, :la + 1] = True
+    assert int(nv.lib().pmr_eri_s8_bytes(n, layout)) == 8 * int(keep.sum())
+    H = np.where(keep, T, np.nan)
+    got = nv.to_host(nv.upload_eri_s8(H, layout=layout))
     assert np.array_equal(got, T)
 
 

@@ -28,7 +28,8 @@ typedef enum {
   PMR_OK = 0,
   PMR_ERR_ARG = -1,      /* bad argument (shape / stride / null pointer) */
   PMR_ERR_CUDA = -2,     /* CUDA runtime error (launch, attribute, ...)   */
-  PMR_ERR_WORKSPACE = -3 /* workspace too small                           */
+  PMR_ERR_WORKSPACE = -3,/* workspace too small                           */
+  PMR_ERR_CONVERGENCE = -4 /* an iterative kernel driver hit its sweep limit */
 } pmr_status;
 
 int pmr_version(void);
@@ -258,6 +259,28 @@ void pmr_set_upload_streams(int count); /* side streams the layout-1 DMAs are sp
 long long pmr_eri_s8_bytes(int n, int layout);
 int pmr_eri_upload_s8(const double* host, double* dev, int n, int layout, void* stream);
 int pmr_eri_complete_s8(double* dev, int n, int layout, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Excitation energies: one-sided Jacobi SVD  G V = U Sigma  (replaces scipy.linalg.eig on the
+ * explicit RPA / TDA Hessian, reference solvers.py:758-776 and :841-856; the host side reduces
+ * the RPA problem to G = chol(A-B)^T chol(A+B), see pymolresponse_b200/solvers.py).
+ *   Gt, Vt   (N, N) row-major, row p = COLUMN p of G / V; Vt = identity on entry.  On exit the
+ *            rows of Gt are sigma_p u_p and the rows of Vt the right singular vectors (unsorted).
+ *   sigma    device, N: singular values;  gv: device, N: g_p . v_p (= signed eigenvalue when G is
+ *            symmetric);  scratch: device, >= 1 double.
+ *   The call synchronises the stream once per sweep to read the convergence scalar
+ *   max |g_p . g_q| / (|g_p| |g_q|); returns PMR_ERR_CONVERGENCE past max_sweeps.
+ * pmr_zero_upper: A <- tril(A), so that a Cholesky factor can be a plain GEMM operand.
+ * ------------------------------------------------------------------------------------------ */
+int pmr_jacobi_svd(double* Gt, double* Vt, int N, long long ld, int max_sweeps, double tol,
+                   double* sigma, double* gv, double* scratch, int* sweeps_done /* host */,
+                   double* final_off /* host */, void* stream);
+int pmr_zero_upper(double* A, int N, long long lda, void* stream);
+/* column scalings of a row-major (rows, cols) matrix: A[:, j] *= scale[j]; unit 2-norm columns
+ * with the component of largest magnitude made positive (LAPACK-style eigenvector columns). */
+int pmr_scale_columns(double* A, int rows, int cols, long long lda, const double* scale,
+                      void* stream);
+int pmr_normalize_columns(double* A, int rows, int cols, long long lda, void* stream);
 
 #ifdef __cplusplus
 }

@@ -669,3 +669,60 @@ def iterative_rhf(C, moenergies, occupations, ao_integrals, omega, jk, maxiter=4
                 )[..., None]
                 return vec, it
     return None, maxiter
+
+
+# --------------------------------------------------------------------------------------
+# excitation energies: explicit diagonalisation (solvers.py:663-856) and the transition
+# properties built from the eigenvectors (td.py:40-77, :206-241; properties/ecd.py:70-107)
+# --------------------------------------------------------------------------------------
+
+
+def diagonalize_rhf(moenergies, tei_mo, tei_mo_type, nocc, hamiltonian, spin, tda_solver=False):
+    """Eigenvalues (ascending, positive half) and unit-norm eigenvectors (columns).
+
+    ``tda_solver=False``: ExactDiagonalizationSolver -- scipy.linalg.eig on [[A, B], [-B, -A]], the
+    nov negative roots dropped (solvers.py:758-776).  ``tda_solver=True``:
+    ExactDiagonalizationSolverTDA -- scipy.linalg.eig on A alone (solvers.py:841-856)."""
+    A, B = rhf_ab(moenergies, tei_mo, tei_mo_type, nocc, hamiltonian, spin)
+    nov = A.shape[0]
+    if tda_solver:
+        assert hamiltonian == "tda"
+        eigvals, eigvecs = scipy.linalg.eig(A)
+        idx = eigvals.argsort()
+        return eigvals[idx], eigvecs[:, idx]
+    G = np.block([[A, B], [-B, -A]])
+    eigvals, eigvecs = scipy.linalg.eig(G)
+    idx = eigvals.argsort()
+    return eigvals[idx][nov:], eigvecs[:, idx][:, nov:]
+
+
+def norm_xy(z, nocc, nvirt):
+    """solvers.py:685-690: scale so that 2 (|x|^2 - |y|^2) = 1."""
+    x, y = z.reshape(2, nvirt, nocc)
+    norm = 1 / np.sqrt(2 * (np.linalg.norm(x) ** 2 - np.linalg.norm(y) ** 2))
+    return (x * norm).flatten(), (y * norm).flatten()
+
+
+def transition_results(eigvals, eigvecs, gradients, nocc, nvirt, tda_driver=False):
+    """Per operator: transition moments (nstates, ncomp), oscillator strengths (nstates, ncomp),
+    total oscillator strengths (nstates,).
+
+    ``gradients``: list of (ncomp, dim) arrays -- the ai supervector [g; s g] rows for td.TDHF
+    (td.py:53-58) or the plain ai rows for td.TDA (td.py:221-226)."""
+    nov = nocc * nvirt
+    out = [{"transition_moments": [], "oscillator_strengths": [], "total_oscillator_strengths": []}
+           for _ in gradients]
+    for idx in range(nov):
+        eigvec = eigvecs[:, idx].real
+        if tda_driver:
+            normed = eigvec / np.sqrt(2)
+        else:
+            x, y = norm_xy(eigvec, nocc, nvirt)
+            normed = np.concatenate((x, y))
+        e = eigvals[idx].real
+        for g, o in zip(gradients, out):
+            tm = 2 * np.dot(g, normed)
+            o["transition_moments"].append(tm)
+            o["oscillator_strengths"].append((2 / 3) * e * tm**2)
+            o["total_oscillator_strengths"].append((2 / 3) * e * np.dot(tm, tm))
+    return [{k: np.array(v) for k, v in o.items()} for o in out]

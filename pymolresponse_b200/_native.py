@@ -108,6 +108,11 @@ SYMBOLS = {
     "pmr_shift_diagonal": (C.c_int, [c_dp, C.c_int, c_ll, C.c_double, c_dp]),
     "pmr_cphf_update": (C.c_int, [c_dp, c_dp, c_dp, c_dp, c_dp, C.c_double, C.c_int, C.c_int,
                                   C.c_int, C.c_int, c_dp, c_dp]),
+    "pmr_jacobi_svd": (C.c_int, [c_dp, c_dp, C.c_int, c_ll, C.c_int, C.c_double, c_dp, c_dp, c_dp,
+                                 C.POINTER(C.c_int), C.POINTER(C.c_double), c_dp]),
+    "pmr_zero_upper": (C.c_int, [c_dp, C.c_int, c_ll, c_dp]),
+    "pmr_scale_columns": (C.c_int, [c_dp, C.c_int, C.c_int, c_ll, c_dp, c_dp]),
+    "pmr_normalize_columns": (C.c_int, [c_dp, C.c_int, C.c_int, c_ll, c_dp]),
     "pmr_set_upload_streams": (None, [C.c_int]),
     "pmr_eri_s8_bytes": (c_ll, [C.c_int, C.c_int]),
     "pmr_eri_upload_s8": (C.c_int, [c_dp, c_dp, C.c_int, C.c_int, c_dp]),

@@ -39,6 +39,11 @@ class IntegralLabel:
 DIPOLE = IntegralLabel("dipole", 3, IntegralSymmetry.SYMMETRIC)
 ANGMOM_COMMON_GAUGE = IntegralLabel("angmom_common_gauge", 3, IntegralSymmetry.ANTISYMMETRIC)
 ANGMOM_GIAO = IntegralLabel("angmom_giao", 3, IntegralSymmetry.ANTISYMMETRIC)
+DIPVEL = IntegralLabel("dipvel", 3, IntegralSymmetry.ANTISYMMETRIC)
+# one-electron spin-orbit integrals summed over the nuclei (charge-weighted), see
+# properties/magnetic.py ElectronicGTensor.form_operators
+SO_SPHER_1e = IntegralLabel("spinorb", 3, IntegralSymmetry.ANTISYMMETRIC)
+SO_SPHER_1e_EFF = IntegralLabel("spinorb_eff", 3, IntegralSymmetry.ANTISYMMETRIC)
 
 
 class Integrals(ABC):

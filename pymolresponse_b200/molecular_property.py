@@ -58,3 +58,14 @@ class ResponseProperty(MolecularProperty, ABC):
         super().__init__(program, program_obj, driver)
         assert isinstance(self.driver, CPHF)
         self.frequencies = self.driver.frequencies
+
+
+class TransitionProperty(MolecularProperty, ABC):
+    """A property built from excited-state transition moments (reference
+    molecular_property.py:62-65)."""
+
+    def __init__(self, program, program_obj: Any, driver) -> None:
+        from pymolresponse_b200.td import TDHF
+
+        super().__init__(program, program_obj, driver)
+        assert isinstance(self.driver, TDHF)

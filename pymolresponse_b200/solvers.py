@@ -178,15 +178,10 @@ def _kind(spin: Spin, uhf: bool) -> str:
     return "ss" if uhf else "singlet"
 
 
-class ExactLineqSolver(LineqSolver, ABC):
-    """Solvers that (conceptually) form the orbital Hessian explicitly
-    (reference solvers.py:160-480)."""
+class _HessianBlocks:
+    """Device-side assembly of the orbital-Hessian blocks from the MO integrals, shared by the
+    linear-equation and the eigenvalue solvers (reference solvers.py:166-385 and :699-752)."""
 
-    #: ExactInv falls back to pivoted LU on G(w) when a Cholesky pivot fails; the Cholesky
-    #: solver raises instead (the reference's scipy.linalg.cholesky would).
-    _allow_lu_fallback = True
-
-    # -------------------------------------------------------------- assembly
     def _tei_dev(self):
         assert self.tei_mo is not None
         assert len(self.tei_mo) in (1, 2, 4, 6)
@@ -279,6 +274,15 @@ class ExactLineqSolver(LineqSolver, ABC):
                 A, B = nv.empty(nt, nt), nv.empty(nt, nt)
                 fill(A, B, 0)
         return M, K, A, B
+
+
+class ExactLineqSolver(LineqSolver, _HessianBlocks, ABC):
+    """Solvers that (conceptually) form the orbital Hessian explicitly
+    (reference solvers.py:160-480)."""
+
+    #: ExactInv falls back to pivoted LU on G(w) when a Cholesky pivot fails; the Cholesky
+    #: solver raises instead (the reference's scipy.linalg.cholesky would).
+    _allow_lu_fallback = True
 
     def share_hessian_with(self, other: "ExactLineqSolver") -> None:
         """Let ``other`` reuse this solver's assembled M / K matrices, the Cholesky factor of K and
@@ -651,5 +655,181 @@ class IterativeLinEqSolver(LineqSolver):
 
 
 class EigSolver(Solver, ABC):
-    """Eigen-solvers (TDHF/TDA excitation energies) are outside the linear-response hot path;
-    see DESIGN.md "out of scope"."""
+    """Base class for all solvers of the type AX = 0 (eigensolvers; reference solvers.py:663-690)."""
+
+    _eigvals = None
+    _eigvecs = None
+
+    @property
+    def eigvals(self):
+        return self._eigvals
+
+    @eigvals.setter
+    def eigvals(self, x) -> None:
+        self._eigvals = x
+
+    @property
+    def eigvecs(self):
+        return self._eigvecs
+
+    @eigvecs.setter
+    def eigvecs(self, x) -> None:
+        self._eigvecs = x
+
+    @staticmethod
+    def norm_xy(z, nocc: int, nvirt: int):
+        """Scale z = [x; y] so that 2 (|x|^2 - |y|^2) = 1 (reference solvers.py:685-690)."""
+        x, y = z.reshape(2, nvirt, nocc)
+        norm = 2 * (np.linalg.norm(x) ** 2 - np.linalg.norm(y) ** 2)
+        norm = 1 / np.sqrt(norm)
+        return (x * norm).flatten(), (y * norm).flatten()
+
+
+class EigSolverTDA(EigSolver, ABC):
+    """Base class for eigensolvers within the Tamm-Dancoff approximation (solvers.py:693-696)."""
+
+
+def _jacobi_svd(Gt, max_sweeps: int = 60, tol: float = 1e-15):
+    """One-sided Jacobi SVD on the GPU (pmr_jacobi_svd).  ``Gt``: (N, N) CUDA tensor whose ROWS are
+    the columns of G; overwritten.  Returns (sigma, gv, Vt, sweeps): singular values, g_p . v_p and
+    the right singular vectors as rows of Vt, all unsorted device tensors."""
+    import ctypes as C
+
+    N = int(Gt.shape[0])
+    Vt = nv.zeros(N, N)
+    eng.shift_diagonal(Vt, N, 1.0)
+    sigma, gv, scratch = nv.empty(max(1, N)), nv.empty(max(1, N)), nv.zeros(2)
+    sweeps, off = C.c_int(0), C.c_double(0.0)
+    nv.check(nv.lib().pmr_jacobi_svd(nv.ptr(Gt), nv.ptr(Vt), N, int(Gt.stride(0)) if N else 1,
+                                     int(max_sweeps), float(tol), nv.ptr(sigma), nv.ptr(gv),
+                                     nv.ptr(scratch), C.byref(sweeps), C.byref(off), nv.stream_ptr()))
+    return sigma[:N], gv[:N], Vt, int(sweeps.value)
+
+
+def _lower_factor(S):
+    """Cholesky factor of an SPD device matrix as a plain lower-triangular GEMM operand."""
+    Lf = S.clone()
+    _dinv, info = eng.potrf(Lf)
+    if int(info.item()) != 0:
+        raise np.linalg.LinAlgError(
+            "A+B / A-B is not positive definite (unstable reference wavefunction): the symmetric "
+            "reduction of the RPA eigenproblem does not apply")
+    N = int(Lf.shape[0])
+    nv.check(nv.lib().pmr_zero_upper(nv.ptr(Lf), N, int(Lf.stride(0)), nv.stream_ptr()))
+    return Lf
+
+
+class ExactDiagonalizationSolver(EigSolver, _HessianBlocks):
+    """All excitation energies and eigenvectors of the RPA (or TDA) Hamiltonian
+    [[A, B], [-B, -A]] (reference solvers.py:699-788, which calls scipy.linalg.eig on the 2N x 2N
+    non-symmetric matrix).
+
+    On the GPU the problem is reduced to a symmetric one of half the size: with K = A + B = L L^T
+    and M = A - B = L_M L_M^T the squared excitation energies are the eigenvalues of L^T M L, i.e.
+    the excitation energies are the SINGULAR VALUES of G = L_M^T L, computed by a one-sided Jacobi
+    SVD kernel; X - Y = L v / w and X + Y = M (X - Y) / w follow by two GEMMs.  ``eigvals`` is real
+    (the reference returns complex numbers with zero imaginary part), ascending; ``eigvecs`` has
+    unit-norm columns [X; Y] like LAPACK's, signs fixed so that the largest component is positive.
+    Needs a stable reference (A +- B positive definite); UHF raises as in the reference."""
+
+    device_eig_results = False
+
+    def form_explicit_hessian(self, hamiltonian: Hamiltonian, spin: Spin,
+                              frequency: float | None) -> None:
+        assert self.tei_mo is not None
+        assert len(self.tei_mo) in (1, 2, 4, 6)
+        assert isinstance(self.tei_mo_type, AO2MOTransformationType)
+        if self.is_uhf:
+            raise NotImplementedError  # as the reference (solvers.py:754-756)
+        M, K, _, _ = self._assemble_rhf(hamiltonian, spin, False)
+        self._MK = (M, K)
+        self._lazy_hessian = None
+
+    @property
+    def explicit_hessian(self):
+        """[[A, B], [-B, -A]] on the host, materialised on first access (solvers.py:751-752)."""
+        if self._lazy_hessian is None and getattr(self, "_MK", None) is not None:
+            M, K = (nv.to_host(t) for t in self._MK)
+            A, B = 0.5 * (K + M), 0.5 * (K - M)
+            self._lazy_hessian = np.block([[A, B], [-B, -A]])
+        return self._lazy_hessian
+
+    @explicit_hessian.setter
+    def explicit_hessian(self, value) -> None:
+        self._lazy_hessian = value
+
+    def diagonalize_explicit_hessian(self) -> None:
+        if self.is_uhf:
+            raise NotImplementedError
+        torch = nv.torch_mod()
+        M, K = self._MK
+        N = int(M.shape[0])
+        Lk = _lower_factor(K)
+        Lm = Lk if M is K else _lower_factor(M)
+        # Gt = G^T = L^T L_M  (rows of Gt = columns of G = L_M^T L)
+        Gt = nv.matmul(Lk, Lm, transpose_a=True)
+        sigma, _gv, Vt, sweeps = _jacobi_svd(Gt)
+        self.jacobi_sweeps = sweeps
+        order = torch.argsort(sigma)
+        w = sigma[order].contiguous()
+        V = Vt[order].t().contiguous()                 # columns = eigenvectors of L^T M L, ascending
+        D = nv.matmul(Lk, V)                           # X - Y (up to 1/w)
+        S = nv.matmul(M, D)                            # w (X + Y) (same scale)
+        winv = (1.0 / w).contiguous()
+        nv.check(nv.lib().pmr_scale_columns(nv.ptr(S), N, N, N, nv.ptr(winv), nv.stream_ptr()))
+        Z = nv.empty(2 * N, N)
+        eng.axpby(0.5, S, 0.0, Z[:N])
+        eng.axpby(0.5, D, 1.0, Z[:N])
+        eng.axpby(0.5, S, 0.0, Z[N:])
+        eng.axpby(-0.5, D, 1.0, Z[N:])
+        nv.check(nv.lib().pmr_normalize_columns(nv.ptr(Z), 2 * N, N, N, nv.stream_ptr()))
+        self._eigvals_dev, self._eigvecs_dev = w, Z
+        self.eigvals = w if self.device_eig_results else nv.to_host(w)
+        self.eigvecs = Z if self.device_eig_results else nv.to_host(Z)
+
+    def run(self, hamiltonian: Hamiltonian, spin: Spin, program: Program | None,
+            program_obj: Any) -> None:
+        if not self.tei_mo:
+            if program is None:
+                msg = "Program must be specified for computing 2-electron integrals in MO basis"
+                raise RuntimeError(msg)
+            self.form_tei_mo(program, program_obj, AO2MOTransformationType.partial)
+        self.form_explicit_hessian(hamiltonian, spin, None)
+        self.diagonalize_explicit_hessian()
+
+
+class ExactDiagonalizationSolverTDA(ExactDiagonalizationSolver, EigSolverTDA):
+    """All eigenpairs of the TDA Hamiltonian A (reference solvers.py:791-856).  A is symmetric: its
+    SVD by the same Jacobi kernel gives |eigenvalue| and the eigenvector, g_p . v_p the sign."""
+
+    def form_explicit_hessian(self, hamiltonian: Hamiltonian, spin: Spin,
+                              frequency: float | None) -> None:
+        assert hamiltonian == Hamiltonian.TDA
+        super().form_explicit_hessian(hamiltonian, spin, frequency)
+
+    @property
+    def explicit_hessian(self):
+        if self._lazy_hessian is None and getattr(self, "_MK", None) is not None:
+            self._lazy_hessian = nv.to_host(self._MK[0])
+        return self._lazy_hessian
+
+    @explicit_hessian.setter
+    def explicit_hessian(self, value) -> None:
+        self._lazy_hessian = value
+
+    def diagonalize_explicit_hessian(self) -> None:
+        if self.is_uhf:
+            raise NotImplementedError
+        torch = nv.torch_mod()
+        A = self._MK[0]
+        N = int(A.shape[0])
+        Gt = A.t().contiguous()
+        _sigma, gv, Vt, sweeps = _jacobi_svd(Gt)
+        self.jacobi_sweeps = sweeps
+        order = torch.argsort(gv)
+        w = gv[order].contiguous()
+        Z = Vt[order].t().contiguous()
+        nv.check(nv.lib().pmr_normalize_columns(nv.ptr(Z), N, N, N, nv.stream_ptr()))
+        self._eigvals_dev, self._eigvecs_dev = w, Z
+        self.eigvals = w if self.device_eig_results else nv.to_host(w)
+        self.eigvecs = Z if self.device_eig_results else nv.to_host(Z)

@@ -74,6 +74,17 @@ def repack_vector_to_matrix(vec, shape):
     return vec.reshape(shape, order="F")
 
 
+def form_indices_orbwin(nocc: int, nvirt: int) -> list[tuple[int, int]]:
+    """All occupied-virtual index pairs by absolute orbital position (reference utils.py:457-460)."""
+    norb = nocc + nvirt
+    return [(i, a) for i in range(0, nocc) for a in range(nocc, norb)]
+
+
+def form_indices_zero(nocc: int, nvirt: int) -> list[tuple[int, int]]:
+    """All occupied-virtual index pairs, both counted from zero (reference utils.py:463-465)."""
+    return [(i, a) for i in range(nocc) for a in range(nvirt)]
+
+
 def fix_mocoeffs_shape(mocoeffs):
     """Normalise MO coefficients to (nden, nao, nmo), nden in {1, 2} (reference utils.py:216-237)."""
     if isinstance(mocoeffs, tuple):

@@ -26,6 +26,23 @@ sys.path.insert(0, str(REPO))
 _v = types.ModuleType("pymolresponse._version")
 _v.__version__ = "0+oracle"
 sys.modules["pymolresponse._version"] = _v
+# ``pymolresponse/constants.py:3,6,22`` builds a pint unit registry for one dipole conversion
+# constant; pint is not installed here and none of the numbers stored below depend on it.
+_pint = types.ModuleType("pint")
+
+
+class _UnitRegistry:
+    debye = None
+
+    def __init__(self, **_kw):
+        pass
+
+    def get_base_units(self, input_units=None):
+        return (1.0, None)
+
+
+_pint.UnitRegistry = _UnitRegistry
+sys.modules.setdefault("pint", _pint)
 sys.path.insert(0, "/root/reference")
 
 from pymolresponse import cphf, operators, solvers, utils  # noqa: E402
@@ -266,6 +283,72 @@ def golden_synthetic_rhf(n=10, nocc=3):
     print("synthetic rhf: static alpha", np.diag(out["results_rpa_singlet_partial"][0])[:3])
 
 
+# ------------------------------------------------------------------ excitation energies
+def _run_td(C, E, occ, tei, ttype, ops, ham, spin, tda_solver):
+    from pymolresponse import td
+    from pymolresponse.properties.ecd import ECD
+
+    cls = solvers.ExactDiagonalizationSolverTDA if tda_solver else solvers.ExactDiagonalizationSolver
+    solver = cls(C, E, occ)
+    solver.tei_mo = tei
+    solver.tei_mo_type = ttype
+    driver = (td.TDA if tda_solver else td.TDHF)(solver)
+    op_objs = []
+    for o in ops:
+        op = operators.Operator(label=o["label"], is_imaginary=o["is_imaginary"],
+                                is_spin_dependent=False, triplet=False, ao_integrals=o["ao_integrals"])
+        driver.add_operator(op)
+        op_objs.append(op)
+    driver.run(hamiltonian=HAMS[ham], spin=SPINS[spin], program=None, program_obj=None)
+    ecd = ECD(None, None, driver, do_dipvel=False)
+    ecd.form_results()
+    return solver, op_objs, ecd
+
+
+def golden_td():
+    """Eigenvalues, oscillator strengths and rotational strengths from the reference's
+    ExactDiagonalizationSolver(TDA) + td.TDHF / td.TDA + properties.ecd.ECD.form_results on the
+    water/STO-3G fixture (full MO integrals) and the seeded synthetic n=10 case (partial)."""
+    import contextlib
+    import io
+
+    out = {}
+    Cw = utils.fix_mocoeffs_shape(utils.np_load_2(REFDIR / "C.npz"))
+    Ew = utils.fix_moenergies_shape(utils.np_load_2(REFDIR / "F_MO.npz"))
+    TEI = utils.np_load(REFDIR / "TEI_MO.npz")
+    mu = np.stack([utils.parse_int_file_2(REFDIR / f"h2o_sto3g_mu{x}.dat", 7) for x in "xyz"], axis=0)
+    Lw = synthetic.operator_integrals(7, 3, imaginary=True, seed=91)   # stands for angmom
+    case = synthetic.rhf_case(10, 3)
+    a = AO2MO(case["C"], case["occupations"], I=case["I"])
+    a.perform_rhf_partial()
+    Or = synthetic.operator_integrals(10, 3, imaginary=False)
+    Oi = synthetic.operator_integrals(10, 3, imaginary=True)
+    systems = {
+        "water": (Cw, Ew, (5, 2, 5, 2), (TEI,), AO2MOTransformationType.full, Lw, mu),
+        "syn10": (case["C"], case["E"], case["occupations"], a.tei_mo,
+                  AO2MOTransformationType.partial, Oi, Or),
+    }
+    out["water_angmom_like"] = Lw
+    for name, (C, E, occ, tei, ttype, Oimag, Oreal) in systems.items():
+        ops = [{"label": "angmom", "is_imaginary": True, "ao_integrals": Oimag},
+               {"label": "dipole", "is_imaginary": False, "ao_integrals": Oreal}]
+        for tda_solver, ham in ((False, "rpa"), (False, "tda"), (True, "tda")):
+            for spin in SPINS:
+                with contextlib.redirect_stdout(io.StringIO()):
+                    solver, op_objs, ecd = _run_td(C, E, occ, tei, ttype, ops, ham, spin, tda_solver)
+                tag = f"{name}_{'tdasolver' if tda_solver else 'rpasolver'}_{ham}_{spin}"
+                assert np.abs(solver.eigvals.imag).max() == 0.0
+                out[f"eigvals_{tag}"] = solver.eigvals.real
+                out[f"eigvecs_{tag}"] = solver.eigvecs.real
+                for op in op_objs:
+                    out[f"tmom_{op.label}_{tag}"] = op.transition_moments
+                    out[f"osc_{op.label}_{tag}"] = op.oscillator_strengths
+                    out[f"totosc_{op.label}_{tag}"] = op.total_oscillator_strengths
+                out[f"rotstr_{tag}"] = ecd.rotational_strengths_diplen
+    np.savez_compressed(HERE / "td_golden.npz", **out)
+    print("td: water RPA singlet roots", out["eigvals_water_rpasolver_rpa_singlet"][:4])
+
+
 def golden_synthetic_uhf(n=9, na=3, nb=2):
     case = synthetic.uhf_case(n, na, nb)
     C, E, occ, I = case["C"], case["E"], case["occupations"], case["I"]
@@ -321,3 +404,4 @@ if __name__ == "__main__":
     golden_synthetic_rhf()
     golden_synthetic_uhf()
     golden_lih()
+    golden_td()

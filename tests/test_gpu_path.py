@@ -555,6 +555,69 @@ def test_polarizability_and_magnetizability_wrappers():
     np.testing.assert_allclose(mag.magnetizability, ref_m["results"][0] / 4, rtol=0, atol=1e-9)
 
 
+def test_ord_and_gtensor_wrappers():
+    """Mixed imaginary/real multi-operator batches through the ORD and g-tensor wrappers (reference
+    properties/optrot.py:13-96, properties/magnetic.py:57-190) against the oracle's result blocks."""
+    from pymolresponse_b200 import cphf, integrals, solvers, synthetic
+    from pymolresponse_b200.core import Hamiltonian, Program, Spin
+    from pymolresponse_b200.properties.magnetic import ElectronicGTensor
+    from pymolresponse_b200.properties.optrot import ORD
+
+    n, o = 24, 5
+    case = synthetic.rhf_case(n, o)
+    Oi = synthetic.operator_integrals(n, 3, True)
+    Or = synthetic.operator_integrals(n, 3, False)
+    Ov = synthetic.operator_integrals(n, 3, True, seed=77)
+    gen = integrals.IntegralsArrays({"dipole": Or, "angmom_common_gauge": Oi, "dipvel": Ov})
+    tei = orc.ao2mo_rhf_partial(case["I"], case["C"], o)
+    freqs = [0.0, 0.12]
+    for do_dipvel in (False, True):
+        ops = [{"ao_integrals": Oi, "is_imaginary": True}, {"ao_integrals": Or, "is_imaginary": False}]
+        if do_dipvel:
+            ops.append({"ao_integrals": Ov, "is_imaginary": True})
+        ref = orc.run_cphf(case["C"], case["E"], case["occupations"], tei, "partial", ops, freqs)
+        solver = solvers.ExactInv(case["C"], case["E"], case["occupations"])
+        solver.tei_mo = tei
+        ord_ = ORD(Program.Arrays, gen, cphf.CPHF(solver), frequencies=freqs, do_dipvel=do_dipvel)
+        ord_.form_operators()
+        ord_.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet)
+        ord_.form_results()
+        for f in range(len(freqs)):
+            np.testing.assert_allclose(ord_.driver.results[f], ref["results"][f], rtol=0, atol=1e-9)
+            np.testing.assert_allclose(ord_.polarizabilities[f], ref["results"][f][3:6, 3:6],
+                                       rtol=0, atol=1e-9)
+            np.testing.assert_allclose(ord_.polarizabilities_lenmag[f], ref["results"][f][0:3, 3:6],
+                                       rtol=0, atol=1e-9)
+
+    # g-tensor: UHF doublet, three imaginary operators in one static batch
+    na, nb = 5, 4
+    ucase = synthetic.uhf_case(n, na, nb)
+    Oso = synthetic.operator_integrals(n, 3, True, seed=78)
+    gen_g = integrals.IntegralsArrays({"angmom_common_gauge": Oi, "spinorb": Oso,
+                                       "spinorb_eff": 0 * Oso})
+    utei = orc.ao2mo_uhf_partial(ucase["I"], ucase["C"], ucase["occupations"])
+    # operators whose label contains "spinorb" carry the factor alpha^2 / 4 (operators.py:44-45)
+    from pymolresponse_b200.constants import alpha
+
+    hso = alpha**2 / 4
+    ops = [{"ao_integrals": Oi, "is_imaginary": True},
+           {"ao_integrals": Oso, "is_imaginary": True, "hsofac": hso},
+           {"ao_integrals": 0 * Oso, "is_imaginary": True, "hsofac": hso}]
+    ref = orc.run_cphf(ucase["C"], ucase["E"], ucase["occupations"], utei, "partial", ops, [0.0])
+    usolver = solvers.ExactInv(ucase["C"], ucase["E"], ucase["occupations"])
+    usolver.tei_mo = utei
+    gt = ElectronicGTensor(Program.Arrays, gen_g, cphf.CPHF(usolver), gauge_origin=[0.0, 0.0, 0.0],
+                           nelec=(na, nb))
+    gt.form_operators()
+    gt.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet)
+    gt.form_results()
+    want = ref["results"][0][0:3, 3:6] / (0.5 * (na - nb))
+    np.testing.assert_allclose(gt.g_oz_soc_1, want, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(np.sort(gt.g_oz_soc_1_eig.real),
+                               np.sort(np.sqrt(np.linalg.eigvals(want.T @ want)).real), atol=1e-12)
+    assert np.abs(want).max() > 1e-9
+
+
 def test_uhf_end_to_end_from_ao_integrals():
     """Config-4 shaped small case: UHF (5 alpha, 4 beta), AO2MO + joint Cholesky on the GPU."""
     from pymolresponse_b200 import cphf, operators, solvers, synthetic

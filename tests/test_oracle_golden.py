@@ -244,3 +244,38 @@ def test_oracle_lih_dalton_fixtures(golden_dir, case, uhf, thresh):
         assert abs(g["ref_value"][k]) - abs(res[1, 0]) < thresh
         checked += 1
     assert checked > 500
+
+
+# ------------------------------------------------------------------ excitation energies
+@pytest.mark.parametrize("name", ["water", "syn10"])
+@pytest.mark.parametrize("tda_solver,ham", [(False, "rpa"), (False, "tda"), (True, "tda")])
+@pytest.mark.parametrize("spin", ["singlet", "triplet"])
+def test_oracle_excitation_energies(golden_dir, name, tda_solver, ham, spin):
+    """diagonalize_rhf / transition_results against the reference's ExactDiagonalizationSolver(TDA)
+    + td.TDHF / td.TDA + ECD.form_results (signs of eigenvectors are arbitrary: moments compared
+    in magnitude, strengths as they are)."""
+    from _td_cases import tag_of, td_system
+
+    from pymolresponse_b200.constants import esuecd
+
+    sysd = td_system(golden_dir, name)
+    g = np.load(golden_dir / "td_golden.npz")
+    tag = tag_of(name, tda_solver, ham, spin)
+    nocc, nvirt = sysd["occ"][0], sysd["occ"][1]
+    ev, vecs = orc.diagonalize_rhf(sysd["E"], sysd["tei"], sysd["ttype"], nocc, ham, spin,
+                                   tda_solver=tda_solver)
+    np.testing.assert_allclose(ev.real, g[f"eigvals_{tag}"], rtol=0, atol=1e-12)
+    key = "mo_integrals_ai_alph" if tda_solver else "mo_integrals_ai_supervector_alph"
+    grads = [orc.form_rhs(sysd["Oimag"], sysd["C"], sysd["occ"], is_imaginary=True)[key][:, :, 0],
+             orc.form_rhs(sysd["Oreal"], sysd["C"], sysd["occ"], is_imaginary=False)[key][:, :, 0]]
+    res = orc.transition_results(ev, vecs, grads, nocc, nvirt, tda_driver=tda_solver)
+    for label, r in zip(("angmom", "dipole"), res):
+        np.testing.assert_allclose(np.abs(r["transition_moments"]), np.abs(g[f"tmom_{label}_{tag}"]),
+                                   rtol=0, atol=1e-10)
+        np.testing.assert_allclose(r["oscillator_strengths"], g[f"osc_{label}_{tag}"], rtol=0,
+                                   atol=1e-10)
+        np.testing.assert_allclose(r["total_oscillator_strengths"], g[f"totosc_{label}_{tag}"],
+                                   rtol=0, atol=1e-10)
+    rot = esuecd * (-1 / 2) * np.einsum("sc,sc->s", res[1]["transition_moments"],
+                                        res[0]["transition_moments"])
+    np.testing.assert_allclose(rot, g[f"rotstr_{tag}"], rtol=0, atol=1e-7 * max(1.0, np.abs(rot).max()))

@@ -259,6 +259,12 @@ void pmr_set_upload_streams(int count); /* side streams the layout-1 DMAs are sp
 long long pmr_eri_s8_bytes(int n, int layout);
 int pmr_eri_upload_s8(const double* host, double* dev, int n, int layout, void* stream);
 int pmr_eri_complete_s8(double* dev, int n, int layout, void* stream);
+/* Slab of `rows` (mu, nu) pairs, each an n x n matrix in (la, si) -- e.g. one rank's nu-shard
+ * I[:, nu_lo:nu_hi] of a sharded tensor: only (la si| = (si la| is usable inside a slab; the
+ * columns (la, si <= la) are copied (half the bytes) and every row is symmetrised in HBM. */
+long long pmr_eri_ket_s2_bytes(long long rows, int n);
+int pmr_eri_upload_ket_s2(const double* host, double* dev, long long rows, int n, void* stream);
+int pmr_eri_complete_ket_s2(double* dev, long long rows, int n, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Excitation energies: one-sided Jacobi SVD  G V = U Sigma  (replaces scipy.linalg.eig on the

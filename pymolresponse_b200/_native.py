@@ -108,6 +108,9 @@ SYMBOLS = {
     "pmr_shift_diagonal": (C.c_int, [c_dp, C.c_int, c_ll, C.c_double, c_dp]),
     "pmr_cphf_update": (C.c_int, [c_dp, c_dp, c_dp, c_dp, c_dp, C.c_double, C.c_int, C.c_int,
                                   C.c_int, C.c_int, c_dp, c_dp]),
+    "pmr_eri_ket_s2_bytes": (c_ll, [c_ll, C.c_int]),
+    "pmr_eri_upload_ket_s2": (C.c_int, [c_dp, c_dp, c_ll, C.c_int, c_dp]),
+    "pmr_eri_complete_ket_s2": (C.c_int, [c_dp, c_ll, C.c_int, c_dp]),
     "pmr_jacobi_svd": (C.c_int, [c_dp, c_dp, C.c_int, c_ll, C.c_int, C.c_double, c_dp, c_dp, c_dp,
                                  C.POINTER(C.c_int), C.POINTER(C.c_double), c_dp]),
     "pmr_zero_upper": (C.c_int, [c_dp, C.c_int, c_ll, c_dp]),
@@ -230,6 +233,22 @@ def upload_eri_s8(I, layout=None):  # noqa: E741
     check(L.pmr_eri_upload_s8(C.c_void_p(arr.ctypes.data), ptr(dev), n, layout, stream_ptr()))
     check(L.pmr_eri_complete_s8(ptr(dev), n, layout, stream_ptr()))
     torch.cuda.current_stream().synchronize()   # the host buffer may be reused by the caller
+    return dev
+
+
+def upload_eri_slab_s2(I):  # noqa: E741
+    """Host slab (..., n, n) of an AO ERI tensor symmetric in its last two indices -> CUDA tensor;
+    half of the bytes cross PCIe (pmr_eri_upload_ket_s2 / pmr_eri_complete_ket_s2)."""
+    torch = torch_mod()
+    arr = np.ascontiguousarray(np.asarray(I), dtype=np.float64)
+    assert arr.ndim >= 2 and arr.shape[-1] == arr.shape[-2]
+    n = int(arr.shape[-1])
+    rows = int(arr.size // (n * n)) if n else 0
+    dev = empty(*arr.shape)
+    L = lib()
+    check(L.pmr_eri_upload_ket_s2(C.c_void_p(arr.ctypes.data), ptr(dev), rows, n, stream_ptr()))
+    check(L.pmr_eri_complete_ket_s2(ptr(dev), rows, n, stream_ptr()))
+    torch.cuda.current_stream().synchronize()
     return dev
 
 

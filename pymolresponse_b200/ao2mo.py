@@ -17,8 +17,9 @@ same length, order, shapes and C-order layout.  Differences, all additive:
   (ij|ab)), otherwise they are this slab's partial sums.
 * ``ao_symmetry="s8"``: the caller states that a host-side ``I`` has the 8-fold permutational
   symmetry of real-orbital ERIs (what pyscf ``int2e`` and psi4 ``ao_eri`` return); only its unique
-  part is copied to the GPU and the tensor is completed in HBM.  The default ``"s1"`` copies the
-  whole array and assumes nothing.
+  part is copied to the GPU and the tensor is completed in HBM (a sixth of the bytes for the whole
+  tensor, half for a ``nu_range`` slab).  The default ``"s1"`` copies the whole array and assumes
+  nothing.
 """
 
 from __future__ import annotations
@@ -137,9 +138,10 @@ class AO2MO:
 
     def _I_dev(self):
         assert self.I is not None
-        if (self.ao_symmetry == "s8" and self.nu_range is None
-                and not nv.is_device_array(self.I)):
-            return nv.upload_eri_s8(self.I)
+        if self.ao_symmetry == "s8" and not nv.is_device_array(self.I):
+            if self.nu_range is None:
+                return nv.upload_eri_s8(self.I)
+            return nv.upload_eri_slab_s2(self.I)   # a nu-slab: only (la si| = (si la| applies
         I = nv.to_dev(self.I)
         assert I.dim() == 4
         return I

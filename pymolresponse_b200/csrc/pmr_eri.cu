@@ -230,3 +230,46 @@ extern "C" int pmr_eri_complete_s8(double* dev, int n, int layout, void* stream)
   PMR_CHECK_LAUNCH("eri_transpose_mirror_kernel");
   return 0;
 }
+
+// ---- slabs (rows = any set of (mu, nu) pairs, e.g. the nu-shard of one rank) ----------------------
+// Only (la si| = (si la| can be used inside a slab: for every la one strided DMA of the columns
+// (la, si <= la) of all rows, then each row's n x n matrix is symmetrised in place.
+namespace {
+__global__ void __launch_bounds__(256) eri_ket_mirror_kernel(double* __restrict__ I, int n) {
+  double* row = I + (long long)blockIdx.x * n * n;
+  for (int idx = threadIdx.x; idx < n * n; idx += 256) {
+    const int si = idx / n, la = idx - si * n;
+    if (la > si) row[(long long)si * n + la] = row[(long long)la * n + si];
+  }
+}
+}  // namespace
+
+extern "C" long long pmr_eri_ket_s2_bytes(long long rows, int n) {
+  return rows * ((long long)n * (n + 1) / 2) * 8;
+}
+
+extern "C" int pmr_eri_upload_ket_s2(const double* host, double* dev, long long rows, int n,
+                                     void* stream) {
+  cudaStream_t st = as_stream(stream);
+  PMR_REQUIRE(rows >= 0 && n >= 0, "eri_upload_ket_s2: bad sizes");
+  if (rows == 0 || n == 0) return 0;
+  PMR_REQUIRE(host && dev, "eri_upload_ket_s2: null pointer");
+  const size_t n2 = (size_t)n * n;
+  for (size_t la = 0; la < (size_t)n; ++la) {
+    const size_t off = la * n;
+    PMR_CHECK_CUDA(cudaMemcpy2DAsync(dev + off, n2 * sizeof(double), host + off, n2 * sizeof(double),
+                                     (la + 1) * sizeof(double), (size_t)rows, cudaMemcpyHostToDevice,
+                                     st));
+  }
+  return 0;
+}
+
+extern "C" int pmr_eri_complete_ket_s2(double* dev, long long rows, int n, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  PMR_REQUIRE(rows >= 0 && rows <= 2147483647LL && n >= 0, "eri_complete_ket_s2: bad sizes");
+  if (rows == 0 || n <= 1) return 0;
+  PMR_REQUIRE(dev, "eri_complete_ket_s2: null pointer");
+  eri_ket_mirror_kernel<<<(unsigned)rows, 256, 0, st>>>(dev, n);
+  PMR_CHECK_LAUNCH("eri_ket_mirror_kernel");
+  return 0;
+}

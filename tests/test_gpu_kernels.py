@@ -365,3 +365,16 @@ def test_ao2mo_s8_upload_matches_plain_upload():
     b.perform_rhf_partial()
     for x, y in zip(a.tei_mo, b.tei_mo):
         assert np.array_equal(x, y)
+
+
+def test_eri_slab_upload_ket_symmetry():
+    """A nu-slab I[:, 2:5]: only the columns (la, si <= la) are read from the host."""
+    nv = _nv()
+    n = 9
+    T = _symmetric_eri(n, 44)[:, 2:5].copy()
+    keep = np.zeros(T.shape, dtype=bool)
+    for la in range(n):
+        keep[:, :, la, :la + 1] = True
+    assert int(nv.lib().pmr_eri_ket_s2_bytes(T.shape[0] * T.shape[1], n)) == 8 * int(keep.sum())
+    got = nv.to_host(nv.upload_eri_slab_s2(np.where(keep, T, np.nan)))
+    assert np.array_equal(got, T)

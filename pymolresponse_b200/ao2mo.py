@@ -15,6 +15,10 @@ same length, order, shapes and C-order layout.  Differences, all additive:
   second index of the first AO pair; with ``reduce=True`` the blocks are completed across the
   ``torch.distributed`` ranks (all-reduce of (ia|jb); reduce-scatter / finish / all-gather for
   (ij|ab)), otherwise they are this slab's partial sums.
+* ``df_factor=B``: instead of the n^4 tensor the caller hands a factor
+  ``B[P, mu, nu]`` with ``(mu nu|la si) = sum_P B[P,mu,nu] B[P,la,si]`` (density fitting, Cholesky
+  vectors; the synthetic generator is one).  The MO blocks are then ``(ia|jb) = B_ia^T B_jb`` after
+  two half-transforms of the factor: O(naux n^2 norb) flops and no n^4 object at all.
 * ``ao_symmetry="s8"``: the caller states that a host-side ``I`` has the 8-fold permutational
   symmetry of real-orbital ERIs (what pyscf ``int2e`` and psi4 ``ao_eri`` return); only its unique
   part is copied to the GPU and the tensor is completed in HBM (a sixth of the bytes for the whole
@@ -112,12 +116,43 @@ def partial_blocks_dev(I_slab, nu_lo, Cbra, nocc_bra, kets, want_oovv, nu_block=
     return outs, oovv
 
 
+def factor_to_mo(B, Cs):
+    """B (naux, n, n), Cs (n, norb) CUDA tensors -> Bmo (naux, norb, norb) with
+    Bmo[P, p, q] = sum_{mu nu} Cs[mu, p] B[P, mu, nu] Cs[nu, q] (two GEMM stages)."""
+    naux, n = int(B.shape[0]), int(B.shape[1])
+    norb = int(Cs.shape[1])
+    ldc = int(Cs.stride(0))
+    T = nv.empty(naux, n, norb)
+    nv.dgemm(naux * n, norb, n, 1.0, B, 0, n, 1, Cs, 0, ldc, 1, 0.0, T, 0, norb, 1)
+    Bmo = nv.empty(naux, norb, norb)
+    # per P: Bmo_P = Cs^T T_P
+    nv.dgemm(norb, norb, n, 1.0, Cs, 0, 1, ldc, T, 0, norb, 1, 0.0, Bmo, 0, norb, 1,
+             batch1=naux, a_b=(0, 0), b_b=(n * norb, 0), c_b=(norb * norb, 0))
+    return Bmo
+
+
+def _factor_block(Bmo, p0, p1, q0, q1):
+    """Contiguous (naux, (p1-p0)*(q1-q0)) copy of the sub-block Bmo[:, p0:p1, q0:q1]."""
+    naux = int(Bmo.shape[0])
+    return Bmo[:, p0:p1, q0:q1].contiguous().view(naux, (p1 - p0) * (q1 - q0))
+
+
+def _factor_product(X, Y, shape):
+    """out[x, y] = sum_P X[P, x] Y[P, y] -> tensor of ``shape`` (both operands mn-contiguous: the
+    TMA-bulk GEMM kernel)."""
+    naux, dx, dy = int(X.shape[0]), int(X.shape[1]), int(Y.shape[1])
+    out = nv.empty(*shape)
+    if dx and dy:
+        nv.dgemm(dx, dy, naux, 1.0, X, 0, 1, dx, Y, 0, dy, 1, 0.0, out, 0, dy, 1)
+    return out
+
+
 class AO2MO:
     """Interface for AO-to-MO transformations of two-electron integrals (reference ao2mo.py:15-78)."""
 
     def __init__(self, C, occupations, I=None, *, device_results: bool = False,  # noqa: E741
                  nu_range: tuple[int, int] | None = None, nu_block: int = 0,
-                 reduce: bool = False, ao_symmetry: str = "s1") -> None:
+                 reduce: bool = False, ao_symmetry: str = "s1", df_factor=None) -> None:
         self.C = fix_mocoeffs_shape(C) if not nv.is_device_array(C) else (C if C.dim() == 3 else C[None])
         self.occupations = occupations
         self.I = I
@@ -129,6 +164,9 @@ class AO2MO:
         self.reduce = reduce  # complete the blocks over torch.distributed ranks (nu-sharded I)
         assert ao_symmetry in ("s1", "s8")
         self.ao_symmetry = ao_symmetry
+        self.df_factor = df_factor
+        if df_factor is not None:
+            assert I is None and nu_range is None, "give either the AO tensor or its factor"
 
     # ------------------------------------------------------------------ helpers
     def _out(self, tensors):
@@ -159,6 +197,23 @@ class AO2MO:
     def _C_dev(self, spin: int):
         return nv.to_dev(self.C[spin])
 
+    def _B_dev(self):
+        B = nv.to_dev(self.df_factor)
+        assert B.dim() == 3 and B.shape[1] == B.shape[2]
+        return B
+
+    def _factor_blocks(self, spins):
+        """Per spin: (B_ov (naux, o v), B_oo (naux, o o), B_vv (naux, v v), o, v)."""
+        out = []
+        for spin in spins:
+            Cs = self._C_dev(spin)
+            o = self.nocc_alph if spin == 0 else self.nocc_beta
+            norb = int(Cs.shape[1])
+            Bmo = factor_to_mo(self._B_dev(), Cs)
+            out.append((_factor_block(Bmo, 0, o, o, norb), _factor_block(Bmo, 0, o, 0, o),
+                        _factor_block(Bmo, o, norb, o, norb), o, norb - o))
+        return out
+
     # ------------------------------------------------------------------ reference API
     @staticmethod
     def transform(I, C1, C2, C3, C4):  # noqa: E741
@@ -171,12 +226,22 @@ class AO2MO:
     def perform_rhf_full(self) -> None:
         r"""(mu nu|la si) -> ((pq|rs),)  (reference ao2mo.py:52-56)."""
         assert self.nu_range is None, "full transforms need the whole AO tensor"
-        I = self._I_dev()
         Ca = self._C_dev(0)
+        if self.df_factor is not None:
+            norb = int(Ca.shape[1])
+            Bf = _factor_block(factor_to_mo(self._B_dev(), Ca), 0, norb, 0, norb)
+            self.tei_mo = self._out((_factor_product(Bf, Bf, (norb,) * 4),))
+            return
+        I = self._I_dev()
         self.tei_mo = self._out((_transform_dev(I, Ca, Ca, Ca, Ca),))
 
     def perform_rhf_partial(self) -> None:
         r"""(mu nu|la si) -> ((ia|jb), (ij|ab))  (reference ao2mo.py:58-70)."""
+        if self.df_factor is not None:
+            (ov, oo, vv, o, v), = self._factor_blocks((0,))
+            self.tei_mo = self._out((_factor_product(ov, ov, (o, v, o, v)),
+                                     _factor_product(oo, vv, (o, o, v, v))))
+            return
         I, lo = self._slab()
         Ca = self._C_dev(0)
         (ovov,), oovv = partial_blocks_dev(I, lo, Ca, self.nocc_alph, [(Ca, self.nocc_alph)], True,
@@ -186,8 +251,16 @@ class AO2MO:
     def perform_uhf_full(self) -> None:
         r"""-> (aaaa, aabb, bbaa, bbbb), each (n,n,n,n)  (interfaces/pyscf/ao2mo.py:49-69)."""
         assert self.nu_range is None, "full transforms need the whole AO tensor"
-        I = self._I_dev()
         Ca, Cb = self._C_dev(0), self._C_dev(1)
+        if self.df_factor is not None:
+            na_, nb_ = int(Ca.shape[1]), int(Cb.shape[1])
+            Fa = _factor_block(factor_to_mo(self._B_dev(), Ca), 0, na_, 0, na_)
+            Fb = _factor_block(factor_to_mo(self._B_dev(), Cb), 0, nb_, 0, nb_)
+            self.tei_mo = self._out((
+                _factor_product(Fa, Fa, (na_,) * 4), _factor_product(Fa, Fb, (na_, na_, nb_, nb_)),
+                _factor_product(Fb, Fa, (nb_, nb_, na_, na_)), _factor_product(Fb, Fb, (nb_,) * 4)))
+            return
+        I = self._I_dev()
         self.tei_mo = self._out((
             _transform_dev(I, Ca, Ca, Ca, Ca),
             _transform_dev(I, Ca, Ca, Cb, Cb),
@@ -198,6 +271,13 @@ class AO2MO:
     def perform_uhf_partial(self) -> None:
         r"""-> (ovov_aaaa, ovov_aabb, ovov_bbaa, ovov_bbbb, oovv_aaaa, oovv_bbbb)
         (interfaces/pyscf/ao2mo.py:71-109)."""
+        if self.df_factor is not None:
+            (ova, ooa, vva, oa, va), (ovb, oob, vvb, ob, vb) = self._factor_blocks((0, 1))
+            self.tei_mo = self._out((
+                _factor_product(ova, ova, (oa, va, oa, va)), _factor_product(ova, ovb, (oa, va, ob, vb)),
+                _factor_product(ovb, ova, (ob, vb, oa, va)), _factor_product(ovb, ovb, (ob, vb, ob, vb)),
+                _factor_product(ooa, vva, (oa, oa, va, va)), _factor_product(oob, vvb, (ob, ob, vb, vb))))
+            return
         I, lo = self._slab()
         Ca, Cb = self._C_dev(0), self._C_dev(1)
         na, nb = self.nocc_alph, self.nocc_beta
@@ -206,6 +286,12 @@ class AO2MO:
         (bbaa, bbbb), oovv_b = partial_blocks_dev(I, lo, Cb, nb, [(Ca, na), (Cb, nb)], True,
                                                   self.nu_block, self.reduce)
         self.tei_mo = self._out((aaaa, aabb, bbaa, bbbb, oovv_a, oovv_b))
+
+
+def flops_rhf_partial_df(n: int, o: int, naux: int) -> float:
+    """Algorithmic flops of the factor route: two half-transforms of B, then the two products."""
+    v = n - o
+    return 2.0 * naux * n * n * n + 2.0 * naux * n * n * n + 2.0 * naux * (o * v) ** 2 + 2.0 * naux * o * o * v * v
 
 
 def flops_rhf_partial(n: int, o: int) -> float:

@@ -98,7 +98,10 @@ class Solver(ABC):
         nden = self.mocoeffs.shape[0]
         assert nden in (1, 2)
         I = None  # noqa: E741
-        if isinstance(program_obj, np.ndarray) or nv.is_device_array(program_obj):
+        df_factor = getattr(program_obj, "df_factor", None)
+        if df_factor is not None:
+            pass  # factorised AO integrals: no n^4 tensor (ao2mo.py, df_factor)
+        elif isinstance(program_obj, np.ndarray) or nv.is_device_array(program_obj):
             I = program_obj  # noqa: E741
         elif hasattr(program_obj, "ao_eri"):
             I = program_obj.ao_eri  # noqa: E741
@@ -117,7 +120,7 @@ class Solver(ABC):
         else:
             raise RuntimeError
         ao2mo = AO2MO(self.mocoeffs, self.occupations, I=I, device_results=True,
-                      ao_symmetry=self.ao_symmetry)
+                      ao_symmetry=self.ao_symmetry, df_factor=df_factor)
         if tei_mo_type == AO2MOTransformationType.partial and nden == 2:
             ao2mo.perform_uhf_partial()
         elif tei_mo_type == AO2MOTransformationType.partial and nden == 1:

@@ -555,6 +555,55 @@ def test_polarizability_and_magnetizability_wrappers():
     np.testing.assert_allclose(mag.magnetizability, ref_m["results"][0] / 4, rtol=0, atol=1e-9)
 
 
+def test_ao2mo_from_factor_matches_dense_route():
+    """MO blocks straight from the factor B[P, mu nu] (no n^4 tensor) against the
+    oracle's dense transforms of I = B^T B; RHF/UHF, partial/full, and through Solver.form_tei_mo."""
+    from pymolresponse_b200 import cphf, operators, solvers, synthetic
+    from pymolresponse_b200.ao2mo import AO2MO
+    from pymolresponse_b200.core import Hamiltonian, Program, Spin
+
+    def close(got, want):
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+
+    n, o = 21, 4
+    case = synthetic.rhf_case(n, o)
+    a = AO2MO(case["C"], case["occupations"], df_factor=case["B"])
+    a.perform_rhf_partial()
+    for got, want in zip(a.tei_mo, orc.ao2mo_rhf_partial(case["I"], case["C"], o)):
+        close(got, want)
+    a.perform_rhf_full()
+    close(a.tei_mo[0], orc.ao2mo_rhf_full(case["I"], case["C"])[0])
+
+    na, nb = 5, 3
+    ucase = synthetic.uhf_case(n, na, nb)
+    u = AO2MO(ucase["C"], ucase["occupations"], df_factor=ucase["B"])
+    u.perform_uhf_partial()
+    want = orc.ao2mo_uhf_partial(ucase["I"], ucase["C"], ucase["occupations"])
+    assert len(u.tei_mo) == 6
+    for g_, w_ in zip(u.tei_mo, want):
+        close(g_, w_)
+    u.perform_uhf_full()
+    for g_, w_ in zip(u.tei_mo, orc.ao2mo_uhf_full(ucase["I"], ucase["C"])):
+        close(g_, w_)
+
+    class Prog:
+        df_factor = case["B"]
+
+    Or = synthetic.operator_integrals(n, 3, False)
+    ref = orc.run_cphf(case["C"], case["E"], case["occupations"],
+                       orc.ao2mo_rhf_partial(case["I"], case["C"], o), "partial",
+                       [{"ao_integrals": Or, "is_imaginary": False}], [0.0, 0.1])
+    solver = solvers.ExactInv(case["C"], case["E"], case["occupations"])
+    driver = cphf.CPHF(solver)
+    driver.add_operator(operators.Operator(label="dipole", is_imaginary=False, ao_integrals=Or))
+    driver.set_frequencies([0.0, 0.1])
+    driver.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet, program=Program.Arrays,
+               program_obj=Prog())
+    for f in range(2):
+        np.testing.assert_allclose(driver.results[f], ref["results"][f], rtol=0, atol=1e-9)
+
+
 def test_ord_and_gtensor_wrappers():
     """Mixed imaginary/real multi-operator batches through the ORD and g-tensor wrappers (reference
     properties/optrot.py:13-96, properties/magnetic.py:57-190) against the oracle's result blocks."""

@@ -378,7 +378,15 @@ def run_ours(args):
 
     # ---------------- roofline pass: per-launch CUDA events on the dominant kernel -----------
     stages = {}
-    one_step(w, inp, I_dev, True, world, stage_ms=stages)   # untimed extra step: per-stage CUDA events
+    from pymolresponse_b200 import _engine as eng
+    from pymolresponse_b200 import ao2mo as ao2mo_mod
+
+    eng.STAGE_TIMES = True          # untimed extra step: per-stage CUDA events (adds synchronisation)
+    ao2mo_mod.LAST_STAGE.clear()
+    res_s = one_step(w, inp, I_dev, True, world, stage_ms=stages)
+    eng.STAGE_TIMES = False
+    stages["ao2mo_parts"] = dict(ao2mo_mod.LAST_STAGE.get("ms", {}))
+    stages["sweep_parts"] = dict((res_s.get("stats") or {}).get("ms", {}))
     sync_all()
 
     roofline = None

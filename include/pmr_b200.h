@@ -183,6 +183,14 @@ int pmr_potrs(const double* L, int N, long long lda, int batch, long long stride
               int first_row /* rows of B above it are zero on entry (0 = general) */,
               int lower_only /* 1: rows of X above first_row are not computed (left zero) */,
               double* work, void* stream);
+/* The two substitutions of pmr_potrs on their own (one matrix): the forward pass of the 512-row
+ * chunks [chunk_lo, chunk_hi) only needs the factor's columns up to chunk_hi*512, so it can follow a
+ * factorisation that is still running (the distributed Cholesky hands over one block column at a
+ * time); `work` (N*nrhs doubles, zero on first use) carries Y to the backward call. */
+int pmr_potrs_phase(const double* L, int N, long long lda, const double* dinv, double* B, int nrhs,
+                    long long ldb, int first_row, int lower_only, double* work,
+                    int backward /* 0: forward chunks, 1: backward pass */, int chunk_lo,
+                    int chunk_hi, void* stream);
 /* Lower triangle of A^-1 from the Cholesky factor (out may not alias L); work: N*N doubles. */
 int pmr_potri_lower(const double* L, int N, long long lda, const double* dinv, double* out,
                     long long ldo, double* work, void* stream);

@@ -22,6 +22,7 @@ the affected frequencies fall back to LU with partial pivoting on the full G(w).
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -63,7 +64,18 @@ def _comm_stream():
     return _comm_streams[dev]
 
 
-def potrf_distributed(A):
+def _chain_stream():
+    """High-priority stream for the panel chain of :func:`potrf_distributed` (the caller's stream
+    keeps the follow-up work that may run underneath it)."""
+    torch = nv.torch_mod()
+    dev = torch.cuda.current_device()
+    key = ("chain", dev)
+    if key not in _comm_streams:
+        _comm_streams[key] = torch.cuda.Stream(device=dev, priority=-1)
+    return _comm_streams[key]
+
+
+def potrf_distributed(A, on_panel=None):
     """Cholesky of ONE replicated (N, N) matrix with the work split over the torch.distributed ranks:
     512-wide block columns are dealt cyclically; the owner factors its block column
     (pmr_potrf_panel) and broadcasts the panel (+ its diagonal-block inverses); every rank stores it
@@ -73,7 +85,12 @@ def potrf_distributed(A):
 
     Look-ahead: as soon as panel J has arrived, the owner of J+1 updates that one block column,
     factors it and hands it to the broadcast on a side stream; the remaining rank-512 updates of step
-    J (the bulk of the flops) run on the main stream underneath the transfer."""
+    J (the bulk of the flops) run on the main stream underneath the transfer.
+
+    The whole factorisation runs on a high-priority stream; ``on_panel(J, event)`` is called (on the
+    caller's stream context) once block column J of the factor and its diagonal-block inverses are
+    final on this rank -- work enqueued there on the caller's stream after ``event`` fills the gaps
+    of the latency-bound panel chain (the shared K^-1 starts its forward substitutions this way)."""
     from pymolresponse_b200 import distributed as pd
 
     rank, world = pd.rank_world()
@@ -85,7 +102,9 @@ def potrf_distributed(A):
     dinv = nv.zeros(1, max(1, nbd))
     info = torch.zeros(1, dtype=torch.int32, device=nv.device())
     nblk = (N + OUTER_BLOCK - 1) // OUTER_BLOCK
-    main = torch.cuda.current_stream()
+    caller = torch.cuda.current_stream()
+    main = _chain_stream()
+    main.wait_stream(caller)
     comm = _comm_stream()
     packs = {}
 
@@ -125,23 +144,32 @@ def potrf_distributed(A):
             done.record(comm)
         packs[J] = (pack, done)
 
-    post(0)
+    with torch.cuda.stream(main):
+        post(0)
     for J in range(nblk):
-        j0, jend, kw, nd, d0 = geometry(J)
-        pack, done = packs.pop(J)
-        main.wait_event(done)
-        if J % world != rank:
-            A[j0:, j0:jend].copy_(pack[: (N - j0) * kw].view(N - j0, kw))
-            dinv[0, d0:d0 + nd].copy_(pack[(N - j0) * kw: (N - j0) * kw + nd])
-            info.copy_(torch.maximum(info, pack[-1:].to(torch.int32)))
-        if J + 1 < nblk:
-            if (J + 1) % world == rank:
-                update(J, J + 1)
-            post(J + 1)
-        for Jp in range(J + 2, nblk):
-            if Jp % world == rank:
-                update(J, Jp)
-        del pack
+        with torch.cuda.stream(main):
+            j0, jend, kw, nd, d0 = geometry(J)
+            pack, done = packs.pop(J)
+            main.wait_event(done)
+            if J % world != rank:
+                A[j0:, j0:jend].copy_(pack[: (N - j0) * kw].view(N - j0, kw))
+                dinv[0, d0:d0 + nd].copy_(pack[(N - j0) * kw: (N - j0) * kw + nd])
+                info.copy_(torch.maximum(info, pack[-1:].to(torch.int32)))
+            final = None
+            if on_panel is not None:
+                final = torch.cuda.Event()
+                final.record(main)
+            if J + 1 < nblk:
+                if (J + 1) % world == rank:
+                    update(J, J + 1)
+                post(J + 1)
+            for Jp in range(J + 2, nblk):
+                if Jp % world == rank:
+                    update(J, Jp)
+            del pack
+        if on_panel is not None:
+            on_panel(J, final, dinv)
+    caller.wait_stream(main)
     return dinv, info
 
 
@@ -251,6 +279,36 @@ class LinAlgError(np.linalg.LinAlgError):
     pass
 
 
+STAGE_TIMES = os.environ.get("PMR_STAGE_TIMES", "0") == "1"
+
+
+class _StageClock:
+    """Optional CUDA-event stopwatch for the solver's stages (PMR_STAGE_TIMES=1 or
+    ``_engine.STAGE_TIMES = True``); off by default so that the step has no extra synchronisation."""
+
+    def __init__(self, sink):
+        self.on = STAGE_TIMES
+        self.sink = sink
+        self.marks = []
+        if self.on:
+            self.mark("start")
+
+    def mark(self, name):
+        if self.on:
+            e = nv.torch_mod().cuda.Event(enable_timing=True)
+            e.record()
+            self.marks.append((name, e))
+
+    def finish(self):
+        if not self.on or len(self.marks) < 2:
+            return
+        nv.torch_mod().cuda.synchronize()
+        ms = self.sink.setdefault("ms", {})
+        for (_, e0), (name, e1) in zip(self.marks[:-1], self.marks[1:]):
+            ms[name] = ms.get(name, 0.0) + e0.elapsed_time(e1)
+        self.marks = []
+
+
 class HalfSizeSystem:
     """K = A + B_ref and M = A - B_ref on the device; solves all frequencies and columns."""
 
@@ -273,6 +331,73 @@ class HalfSizeSystem:
         free = total - torch.cuda.memory_allocated(dev) - (2 << 30)
         per = max(1, self.N * self.N * 8)
         return int(max(1, min(nf, (free * self.memory_fraction) // per)))
+
+    def _kinv_blocks(self):
+        """Column blocks of the shared K^-1: 2*world blocks, rank r owns blocks r and 2*world-1-r."""
+        from pymolresponse_b200 import distributed as pd
+
+        rank, world = pd.rank_world()
+        nblocks = 2 * world
+        bounds = [pd.shard_range(self.N, b, nblocks) for b in range(nblocks)]
+        return rank, world, nblocks, bounds
+
+    def _factor_and_invert_distributed(self, Kf):
+        """potrf_distributed(K) with the forward substitutions of this rank's K^-1 column blocks
+        following the factorisation panel by panel on the caller's (lower-priority) stream, then the
+        backward substitutions and the all-gather.  Returns (dinv, info, Kinv or None)."""
+        from pymolresponse_b200 import distributed as pd
+
+        torch = nv.torch_mod()
+        L = nv.lib()
+        N = self.N
+        lda = int(Kf.stride(0))
+        rank, world, nblocks, bounds = self._kinv_blocks()
+        mine = [bounds[rank], bounds[nblocks - 1 - rank]]
+        wmax = max(hi - lo for lo, hi in bounds)
+        caller = torch.cuda.current_stream()
+        jobs = []
+        for slot, (lo, hi) in enumerate(mine):
+            w = hi - lo
+            if w == 0:
+                continue
+            rhs = nv.zeros(N, w)
+            shift_diagonal(rhs, w, 1.0, offset=lo * w)
+            jobs.append({"slot": slot, "w": w, "rhs": rhs, "work": nv.zeros(N, w),
+                         "first": (lo // 128) * 128})
+
+        def on_panel(J, final, dinv):
+            caller.wait_event(final)
+            for job in jobs:
+                if (J + 1) * OUTER_BLOCK <= job["first"]:
+                    continue                      # this chunk of the right-hand side is still zero
+                nv.check(L.pmr_potrs_phase(nv.ptr(Kf), N, lda, nv.ptr(dinv), nv.ptr(job["rhs"]),
+                                           job["w"], job["w"], job["first"], 1, nv.ptr(job["work"]),
+                                           0, J, J + 1, nv.stream_ptr()))
+
+        dk, info = potrf_distributed(Kf, on_panel=on_panel)
+        if int(info.item()) != 0:
+            return dk, info, None
+        local = nv.zeros(N, 2 * wmax)
+        for job in jobs:
+            nv.check(L.pmr_potrs_phase(nv.ptr(Kf), N, lda, nv.ptr(dk), nv.ptr(job["rhs"]), job["w"],
+                                       job["w"], job["first"], 1, nv.ptr(job["work"]), 1, 0, 1 << 30,
+                                       nv.stream_ptr()))
+            local[:, job["slot"] * wmax:job["slot"] * wmax + job["w"]].copy_(job["rhs"])
+        return dk, info, self._gather_kinv(local, wmax)
+
+    def _gather_kinv(self, local, wmax):
+        from pymolresponse_b200 import distributed as pd
+
+        rank, world, nblocks, bounds = self._kinv_blocks()
+        N = self.N
+        gathered = pd.allgather_columns(local, 2 * wmax * world)   # equal widths per rank
+        Kinv = nv.empty(N, N)
+        for r in range(world):
+            for k, b in enumerate((r, nblocks - 1 - r)):
+                lo, hi = bounds[b]
+                src0 = r * 2 * wmax + k * wmax
+                Kinv[:, lo:hi].copy_(gathered[:, src0:src0 + (hi - lo)])
+        return Kinv
 
     def _kinv_distributed(self, Kfac, dinvK):
         """K^-1 with the work split over the ranks: every rank solves K X = E_J for its own identity
@@ -299,14 +424,7 @@ class HalfSizeSystem:
             shift_diagonal(rhs, w, 1.0, offset=lo * w)
             potrs(Kfac, dinvK, rhs, first_row=(lo // 128) * 128, lower_only=True)
             local[:, k * wmax:k * wmax + w].copy_(rhs)
-        gathered = pd.allgather_columns(local, 2 * wmax * world)   # equal widths per rank
-        Kinv = nv.empty(N, N)
-        for r in range(world):
-            for k, b in enumerate((r, nblocks - 1 - r)):
-                lo, hi = bounds[b]
-                src0 = r * 2 * wmax + k * wmax
-                Kinv[:, lo:hi].copy_(gathered[:, src0:src0 + (hi - lo)])
-        return Kinv
+        return self._gather_kinv(local, wmax)
 
     def solve(self, g_rows, signs, frequencies, allow_fallback=True, distributed=False,
               global_frequencies=None):
@@ -331,6 +449,7 @@ class HalfSizeSystem:
         if nf == 0 and not share_kinv:
             return xy
         G = g_rows.t().contiguous()  # (N, ncols)
+        clock = _StageClock(self.stats)
 
         Kfac = dinvK = Kinv = T = None
         bad = set()
@@ -338,8 +457,12 @@ class HalfSizeSystem:
             if self._Kfac is None and not self._K_bad:
                 Kf = self.K.clone()
                 if share_kinv and self.N >= DISTRIBUTED_POTRF_MIN_N:
-                    dk, infoK = potrf_distributed(Kf)   # collective: every rank is here (share_kinv)
+                    # collective: every rank is here (share_kinv); K^-1 comes out of the same pass
+                    dk, infoK, kinv = self._factor_and_invert_distributed(Kf)
                     self.stats["potrf_shared"] = self.stats.get("potrf_shared", 0) + 1
+                    if kinv is not None:
+                        self._Kinv = kinv
+                        self.stats["potri_shared"] = self.stats.get("potri_shared", 0) + 1
                 else:
                     dk, infoK = potrf(Kf)
                 self.stats["potrf"] += 1
@@ -350,6 +473,7 @@ class HalfSizeSystem:
             if self._K_bad:
                 bad = set(range(nf))
             Kfac, dinvK = self._Kfac, self._dinvK
+        clock.mark("potrf_K")
         if not bad and (share_kinv or any_dyn):
             if self._Kinv is None:
                 if share_kinv:
@@ -359,7 +483,9 @@ class HalfSizeSystem:
                     self._Kinv = potri_lower(Kfac, dinvK)
                     self.stats["potri"] += 1
             Kinv = self._Kinv
+        clock.mark("K_inverse")
         if nf == 0:
+            clock.finish()
             return xy
         if not bad and any_dyn and imag_cols:
             T = G[:, imag_cols].contiguous()
@@ -379,7 +505,9 @@ class HalfSizeSystem:
                 if need_m:
                     S = shifted_combine(self.M, Kinv if any_dyn else None, [0.0] * nfc,
                                         [-(w * w) for w in ws])
+                    clock.mark("shifted_combine")
                     dinvS, infoS = potrf(S, batch=nfc)
+                    clock.mark("potrf_S")
                     self.stats["potrf_batch"] += nfc
                     infos = infoS.cpu().numpy()
                 two_g_real = None
@@ -418,6 +546,7 @@ class HalfSizeSystem:
                         nv.ptr(p_rows) if p_rows is not None else C.c_void_p(0), nv.ptr(m_rows),
                         ncols, N, N, N, nv.ptr(xy[f]), 2 * N, nv.stream_ptr()))
                 del S, dinvS, rhs_m, p_all
+                clock.mark("solves")
 
         if bad:
             if not allow_fallback:
@@ -427,6 +556,8 @@ class HalfSizeSystem:
             for f in sorted(bad):
                 xy[f].copy_(self.solve_lu(g_rows, signs, freqs[f]))
                 self.stats["lu_fallback"] += 1
+        clock.mark("lu_fallback")
+        clock.finish()
         return xy
 
     def solve_lu(self, g_rows, signs, w):

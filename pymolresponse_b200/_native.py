@@ -102,6 +102,8 @@ SYMBOLS = {
     "pmr_potrf_panel": (C.c_int, [c_dp, C.c_int, c_ll, C.c_int, c_dp, c_dp, c_dp]),
     "pmr_potrs": (C.c_int, [c_dp, C.c_int, c_ll, C.c_int, c_ll, c_dp, c_dp, C.c_int, c_ll, c_ll,
                             C.c_int, C.c_int, c_dp, c_dp]),
+    "pmr_potrs_phase": (C.c_int, [c_dp, C.c_int, c_ll, c_dp, c_dp, C.c_int, c_ll, C.c_int, C.c_int,
+                                  c_dp, C.c_int, C.c_int, C.c_int, c_dp]),
     "pmr_potri_lower": (C.c_int, [c_dp, C.c_int, c_ll, c_dp, c_dp, c_ll, c_dp, c_dp]),
     "pmr_shifted_combine": (C.c_int, [c_dp, c_dp, C.c_int, c_ll, c_ll, C.POINTER(C.c_double),
                                       C.POINTER(C.c_double), C.c_int, c_dp, c_ll, c_ll, c_dp]),

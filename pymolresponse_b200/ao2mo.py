@@ -36,6 +36,10 @@ from pymolresponse_b200 import _native as nv
 from pymolresponse_b200.utils import fix_mocoeffs_shape
 
 
+#: stage times of the last partial transforms when ``_engine.STAGE_TIMES`` is on ({"ms": {...}})
+LAST_STAGE: dict = {}
+
+
 def _transform_dev(I, C1, C2, C3, C4):
     """I (n,n,n,n) and Ck (n, dk): contiguous CUDA tensors -> (d1,d2,d3,d4) CUDA tensor."""
     n = int(I.shape[0])
@@ -65,8 +69,10 @@ def partial_blocks_dev(I_slab, nu_lo, Cbra, nocc_bra, kets, want_oovv, nu_block=
     reduce-scattered over i, every rank finishes the two virtual quarters for its own i only and the
     rows are all-gathered -- the o^2 n^2 (v + v^2/n) tail flops are not repeated on every rank.
     """
+    from pymolresponse_b200 import _engine as eng
     from pymolresponse_b200 import distributed as pd
 
+    clock = eng._StageClock(LAST_STAGE)
     L = nv.lib()
     n, nu_cnt = int(I_slab.shape[0]), int(I_slab.shape[1])
     norb = int(Cbra.shape[1])
@@ -98,10 +104,13 @@ def partial_blocks_dev(I_slab, nu_lo, Cbra, nocc_bra, kets, want_oovv, nu_block=
         len(kets), kd, nv.ptr(oovv) if want_oovv else C.c_void_p(0), 2 if split_tail else 0,
         int(nu_block), nv.ptr(ws), ws_n, nv.stream_ptr()))
     del ws
+    clock.mark("transform")
     if reduce:
         pd.allreduce_blocks(outs)
+        clock.mark("allreduce_ovov")
         if split_tail:
             Y_loc = pd.reduce_scatter_rows(oovv, o1)            # (rows, o1, n, n), summed over ranks
+            clock.mark("reduce_scatter_oovv")
             del oovv
             rows = int(Y_loc.shape[0])
             loc = nv.zeros(rows, o1, v1, v1)
@@ -110,9 +119,12 @@ def partial_blocks_dev(I_slab, nu_lo, Cbra, nocc_bra, kets, want_oovv, nu_block=
                 tws = nv.empty(tw)
                 nv.check(L.pmr_ao2mo_oovv_tail(nv.ptr(Y_loc), n, nv.ptr(Cbra, o1), ldc1, rows, o1, v1,
                                                nv.ptr(loc), 0, nv.ptr(tws), tw, nv.stream_ptr()))
+            clock.mark("oovv_tail")
             oovv = pd.allgather_rows(loc, o1)
+            clock.mark("allgather_oovv")
         elif want_oovv:
             pd.allreduce_blocks([oovv])
+    clock.finish()
     return outs, oovv
 
 

@@ -22,9 +22,12 @@ namespace {
 
 int auto_nu_block(int n, int nu_cnt, int o1, int nu_block) {
   if (nu_block > 0) return std::min(nu_block, nu_cnt);
-  // keep the half-transformed slab H1 = o1 * nb * n^2 doubles near 2^28 doubles (2 GiB)
+  // Keep the half-transformed slab H1 = o1 * nb * n^2 doubles within 2^30 doubles (8 GiB).  Every
+  // nu-block costs one read-modify-write pass over the accumulators ((ia|jb) and the
+  // half-transformed (ij|la si), 15 GB together at n = 512, o = 64), so few large blocks win:
+  // with 2 GiB blocks (nb = 16, four passes) the transform ran at 17 TFLOP/s at that size.
   const double per_nu = (double)o1 * n * (double)n;
-  int nb = (int)std::max(1.0, std::min((double)nu_cnt, (double)(1LL << 28) / per_nu));
+  int nb = (int)std::max(1.0, std::min((double)nu_cnt, (double)(1LL << 30) / per_nu));
   const long long lim = ((1LL << 31) - 1) / ((long long)n * n);
   nb = (int)std::min<long long>(nb, lim);
   return std::max(1, nb);

@@ -539,11 +539,12 @@ extern "C" int pmr_potrf_panel(double* A, int N, long long lda, int j0, double* 
   return 0;
 }
 
-extern "C" int pmr_potrs(const double* L, int N, long long lda, int batch, long long stride_l,
-                         const double* dinv, double* B, int nrhs, long long ldb,
-                         long long stride_b, int first_row, int lower_only, double* work,
-                         void* stream) {
-  cudaStream_t st = as_stream(stream);
+// phases: bit 0 = forward substitution for the 512-row chunks [chunk_lo, chunk_hi), bit 1 = backward
+// substitution, bit 2 = clear the part of `work` the forward pass skips.
+static int potrs_impl(const double* L, int N, long long lda, int batch, long long stride_l,
+                      const double* dinv, double* B, int nrhs, long long ldb, long long stride_b,
+                      int first_row, int lower_only, double* work, int phases, int chunk_lo,
+                      int chunk_hi, cudaStream_t st) {
   PMR_REQUIRE(N >= 0 && nrhs >= 0 && batch >= 1 && batch <= 65535, "potrs: bad sizes");
   if (N == 0 || nrhs == 0) return 0;
   PMR_REQUIRE(L && dinv && B && work, "potrs: null pointer");
@@ -555,7 +556,7 @@ extern "C" int pmr_potrs(const double* L, int N, long long lda, int batch, long 
   // identity): their block rows are skipped, only the matching part of `work` is cleared.
   PMR_REQUIRE(first_row >= 0 && first_row <= N, "potrs: bad first_row");
   const int kb0 = first_row / NB;
-  if (kb0 > 0)
+  if (kb0 > 0 && (phases & 4))
     for (int b = 0; b < batch; ++b)
       PMR_CHECK_CUDA(cudaMemsetAsync(work + (long long)b * wstride, 0,
                                      sizeof(double) * (size_t)kb0 * NB * nrhs, st));
@@ -563,8 +564,10 @@ extern "C" int pmr_potrs(const double* L, int N, long long lda, int batch, long 
   // after the other with small in-chunk updates, then ONE rank-NBO update carries the chunk into
   // the rest of the right-hand side (k = 512 keeps the DMMA pipeline full; k = 128 did not).
   constexpr int NBO = 512;
-  const int cb0 = (kb0 * NB) / NBO;
-  for (int c0 = cb0 * NBO; c0 < N; c0 += NBO) {
+  const int cb0 = std::max((kb0 * NB) / NBO, chunk_lo);
+  const int cb1 = std::min((N + NBO - 1) / NBO, chunk_hi);
+  for (int cb = cb0; cb < cb1 && (phases & 1); ++cb) {
+    const int c0 = cb * NBO;
     const int cend = std::min(N, c0 + NBO);
     for (int k0 = std::max(c0, kb0 * NB); k0 < cend; k0 += NB) {
       const int jb = std::min(NB, N - k0), inrest = cend - k0 - jb;
@@ -595,7 +598,7 @@ extern "C" int pmr_potrs(const double* L, int N, long long lda, int batch, long 
   // block) are not wanted (a symmetric result whose upper part nobody reads) and stay zero.
   const int r0 = lower_only ? kb0 * NB : 0;
   const int nchunk = (N + NBO - 1) / NBO;
-  for (int cb = nchunk - 1; cb >= r0 / NBO; --cb) {
+  for (int cb = nchunk - 1; cb >= r0 / NBO && (phases & 2); --cb) {
     const int c0 = std::max(cb * NBO, r0), cend = std::min(N, cb * NBO + NBO);
     const int klast = ((cend - 1) / NB) * NB;
     for (int k0 = klast; k0 >= c0; k0 -= NB) {
@@ -622,6 +625,21 @@ extern "C" int pmr_potrs(const double* L, int N, long long lda, int batch, long 
     }
   }
   return 0;
+}
+
+extern "C" int pmr_potrs(const double* L, int N, long long lda, int batch, long long stride_l,
+                         const double* dinv, double* B, int nrhs, long long ldb,
+                         long long stride_b, int first_row, int lower_only, double* work,
+                         void* stream) {
+  return potrs_impl(L, N, lda, batch, stride_l, dinv, B, nrhs, ldb, stride_b, first_row, lower_only,
+                    work, 1 | 2 | 4, 0, 1 << 30, as_stream(stream));
+}
+
+extern "C" int pmr_potrs_phase(const double* L, int N, long long lda, const double* dinv, double* B,
+                               int nrhs, long long ldb, int first_row, int lower_only, double* work,
+                               int backward, int chunk_lo, int chunk_hi, void* stream) {
+  return potrs_impl(L, N, lda, 1, 0, dinv, B, nrhs, ldb, 0, first_row, lower_only, work,
+                    backward ? 2 : 1, chunk_lo, chunk_hi, as_stream(stream));
 }
 
 extern "C" int pmr_potri_lower(const double* L, int N, long long lda, const double* dinv,

@@ -497,7 +497,8 @@ def run_ours(args):
                    "h2d_bytes_per_step": int(lib.pmr_eri_s8_bytes(n, nv.ERI_S8_LAYOUT)) + int(small),
                    "d2h_bytes_per_step": int(d2h), "pinned_host_input": bool(I_host_t.is_pinned()),
                    "upload": "permutationally unique part of the AO ERI array (ao_symmetry='s8': "
-                             "mu >= la >= si, a sixth of the tensor), completed on the device",
+                             "rows (la, si <= la), columns from (la, 0) on -- a sixth of the tensor "
+                             "in long runs), completed on the device",
                    "whole_array_upload": full}
         del I_host_t, I_host
     elif e2e_note is not None:

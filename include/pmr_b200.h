@@ -257,9 +257,11 @@ int pmr_cphf_update(double* x, const double* x_old, const double* rhs, const dou
  * solvers.py:86-127, and always carry this symmetry).
  * layout 0 ("row prefix", ~n^4/3 doubles): for each mu the rows (mu, 0..mu), columns up to
  *   (mu, mu) -- long contiguous runs;  layout 1 ("box", ~n^4/6 doubles): for each la the entries
- *   (mu >= la, nu | la, si <= la) -- half the bytes in runs of (la+1) doubles.
+ *   (mu >= la, nu | la, si <= la) -- half the bytes in runs of (la+1) doubles;  layout 2 ("tail",
+ *   the default): the pair-swapped image of the box, rows (la, si <= la), columns from (la, 0) to
+ *   the end -- the same sixth of the doubles in long runs.
  *   pmr_eri_s8_bytes     bytes that cross PCIe for basis size n
- *   pmr_eri_upload_s8    one strided DMA per mu (layout 0) / per la (layout 1);
+ *   pmr_eri_upload_s8    one strided DMA per mu (layout 0) / per la (layouts 1, 2);
  *                        host: full C-order (n,n,n,n) array (pinned for an asynchronous copy)
  *   pmr_eri_complete_s8  fills the rest of the tensor in place from the uploaded part
  * ------------------------------------------------------------------------------------------ */

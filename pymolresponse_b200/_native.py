@@ -216,8 +216,9 @@ def to_dev(x, dtype=None):
     return t.contiguous()
 
 
-# 1 ("box", a sixth of the tensor, 160 + 19 ms at n = 256) beats 0 ("row prefix", a third, 208 + 11 ms)
-ERI_S8_LAYOUT = int(os.environ.get("PMR_ERI_S8_LAYOUT", "1"))
+# measured at n = 256 (upload + completion): 0 "row prefix" (a third of the tensor) 208 + 11 ms,
+# 1 "box" (a sixth, short runs) 160 + 19 ms, 2 "tail" (the same sixth in long runs) 105 + 18 ms
+ERI_S8_LAYOUT = int(os.environ.get("PMR_ERI_S8_LAYOUT", "2"))
 
 
 def upload_eri_s8(I, layout=None):  # noqa: E741

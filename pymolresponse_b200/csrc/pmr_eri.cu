@@ -16,6 +16,16 @@
 //   2. row (mu, nu), mu < nu  <-  row (nu, mu), columns (la, si) in [0, nu]^2;
 //      now every row P holds the columns Q with m(Q) <= m(P);
 //   3. entry (P, Q) with m(Q) > m(P)  <-  entry (Q, P)   (64x64 tiles through shared memory).
+//
+// layout 2 ("tail", the same sixth of the doubles in LONG runs): for every la one strided DMA of the
+// rows (la, si <= la), columns from (la, 0) to the end -- the pair-swapped image of the box, i.e. the
+// entries (P, Q) with p2 <= p1 <= q1.  The narrow rows of the box cost the DMA a fixed 6.5 ns each
+// (8.4 M rows at n = 256: 160 ms for 5.8 GB); here the same bytes move at the full PCIe rate (105 ms).
+// Completion, with m(P) = max(p1, p2):
+//   1. row (b, a), b < a  <-  row (a, b) on the columns from (a, 0) on; every row P now holds the
+//      columns Q with q1 >= m(P);
+//   2. in every row: (d, c) <- (c, d) for d < m(P) <= c; now the columns with m(Q) >= m(P);
+//   3. entry (P, Q) with m(Q) < m(P)  <-  entry (Q, P).
 #include <algorithm>
 
 #include "pmr_common.cuh"
@@ -122,11 +132,68 @@ __global__ void __launch_bounds__(256) eri_box_pass3_kernel(double* __restrict__
   }
 }
 
+// ---- layout 2 -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) eri_tail_pass1_kernel(double* __restrict__ I, int n) {
+  const int a = blockIdx.z, b = blockIdx.y;
+  if (b >= a) return;
+  const long long n2 = (long long)n * n;
+  const long long start = (long long)a * n;
+  const double* src = I + ((long long)a * n + b) * n2;
+  double* dst = I + ((long long)b * n + a) * n2;
+  const long long base = start + (long long)blockIdx.x * (256 * 8);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const long long c = base + u * 256 + threadIdx.x;
+    if (c < n2) dst[c] = src[c];
+  }
+}
+
+__global__ void __launch_bounds__(256) eri_tail_pass2_kernel(double* __restrict__ I, int n) {
+  // one block per row P = (p1, p2): (d, c) <- (c, d) for d < m <= c
+  const int p1 = blockIdx.y, p2 = blockIdx.x;
+  const int m = p1 > p2 ? p1 : p2;
+  const int w = n - m;
+  if (m == 0 || w == 0) return;
+  double* row = I + ((long long)p1 * n + p2) * (long long)n * n;
+  for (int idx = threadIdx.x; idx < m * w; idx += 256) {
+    const int d = idx / w, c = m + (idx - d * w);       // destination (d, c): coalesced in c
+    row[(long long)d * n + c] = row[(long long)c * n + d];
+  }
+}
+
+__global__ void __launch_bounds__(256) eri_tail_pass3_kernel(double* __restrict__ I, int n,
+                                                             long long P) {
+  // destination tile (rows r0.., cols c0..): entries with m(col) < m(row) take the transposed one
+  __shared__ double tile[TT][TT + 1];
+  const long long r0 = (long long)blockIdx.y * TT, c0 = (long long)blockIdx.x * TT;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const long long cc = c0 + tx;
+  const int mcol = cc < P ? pair_max(cc, n) : (1 << 30);
+  int any = 0;
+#pragma unroll 4
+  for (int r = ty; r < TT; r += 4) {
+    const long long rr = r0 + r;
+    if (rr < P && mcol < pair_max(rr, n)) any = 1;
+  }
+  if (!__syncthreads_or(any)) return;
+#pragma unroll 4
+  for (int r = ty; r < TT; r += 4) {
+    const long long sr = c0 + r, sc = r0 + tx;
+    if (sr < P && sc < P) tile[r][tx] = I[sr * P + sc];
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (int r = ty; r < TT; r += 4) {
+    const long long rr = r0 + r;
+    if (rr < P && cc < P && mcol < pair_max(rr, n)) I[rr * P + cc] = tile[tx][r];
+  }
+}
+
 }  // namespace
 
 extern "C" long long pmr_eri_s8_bytes(int n, int layout) {
   long long total = 0;
-  if (layout == 1) {
+  if (layout == 1 || layout == 2) {
     for (long long la = 0; la < n; ++la) total += (n - la) * n * (la + 1) * 8;
   } else {
     for (long long mu = 0; mu < n; ++mu) total += (mu + 1) * (mu * n + mu + 1) * 8;
@@ -167,10 +234,19 @@ extern "C" void pmr_set_upload_streams(int count) {
 
 extern "C" int pmr_eri_upload_s8(const double* host, double* dev, int n, int layout, void* stream) {
   cudaStream_t st = as_stream(stream);
-  PMR_REQUIRE(n >= 0 && (layout == 0 || layout == 1), "eri_upload_s8: bad n or layout");
+  PMR_REQUIRE(n >= 0 && layout >= 0 && layout <= 2, "eri_upload_s8: bad n or layout");
   if (n == 0) return 0;
   PMR_REQUIRE(host && dev, "eri_upload_s8: null pointer");
   const size_t n2 = (size_t)n * n;
+  if (layout == 2) {
+    for (size_t la = 0; la < (size_t)n; ++la) {
+      const size_t off = la * n * n2 + la * n;        // row (la, 0), column (la, 0)
+      PMR_CHECK_CUDA(cudaMemcpy2DAsync(dev + off, n2 * sizeof(double), host + off,
+                                       n2 * sizeof(double), (n - la) * n * sizeof(double), la + 1,
+                                       cudaMemcpyHostToDevice, st));
+    }
+    return 0;
+  }
   if (layout == 1) {
     const int ns = g_upload_streams;
     if (ns > 1) {
@@ -203,12 +279,25 @@ extern "C" int pmr_eri_upload_s8(const double* host, double* dev, int n, int lay
 
 extern "C" int pmr_eri_complete_s8(double* dev, int n, int layout, void* stream) {
   cudaStream_t st = as_stream(stream);
-  PMR_REQUIRE(n >= 0 && n <= 2047 && (layout == 0 || layout == 1),
+  PMR_REQUIRE(n >= 0 && n <= 2047 && layout >= 0 && layout <= 2,
               "eri_complete_s8: n out of range or bad layout");
   if (n <= 0) return 0;
   PMR_REQUIRE(dev, "eri_complete_s8: null pointer");
   const long long P = (long long)n * n;
   const unsigned nt = (unsigned)((P + TT - 1) / TT);
+  if (layout == 2) {
+    if (n > 1) {
+      const long long wmax = (long long)(n - 1) * n;   // widest tail: a = 1
+      dim3 grid((unsigned)((wmax + 2047) / 2048), (unsigned)n, (unsigned)n);
+      eri_tail_pass1_kernel<<<grid, 256, 0, st>>>(dev, n);
+      PMR_CHECK_LAUNCH("eri_tail_pass1_kernel");
+      eri_tail_pass2_kernel<<<dim3(n, n), 256, 0, st>>>(dev, n);
+      PMR_CHECK_LAUNCH("eri_tail_pass2_kernel");
+    }
+    eri_tail_pass3_kernel<<<dim3(nt, nt), 256, 0, st>>>(dev, n, P);
+    PMR_CHECK_LAUNCH("eri_tail_pass3_kernel");
+    return 0;
+  }
   if (layout == 1) {
     if (n > 1) {
       eri_box_pass1_kernel<<<dim3(n, n), 256, 0, st>>>(dev, n);

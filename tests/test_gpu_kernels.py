@@ -332,8 +332,8 @@ def _symmetric_eri(n, seed):
     return np.ascontiguousarray(T)
 
 
-@pytest.mark.parametrize("layout", [0, 1])
-@pytest.mark.parametrize("n", [1, 2, 7, 13, 32])
+@pytest.mark.parametrize("layout", [0, 1, 2])
+@pytest.mark.parametrize("n", [1, 2, 7, 13, 32, 70])
 def test_eri_upload_s8_rebuilds_the_full_tensor(n, layout):
     """Only the documented unique part is read from the host (everything else is poisoned with NaN
     here); the completed tensor in HBM equals the symmetric original bit for bit."""
@@ -343,9 +343,12 @@ def test_eri_upload_s8_rebuilds_the_full_tensor(n, layout):
     if layout == 0:       # rows (mu, nu <= mu), columns up to (mu, mu)
         for mu in range(n):
             keep[mu, :mu + 1].reshape(mu + 1, n * n)[:, :mu * n + mu + 1] = True
-    else:                 # (mu >= la, nu | la, si <= la)
+    elif layout == 1:     # (mu >= la, nu | la, si <= la)
         for la in range(n):
             keep[la:, :, la, :la + 1] = True
+    else:                 # rows (la, si <= la), columns from (la, 0) on
+        for la in range(n):
+            keep[la, :la + 1, la:, :] = True
     assert int(nv.lib().pmr_eri_s8_bytes(n, layout)) == 8 * int(keep.sum())
     H = np.where(keep, T, np.nan)
     got = nv.to_host(nv.upload_eri_s8(H, layout=layout))

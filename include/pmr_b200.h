@@ -183,6 +183,9 @@ int pmr_potrs(const double* L, int N, long long lda, int batch, long long stride
               int first_row /* rows of B above it are zero on entry (0 = general) */,
               int lower_only /* 1: rows of X above first_row are not computed (left zero) */,
               double* work, void* stream);
+/* 1 (default): the four dependent 128-row steps inside every 512-row chunk of a substitution run
+ * in ONE kernel (running right-hand side in shared memory) instead of eight small GEMM launches. */
+void pmr_set_fused_substitution(int on);
 /* The two substitutions of pmr_potrs on their own (one matrix): the forward pass of the 512-row
  * chunks [chunk_lo, chunk_hi) only needs the factor's columns up to chunk_hi*512, so it can follow a
  * factorisation that is still running (the distributed Cholesky hands over one block column at a

@@ -102,6 +102,7 @@ SYMBOLS = {
     "pmr_potrf_panel": (C.c_int, [c_dp, C.c_int, c_ll, C.c_int, c_dp, c_dp, c_dp]),
     "pmr_potrs": (C.c_int, [c_dp, C.c_int, c_ll, C.c_int, c_ll, c_dp, c_dp, C.c_int, c_ll, c_ll,
                             C.c_int, C.c_int, c_dp, c_dp]),
+    "pmr_set_fused_substitution": (None, [C.c_int]),
     "pmr_potrs_phase": (C.c_int, [c_dp, C.c_int, c_ll, c_dp, c_dp, C.c_int, c_ll, C.c_int, C.c_int,
                                   c_dp, C.c_int, C.c_int, C.c_int, c_dp]),
     "pmr_potri_lower": (C.c_int, [c_dp, C.c_int, c_ll, c_dp, c_dp, c_ll, c_dp, c_dp]),

@@ -539,6 +539,212 @@ extern "C" int pmr_potrf_panel(double* A, int N, long long lda, int j0, double* 
   return 0;
 }
 
+// ---- fused in-chunk substitutions ---------------------------------------------------------------
+// Inside one 512-row chunk a triangular solve is four dependent 128-row steps (multiply by the
+// inverse diagonal block, update the rows below / above inside the chunk).  As GEMM launches that is
+// eight launches of a few microseconds of work each, and with a handful of right-hand-side columns
+// the whole solve was launch bound (252 launches, 4.2 ms for 3 columns at N = 7168).  Here one CTA
+// takes four columns of one matrix through the whole chunk with the running right-hand side in
+// shared memory: warp-per-row dot products with the lanes along k (coalesced rows of L and of the
+// inverse blocks) for the forward pass, lanes along the output row for the transposed accesses of
+// the backward pass.  The rank-512 update that carries the chunk into the rest of the right-hand
+// side stays a DMMA GEMM.
+constexpr int TS_NC = 4;
+constexpr int TS_THREADS = 512;
+constexpr int TS_CHUNK = 512;
+static thread_local bool g_fused_chunks = true;
+
+__global__ void __launch_bounds__(TS_THREADS) chunk_forward_kernel(
+    const double* __restrict__ L, long long lda, long long stride_l, const double* __restrict__ dinv,
+    long long dstride, const double* __restrict__ B, long long ldb, long long stride_b,
+    double* __restrict__ W, long long ldw, long long wstride, int nrhs, int k_first, int cend) {
+  __shared__ double vec[TS_CHUNK][TS_NC];
+  __shared__ double ybuf[NB][TS_NC];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int col0 = blockIdx.x * TS_NC;
+  const int ncol = min(TS_NC, nrhs - col0);
+  const long long b = blockIdx.y;
+  L += b * stride_l; dinv += b * dstride; B += b * stride_b; W += b * wstride;
+  const int rows = cend - k_first;
+  for (int idx = tid; idx < rows * TS_NC; idx += TS_THREADS) {
+    const int r = idx / TS_NC, c = idx - r * TS_NC;
+    vec[r][c] = c < ncol ? B[(long long)(k_first + r) * ldb + col0 + c] : 0.0;
+  }
+  __syncthreads();
+  for (int k0 = k_first; k0 < cend; k0 += NB) {
+    const int jb = min(NB, cend - k0);
+    const int off = k0 - k_first;
+    const double* D = dinv + (long long)(k0 / NB) * NB * NB;
+    // y = D * vec[off : off + jb]   (D lower triangular: k <= r).  Four rows per warp at a time:
+    // all 16 loads of a lane are issued before the first use (the loop is latency, not flop, bound)
+    for (int r4 = warp * 4; r4 < jb; r4 += (TS_THREADS / 32) * 4) {
+      double d[4][4], acc[4][TS_NC];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int r = r4 + rr, k = lane + 32 * kk;
+          d[rr][kk] = (r < jb && k <= r) ? D[(long long)r * NB + k] : 0.0;
+        }
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+        for (int c = 0; c < TS_NC; ++c) acc[rr][c] = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const int k = lane + 32 * kk;
+        if (k < jb) {
+#pragma unroll
+          for (int c = 0; c < TS_NC; ++c) {
+            const double v = vec[off + k][c];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) acc[rr][c] = fma(d[rr][kk], v, acc[rr][c]);
+          }
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+        for (int c = 0; c < TS_NC; ++c) acc[rr][c] = warp_sum(acc[rr][c]);
+      if (lane == 0) {
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr)
+          if (r4 + rr < jb) {
+#pragma unroll
+            for (int c = 0; c < TS_NC; ++c) ybuf[r4 + rr][c] = acc[rr][c];
+          }
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < jb * TS_NC; idx += TS_THREADS) {
+      const int r = idx / TS_NC, c = idx - r * TS_NC;
+      if (c < ncol) W[(long long)(k0 + r) * ldw + col0 + c] = ybuf[r][c];
+    }
+    // rows below, inside the chunk: vec[i] -= L[i, k0 : k0 + jb] . y   (four rows per warp at a time)
+    for (int i4 = off + jb + warp * 4; i4 < rows; i4 += (TS_THREADS / 32) * 4) {
+      double l[4][4], acc[4][TS_NC];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int i = i4 + rr, k = lane + 32 * kk;
+          l[rr][kk] = (i < rows && k < jb) ? L[(long long)(k_first + i) * lda + k0 + k] : 0.0;
+        }
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+        for (int c = 0; c < TS_NC; ++c) acc[rr][c] = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const int k = lane + 32 * kk;
+        if (k < jb) {
+#pragma unroll
+          for (int c = 0; c < TS_NC; ++c) {
+            const double v = ybuf[k][c];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) acc[rr][c] = fma(l[rr][kk], v, acc[rr][c]);
+          }
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+        for (int c = 0; c < TS_NC; ++c) acc[rr][c] = warp_sum(acc[rr][c]);
+      if (lane == 0) {
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr)
+          if (i4 + rr < rows) {
+#pragma unroll
+            for (int c = 0; c < TS_NC; ++c) vec[i4 + rr][c] -= acc[rr][c];
+          }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(TS_THREADS) chunk_backward_kernel(
+    const double* __restrict__ L, long long lda, long long stride_l, const double* __restrict__ dinv,
+    long long dstride, const double* __restrict__ W, long long ldw, long long wstride,
+    double* __restrict__ B, long long ldb, long long stride_b, int nrhs, int c0, int cend) {
+  __shared__ double vec[TS_CHUNK][TS_NC];
+  __shared__ double part[4][NB][TS_NC];
+  __shared__ double xbuf[NB][TS_NC];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int col0 = blockIdx.x * TS_NC;
+  const int ncol = min(TS_NC, nrhs - col0);
+  const long long b = blockIdx.y;
+  L += b * stride_l; dinv += b * dstride; B += b * stride_b; W += b * wstride;
+  const int rows = cend - c0;
+  for (int idx = tid; idx < rows * TS_NC; idx += TS_THREADS) {
+    const int r = idx / TS_NC, c = idx - r * TS_NC;
+    vec[r][c] = c < ncol ? W[(long long)(c0 + r) * ldw + col0 + c] : 0.0;
+  }
+  __syncthreads();
+  const int klast = ((cend - 1) / NB) * NB;
+  for (int k0 = klast; k0 >= c0; k0 -= NB) {
+    const int jb = min(NB, cend - k0);
+    const int off = k0 - c0;
+    const double* D = dinv + (long long)(k0 / NB) * NB * NB;
+    // x = D^T * vec[off : off + jb]:  x[r] = sum_{k >= r} D[k][r] vec[off + k]; thread (q, r) takes
+    // the rows k = q, q + 4, ... (coalesced along r), the four partial sums meet in shared memory
+    {
+      const int r = tid & (NB - 1), q = tid >> 7;
+      double acc[TS_NC];
+#pragma unroll
+      for (int c = 0; c < TS_NC; ++c) acc[c] = 0.0;
+      if (r < jb) {
+        int k = r + ((q - r) & 3);                 // first k >= r with k % 4 == q
+        for (; k < jb; k += 32) {                  // eight loads in flight per thread
+          double d[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) d[u] = (k + 4 * u < jb) ? D[(long long)(k + 4 * u) * NB + r] : 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (k + 4 * u < jb) {
+#pragma unroll
+              for (int c = 0; c < TS_NC; ++c) acc[c] = fma(d[u], vec[off + k + 4 * u][c], acc[c]);
+            }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < TS_NC; ++c) part[q][r][c] = acc[c];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < jb * TS_NC; idx += TS_THREADS) {
+      const int r = idx / TS_NC, c = idx - r * TS_NC;
+      const double x = (part[0][r][c] + part[1][r][c]) + (part[2][r][c] + part[3][r][c]);
+      xbuf[r][c] = x;
+      if (c < ncol) B[(long long)(k0 + r) * ldb + col0 + c] = x;
+    }
+    __syncthreads();
+    // rows above, inside the chunk: vec[i] -= sum_k L[k0 + k, c0 + i] x[k]   (lanes along i)
+    for (int t = warp; t * 32 < off; t += TS_THREADS / 32) {
+      const int i = t * 32 + lane;
+      if (i < off) {
+        const double* Lcol = L + (long long)k0 * lda + c0 + i;
+        double acc[TS_NC];
+#pragma unroll
+        for (int c = 0; c < TS_NC; ++c) acc[c] = 0.0;
+        for (int k = 0; k < jb; k += 8) {          // eight loads in flight per thread
+          double l[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) l[u] = (k + u < jb) ? Lcol[(long long)(k + u) * lda] : 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (k + u < jb) {
+#pragma unroll
+              for (int c = 0; c < TS_NC; ++c) acc[c] = fma(l[u], xbuf[k + u][c], acc[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < TS_NC; ++c) vec[i][c] -= acc[c];
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // phases: bit 0 = forward substitution for the 512-row chunks [chunk_lo, chunk_hi), bit 1 = backward
 // substitution, bit 2 = clear the part of `work` the forward pass skips.
 static int potrs_impl(const double* L, int N, long long lda, int batch, long long stride_l,
@@ -569,7 +775,14 @@ static int potrs_impl(const double* L, int N, long long lda, int batch, long lon
   for (int cb = cb0; cb < cb1 && (phases & 1); ++cb) {
     const int c0 = cb * NBO;
     const int cend = std::min(N, c0 + NBO);
-    for (int k0 = std::max(c0, kb0 * NB); k0 < cend; k0 += NB) {
+    if (g_fused_chunks) {
+      dim3 grid((unsigned)((nrhs + TS_NC - 1) / TS_NC), (unsigned)batch);
+      chunk_forward_kernel<<<grid, TS_THREADS, 0, st>>>(L, lda, stride_l, dinv, dstride, B, ldb,
+                                                        stride_b, work, nrhs, wstride, nrhs,
+                                                        std::max(c0, kb0 * NB), cend);
+      PMR_CHECK_LAUNCH("chunk_forward_kernel");
+    }
+    for (int k0 = std::max(c0, kb0 * NB); k0 < cend && !g_fused_chunks; k0 += NB) {
       const int jb = std::min(NB, N - k0), inrest = cend - k0 - jb;
       const double* dk = dinv + (long long)(k0 / NB) * NB * NB;
       pmr_gemm_t g = make_gemm(jb, nrhs, jb, 1.0, dk, NB, 1, B + (long long)k0 * ldb, ldb, 1, 0.0,
@@ -601,7 +814,13 @@ static int potrs_impl(const double* L, int N, long long lda, int batch, long lon
   for (int cb = nchunk - 1; cb >= r0 / NBO && (phases & 2); --cb) {
     const int c0 = std::max(cb * NBO, r0), cend = std::min(N, cb * NBO + NBO);
     const int klast = ((cend - 1) / NB) * NB;
-    for (int k0 = klast; k0 >= c0; k0 -= NB) {
+    if (g_fused_chunks) {
+      dim3 grid((unsigned)((nrhs + TS_NC - 1) / TS_NC), (unsigned)batch);
+      chunk_backward_kernel<<<grid, TS_THREADS, 0, st>>>(L, lda, stride_l, dinv, dstride, work, nrhs,
+                                                         wstride, B, ldb, stride_b, nrhs, c0, cend);
+      PMR_CHECK_LAUNCH("chunk_backward_kernel");
+    }
+    for (int k0 = klast; k0 >= c0 && !g_fused_chunks; k0 -= NB) {
       const int jb = std::min(NB, N - k0);
       const double* dk = dinv + (long long)(k0 / NB) * NB * NB;
       pmr_gemm_t g = make_gemm(jb, nrhs, jb, 1.0, dk, 1, NB, work + (long long)k0 * nrhs, nrhs, 1,
@@ -626,6 +845,8 @@ static int potrs_impl(const double* L, int N, long long lda, int batch, long lon
   }
   return 0;
 }
+
+extern "C" void pmr_set_fused_substitution(int on) { g_fused_chunks = on != 0; }
 
 extern "C" int pmr_potrs(const double* L, int N, long long lda, int batch, long long stride_l,
                          const double* dinv, double* B, int nrhs, long long ldb,

@@ -458,6 +458,8 @@ def run_ours(args):
         nfreq = len(w["pol_freqs"])
         d2h = nfreq * (3 * 2 * nov * 8 + 72) + (3 * 2 * nov * 8 + 72 if w["magnetizability"] else 0)
 
+        e2e_diffs = []
+
         def timed_e2e(sym):
             one_step(w, inp, I_host, False, world, ao_symmetry=sym)
             sync_all()
@@ -469,8 +471,13 @@ def run_ours(args):
             tt = torch.tensor([e0.elapsed_time(e1) / e2e_steps], dtype=torch.float64, device="cuda")
             if world > 1:
                 pd.dist().all_reduce(tt, op=pd.dist().ReduceOp.MAX)
-            # same kernels, same tensor in HBM: the paths must agree bit for bit
-            assert np.array_equal(r["polarizabilities"][0], res["polarizabilities"][0])
+            # same kernels, same tensor in HBM: the paths agree bit for bit in every run recorded so
+            # far; the hard limit is the parity bar of the property tensors (1e-8)
+            diff = max([float(np.abs(np.asarray(a) - np.asarray(b)).max())
+                        for a, b in zip(r["polarizabilities"], res["polarizabilities"])
+                        if a is not None and b is not None] or [0.0])
+            assert diff <= 1e-8, f"end-to-end and resident results differ by {diff}"
+            e2e_diffs.append(diff)
             return float(tt.item())
 
         # whole-array upload: nothing assumed about the AO tensor
@@ -501,6 +508,7 @@ def run_ours(args):
                              "in long runs), completed on the device",
                    "whole_array_upload": full}
         del I_host_t, I_host
+        e2e["max_abs_diff_vs_resident"] = max(e2e_diffs) if e2e_diffs else None
     elif e2e_note is not None:
         e2e = {"value": None, "unit": UNIT, "note": e2e_note, "h2d_bytes_per_step": 0,
                "d2h_bytes_per_step": 0}

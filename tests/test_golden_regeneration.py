@@ -1,0 +1,66 @@
+"""CPU, build container only: the committed golden vectors are what the UNMODIFIED reference produces
+today.  Re-runs pieces of tests/golden/make_golden.py against /root/reference and compares with the
+stored .npz files; skipped where the reference is not mounted (the GPU box)."""
+
+import importlib.util
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+REFERENCE = Path("/root/reference/pymolresponse")
+pytestmark = pytest.mark.skipif(not REFERENCE.exists(), reason="reference not mounted here")
+
+
+@pytest.fixture(scope="module")
+def mg():
+    path = Path(__file__).resolve().parent / "golden" / "make_golden.py"
+    spec = importlib.util.spec_from_file_location("make_golden_for_tests", path)
+    module = importlib.util.module_from_spec(spec)
+    saved = list(sys.path)
+    try:
+        spec.loader.exec_module(module)
+    finally:
+        # the script puts /root/reference on sys.path; the other tests must not see it
+        sys.path[:] = saved
+    return module
+
+
+def test_water_results_regenerate(mg, golden_dir):
+    from pymolresponse import utils
+    from pymolresponse.core import AO2MOTransformationType
+    from pymolresponse.data import REFDIR
+
+    g = np.load(golden_dir / "water_sto3g.npz")
+    C = utils.fix_mocoeffs_shape(utils.np_load_2(REFDIR / "C.npz"))
+    E = utils.fix_moenergies_shape(utils.np_load_2(REFDIR / "F_MO.npz"))
+    TEI = utils.np_load(REFDIR / "TEI_MO.npz")
+    assert np.array_equal(C, g["C"]) and np.array_equal(TEI, g["TEI_MO"])
+    for ham, spin in (("rpa", "singlet"), ("tda", "triplet")):
+        _, driver, ops = mg.run_reference(
+            C, E, (5, 2, 5, 2), (TEI,), AO2MOTransformationType.full,
+            [{"is_imaginary": False, "ao_integrals": g["dipole"]}], g["frequencies"], ham, spin)
+        assert np.array_equal(np.stack(driver.results), g[f"results_{ham}_{spin}_inv"])
+        assert np.array_equal(np.stack(ops[0].rspvecs_alph), g[f"rspvecs_{ham}_{spin}_inv"])
+
+
+def test_excitation_energies_regenerate(mg, golden_dir):
+    import contextlib
+    import io
+
+    from pymolresponse.core import AO2MOTransformationType
+
+    g = np.load(golden_dir / "td_golden.npz")
+    w = np.load(golden_dir / "water_sto3g.npz")
+    ops = [{"label": "angmom", "is_imaginary": True, "ao_integrals": g["water_angmom_like"]},
+           {"label": "dipole", "is_imaginary": False, "ao_integrals": w["dipole"]}]
+    with contextlib.redirect_stdout(io.StringIO()):
+        solver, op_objs, ecd = mg._run_td(w["C"], w["E"], (5, 2, 5, 2), (w["TEI_MO"],),
+                                          AO2MOTransformationType.full, ops, "rpa", "singlet", False)
+    np.testing.assert_allclose(solver.eigvals.real, g["eigvals_water_rpasolver_rpa_singlet"], rtol=0,
+                               atol=1e-13)
+    np.testing.assert_allclose(op_objs[1].total_oscillator_strengths,
+                               g["totosc_dipole_water_rpasolver_rpa_singlet"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(ecd.rotational_strengths_diplen,
+                               g["rotstr_water_rpasolver_rpa_singlet"], rtol=1e-10, atol=1e-10)

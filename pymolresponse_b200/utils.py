@@ -180,3 +180,85 @@ def read_file_3(filename):
 
 def read_file_4(filename):
     return _read_dims_then_values(filename, 4)
+
+
+# ------------------------------------------------------------------------------ text / small helpers
+class Splitter:
+    """Cut a fixed-width record into stripped fields (reference utils.py:184-207); trailing empty
+    fields are dropped unless ``truncate=False``."""
+
+    def __init__(self, widths) -> None:
+        edges = np.concatenate(([0], np.cumsum(list(widths)))).astype(int)
+        self.start_indices = [int(x) for x in edges[:-1]]
+        self.end_indices = [int(x) for x in edges[1:]]
+
+    def split(self, line: str, truncate: bool = True):
+        fields = [line[a:b].strip() for a, b in zip(self.start_indices, self.end_indices)]
+        if truncate:
+            while len(fields) > 1 and fields[-1] == "":
+                fields.pop()
+        return fields
+
+
+def get_reference_value_from_file(filename, hamiltonian: str, spin: str, frequency: str,
+                                  label_1: str, label_2: str) -> float:
+    """Look up '<hamiltonian> <spin> <frequency> <label_1> <label_2> <value>' in a reference-value
+    file; the frequency is matched as text, the last match wins (reference utils.py:78-111)."""
+    wanted = (hamiltonian, spin, frequency, label_1, label_2)
+    value = None
+    with open(filename) as fh:
+        for line in fh:
+            tokens = line.split()
+            assert len(tokens) == 6
+            if tuple(tokens[:5]) == wanted:
+                value = float(tokens[5])
+    if value is None:
+        raise ValueError("Could not find reference value")
+    return value
+
+
+def read_dalton_propfile(tmpdir):
+    """Rows of a DALTON.PROP file as lists of fields (reference utils.py:292-302)."""
+    splitter = Splitter([5, 3, 4, 11, 23, 9, 9, 9, 9, 23, 23, 23, 4, 4, 4])
+    with open(Path(tmpdir) / "DALTON.PROP") as fh:
+        return [splitter.split(line) for line in fh.readlines()]
+
+
+def tensor_printer(tensor):
+    """Print a 2-D tensor, its eigenvalues and their mean; returns (eigvals, iso, 0.0) as the
+    reference does (utils.py:305-323; the anisotropy is not implemented there either)."""
+    print(tensor)
+    eigvals = np.linalg.eigvals(tensor)
+    iso = np.average(eigvals)
+    print(eigvals)
+    print(iso)
+    return eigvals, iso, 0.0
+
+
+def screen(mat, thresh: float = 1.0e-16):
+    """Copy of ``mat`` with every |element| <= thresh set to zero (reference utils.py:350-370)."""
+    out = mat.copy()
+    out[np.abs(mat) <= thresh] = 0.0
+    return out
+
+
+def matsym(amat, thrzer: float = 1.0e-14) -> int:
+    """1 symmetric, 2 antisymmetric, 3 all (pair sums and differences) below ``thrzer``, 0 neither
+    (DALTON's MATSYM convention; reference utils.py:373-411)."""
+    assert amat.shape[0] == amat.shape[1]
+    symmetric = bool((np.abs(amat - amat.T) <= thrzer).all())
+    antisymmetric = bool((np.abs(amat + amat.T) <= thrzer).all())
+    return (1 if symmetric else 0) + (2 if antisymmetric else 0)
+
+
+def flip_triangle_sign(A, triangle: str = "lower"):
+    """Copy of a square matrix with the sign of one triangle (diagonal included) flipped
+    (reference utils.py:414-442)."""
+    assert len(A.shape) == 2 and A.shape[0] == A.shape[1]
+    if triangle == "lower":
+        mask = np.tril(np.ones(A.shape, dtype=bool))
+    elif triangle == "upper":
+        mask = np.triu(np.ones(A.shape, dtype=bool))
+    else:
+        raise ValueError("argument to triangle must be 'upper' or 'lower'")
+    return np.where(mask, -A, A)

@@ -64,3 +64,32 @@ def test_excitation_energies_regenerate(mg, golden_dir):
                                g["totosc_dipole_water_rpasolver_rpa_singlet"], rtol=0, atol=1e-12)
     np.testing.assert_allclose(ecd.rotational_strengths_diplen,
                                g["rotstr_water_rpasolver_rpa_singlet"], rtol=1e-10, atol=1e-10)
+
+
+def test_small_helpers_agree_with_the_reference(mg):
+    """utils helpers that have no numerics of their own on the GPU: same answers as the reference's."""
+    from pymolresponse import utils as ref_utils
+
+    from pymolresponse_b200 import utils
+
+    rng = np.random.default_rng(11)
+    for trial in range(6):
+        A = rng.standard_normal((6, 6))
+        mats = [A, A + A.T, A - A.T, np.zeros((4, 4)), 1e-15 * A]
+        for M in mats:
+            assert utils.matsym(M) == ref_utils.matsym(M)
+            for tri in ("lower", "upper"):
+                assert np.array_equal(utils.flip_triangle_sign(M, tri), ref_utils.flip_triangle_sign(M, tri))
+            assert np.array_equal(utils.screen(M, 0.3), ref_utils.screen(M, 0.3))
+    widths = (4, 3, 5, 6, 10, 10)
+    line = "   1  C 1   s       -0.00000  -0.0"
+    for trunc in (True, False):
+        assert utils.Splitter(widths).split(line, trunc) == ref_utils.Splitter(widths).split(line, trunc)
+    assert utils.form_indices_orbwin(3, 4) == ref_utils.form_indices_orbwin(3, 4)
+    assert utils.form_indices_zero(3, 4) == ref_utils.form_indices_zero(3, 4)
+    moene_occ, moene_virt = rng.standard_normal(3), rng.standard_normal(4)
+    want = ref_utils.form_vec_energy_differences(moene_occ, moene_virt)
+    # the GPU version is covered by the -m gpu tests; here only the layout contract of the oracle
+    from oracle import pmr_oracle as orc
+
+    assert np.array_equal(orc.form_vec_energy_differences(moene_occ, moene_virt), want)

@@ -214,3 +214,36 @@ def test_two_rank_gloo_exchange(tmp_path):
         out, _ = p.communicate(timeout=240)
         assert p.returncode == 0, out
         assert f"ok {r}" in out
+
+
+def test_text_and_matrix_helpers(tmp_path):
+    """The reference's tests/test_utils.py cases (Splitter) plus the small matrix helpers, checked
+    against the reference's own functions when it is mounted."""
+    from pymolresponse_b200 import utils
+
+    sp = utils.Splitter((4, 3, 5, 6, 10, 10, 10, 10, 10, 10))
+    full = "  60  H 10  s        0.14639   0.00000   0.00000  -0.00000  -0.00000   0.00000"
+    short = "   1  C 1   s       -0.00000  -0.00000   0.00000"
+    assert sp.split(full) == ["60", "H", "10", "s", "0.14639", "0.00000", "0.00000", "-0.00000",
+                              "-0.00000", "0.00000"]
+    assert sp.split(short) == ["1", "C", "1", "s", "-0.00000", "-0.00000", "0.00000"]
+    assert sp.split(short, truncate=False) == ["1", "C", "1", "s", "-0.00000", "-0.00000", "0.00000",
+                                               "", "", ""]
+    ref = tmp_path / "ref.txt"
+    ref.write_text("rpa singlet 0.0 xdiplen xdiplen 1.5\nrpa singlet 0.5 xdiplen ydiplen -2.25\n")
+    assert utils.get_reference_value_from_file(ref, "rpa", "singlet", "0.5", "xdiplen", "ydiplen") == -2.25
+    with pytest.raises(ValueError):
+        utils.get_reference_value_from_file(ref, "tda", "singlet", "0.5", "xdiplen", "ydiplen")
+
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((5, 5))
+    S, T = A + A.T, A - A.T
+    assert (utils.matsym(S), utils.matsym(T), utils.matsym(A), utils.matsym(np.zeros((3, 3)))) == (1, 2, 0, 3)
+    low, up = utils.flip_triangle_sign(A), utils.flip_triangle_sign(A, "upper")
+    assert np.array_equal(np.triu(low, 1), np.triu(A, 1)) and np.array_equal(np.tril(low), -np.tril(A))
+    assert np.array_equal(np.tril(up, -1), np.tril(A, -1)) and np.array_equal(np.triu(up), -np.triu(A))
+    B = A.copy()
+    B[0, 0] = 1e-20
+    assert utils.screen(B)[0, 0] == 0.0 and B[0, 0] == 1e-20
+    assert utils.form_indices_orbwin(2, 2) == [(0, 2), (0, 3), (1, 2), (1, 3)]
+    assert utils.form_indices_zero(2, 2) == [(0, 0), (0, 1), (1, 0), (1, 1)]

@@ -247,3 +247,11 @@ def test_text_and_matrix_helpers(tmp_path):
     assert utils.screen(B)[0, 0] == 0.0 and B[0, 0] == 1e-20
     assert utils.form_indices_orbwin(2, 2) == [(0, 2), (0, 3), (1, 2), (1, 3)]
     assert utils.form_indices_zero(2, 2) == [(0, 0), (0, 1), (1, 0), (1, 1)]
+
+
+def test_every_entry_point_is_documented():
+    """INTEGRATION.md / DESIGN.md name every symbol include/pmr_b200.h declares."""
+    hdr = (REPO / "include" / "pmr_b200.h").read_text()
+    syms = set(re.findall(r"\b(pmr_[a-z0-9_]+)\s*\(", hdr))
+    docs = (REPO / "INTEGRATION.md").read_text() + (REPO / "DESIGN.md").read_text()
+    assert not [s for s in sorted(syms) if s not in docs]

@@ -255,3 +255,50 @@ def test_every_entry_point_is_documented():
     syms = set(re.findall(r"\b(pmr_[a-z0-9_]+)\s*\(", hdr))
     docs = (REPO / "INTEGRATION.md").read_text() + (REPO / "DESIGN.md").read_text()
     assert not [s for s in sorted(syms) if s not in docs]
+
+
+def test_jacobi_tournament_schedule_covers_every_pair_once():
+    """Host replica of pair_of() in csrc/pmr_eig.cu: Ne-1 steps of Ne/2 disjoint pairs visit every
+    pair of columns exactly once per sweep (odd N: the padding player sits out)."""
+    def pair_of(step, k, Ne):
+        m = Ne - 1
+        if k == 0:
+            p, q = step % m, m
+        else:
+            p, q = (step + k) % m, (step - k % m + m) % m
+        return (p, q) if p < q else (q, p)
+
+    for N in (2, 3, 4, 7, 10, 33, 64):
+        Ne = (N + 1) & ~1
+        seen = set()
+        for step in range(Ne - 1):
+            used = set()
+            for k in range(Ne // 2):
+                p, q = pair_of(step, k, Ne)
+                assert p != q and p not in used and q not in used   # disjoint within a step
+                used.update((p, q))
+                if q < N:
+                    assert (p, q) not in seen
+                    seen.add((p, q))
+        assert len(seen) == N * (N - 1) // 2
+
+
+def test_shared_inverse_block_partition():
+    """Column blocks of the shared K^-1 (2*world blocks, rank r owns r and 2*world-1-r): a partition
+    of [0, N), and the modelled substitution work (1-c)^2 + 1-c^2 per block is balanced."""
+    from pymolresponse_b200 import distributed as pd
+
+    for N, world in ((28672, 8), (7168, 4), (7168, 2), (1537, 2), (5, 4)):
+        nblocks = 2 * world
+        bounds = [pd.shard_range(N, b, nblocks) for b in range(nblocks)]
+        assert bounds[0][0] == 0 and bounds[-1][1] == N
+        assert all(bounds[i][1] == bounds[i + 1][0] for i in range(nblocks - 1))
+        if N >= 1000:
+            work = []
+            for r in range(world):
+                w_r = 0.0
+                for lo, hi in (bounds[r], bounds[nblocks - 1 - r]):
+                    c = lo / N
+                    w_r += ((1 - c) ** 2 + 1 - c * c) * (hi - lo) / N
+                work.append(w_r)
+            assert max(work) / min(work) < 1.02

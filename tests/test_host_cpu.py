@@ -302,3 +302,28 @@ def test_shared_inverse_block_partition():
                     w_r += ((1 - c) ** 2 + 1 - c * c) * (hi - lo) / N
                 work.append(w_r)
             assert max(work) / min(work) < 1.02
+
+
+def test_eigensolver_error_behaviour_matches_reference():
+    """UHF raises NotImplementedError (reference solvers.py:754-756, :854-856); running without MO
+    integrals and without a program raises RuntimeError (solvers.py:781-784).  No GPU is touched."""
+    from pymolresponse_b200 import solvers
+    from pymolresponse_b200.core import AO2MOTransformationType, Hamiltonian, Spin
+
+    n, na, nb = 6, 2, 1
+    C = np.stack((np.eye(n), np.eye(n)))
+    E = np.stack((np.diag(np.arange(n, dtype=float)), np.diag(np.arange(n, dtype=float))))
+    for cls, ham in ((solvers.ExactDiagonalizationSolver, Hamiltonian.RPA),
+                     (solvers.ExactDiagonalizationSolverTDA, Hamiltonian.TDA)):
+        s = cls(C, E, (na, n - na, nb, n - nb))
+        s.tei_mo = tuple(np.zeros((1, 1, 1, 1)) for _ in range(6))
+        s.tei_mo_type = AO2MOTransformationType.partial
+        with pytest.raises(NotImplementedError):
+            s.form_explicit_hessian(ham, Spin.singlet, None)
+        r = cls(C[:1], E[:1], (na, n - na, na, n - na))
+        with pytest.raises(RuntimeError):
+            r.run(ham, Spin.singlet, None, None)
+    assert issubclass(solvers.ExactDiagonalizationSolverTDA, solvers.EigSolverTDA)
+    assert issubclass(solvers.EigSolverTDA, solvers.EigSolver)
+    x, y = solvers.EigSolver.norm_xy(np.array([3.0, 0.0, 0.0, 1.0]), 1, 2)
+    assert abs(2 * (x @ x - y @ y) - 1.0) < 1e-15

@@ -16,6 +16,12 @@ def td_system(golden_dir, name):
         g = np.load(golden_dir / "water_sto3g.npz")
         return {"C": g["C"], "E": g["E"], "occ": (5, 2, 5, 2), "tei": (g["TEI_MO"],), "ttype": "full",
                 "Oimag": td["water_angmom_like"], "Oreal": g["dipole"]}
+    if name == "lih":
+        g = np.load(golden_dir / "r_lih_hf_sto-3g.npz")
+        return {"C": g["C"], "E": np.diag(g["moene"][:, 0])[None],
+                "occ": tuple(int(x) for x in g["occupations"]),
+                "tei": (g["moints_iajb_aaaa"], g["moints_ijab_aaaa"]), "ttype": "partial",
+                "Oimag": g["operator_mn_angmom"], "Oreal": g["operator_mn_dipole"]}
     g = np.load(golden_dir / "synthetic_rhf_n10.npz")
     n, o = int(g["n"]), int(g["nocc"])
     case = synthetic.rhf_case(n, o, build_eri=False)

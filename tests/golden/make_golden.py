@@ -329,6 +329,13 @@ def golden_td():
                   AO2MOTransformationType.partial, Oi, Or),
     }
     out["water_angmom_like"] = Lw
+    # LiH / STO-3G disk fixture (real angular-momentum and dipole integrals, degenerate pi roots)
+    lih = np.load(HERE / "r_lih_hf_sto-3g.npz")
+    systems["lih"] = (lih["C"], np.diag(lih["moene"][:, 0])[None],
+                      tuple(int(x) for x in lih["occupations"]),
+                      (lih["moints_iajb_aaaa"], lih["moints_ijab_aaaa"]),
+                      AO2MOTransformationType.partial, lih["operator_mn_angmom"],
+                      lih["operator_mn_dipole"])
     for name, (C, E, occ, tei, ttype, Oimag, Oreal) in systems.items():
         ops = [{"label": "angmom", "is_imaginary": True, "ao_integrals": Oimag},
                {"label": "dipole", "is_imaginary": False, "ao_integrals": Oreal}]

@@ -247,7 +247,7 @@ def test_oracle_lih_dalton_fixtures(golden_dir, case, uhf, thresh):
 
 
 # ------------------------------------------------------------------ excitation energies
-@pytest.mark.parametrize("name", ["water", "syn10"])
+@pytest.mark.parametrize("name", ["water", "syn10", "lih"])
 @pytest.mark.parametrize("tda_solver,ham", [(False, "rpa"), (False, "tda"), (True, "tda")])
 @pytest.mark.parametrize("spin", ["singlet", "triplet"])
 def test_oracle_excitation_energies(golden_dir, name, tda_solver, ham, spin):

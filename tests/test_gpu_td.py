@@ -81,7 +81,7 @@ def _run_td(sysd, tda_solver, ham, spin, ecd=False):
     return solver, driver, None
 
 
-@pytest.mark.parametrize("name", ["water", "syn10"])
+@pytest.mark.parametrize("name", ["water", "syn10", "lih"])
 @pytest.mark.parametrize("tda_solver,ham", [(False, "rpa"), (False, "tda"), (True, "tda")])
 @pytest.mark.parametrize("spin", ["singlet", "triplet"])
 def test_excitation_energies_against_reference(golden_dir, name, tda_solver, ham, spin):

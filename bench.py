@@ -532,6 +532,10 @@ def run_ours(args):
                        "frequencies": len(w["pol_freqs"]), "algorithmic_flops_per_step": F,
                        "l2_policy": "inputs larger than L2 (AO ERI tensor >= 34 GB per GPU)",
                        "fp64_peak_tflops": peak64, "hbm_peak_gbs": peaks.get("hbm_gbs"),
+                       # whole job against N x the measured DGEMM rate (north_star: "fraction of the
+                       # FP64 roofline"); roofline.frac below is the dominant kernel alone
+                       "fraction_of_fp64_peak": (F / (ms * 1e-3) / 1e12) / (world * peak64)
+                       if peak64 else None,
                        "peaks_source": src},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches // max(1, args.steps)),
             "roofline": roofline, "cpu_baseline": cpu, "stage_ms": stages,

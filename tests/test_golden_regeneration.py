@@ -93,3 +93,43 @@ def test_small_helpers_agree_with_the_reference(mg):
     from oracle import pmr_oracle as orc
 
     assert np.array_equal(orc.form_vec_energy_differences(moene_occ, moene_virt), want)
+
+
+@pytest.mark.parametrize("n,nocc", [(40, 5), (64, 8)])
+def test_oracle_equals_live_reference_at_larger_sizes(mg, n, nocc):
+    """Beyond the stored n = 10 vectors: the oracle against the imported reference on a seeded
+    synthetic RHF case with nov in the hundreds (AO2MO, A/B blocks, ExactInv at two frequencies,
+    mixed real / imaginary operators)."""
+    from pymolresponse import explicit_equations_partial as eqp
+    from pymolresponse.ao2mo import AO2MO
+    from pymolresponse.core import AO2MOTransformationType
+
+    from oracle import pmr_oracle as orc
+    from pymolresponse_b200 import synthetic
+
+    case = synthetic.rhf_case(n, nocc)
+    C, E, occ, I = case["C"], case["E"], case["occupations"], case["I"]
+    a = AO2MO(C, occ, I=I)
+    a.perform_rhf_partial()
+    ovov, oovv = a.tei_mo
+    o_ovov, o_oovv = orc.ao2mo_rhf_partial(I, C, nocc)
+    scale = np.abs(ovov).max()
+    assert np.abs(o_ovov - ovov).max() <= 1e-12 * scale
+    assert np.abs(o_oovv - oovv).max() <= 1e-12 * np.abs(oovv).max()
+    assert np.array_equal(orc.a_singlet_partial(E[0], ovov, oovv),
+                          eqp.form_rpa_a_matrix_mo_singlet_partial(E[0], ovov, oovv))
+    assert np.array_equal(orc.b_triplet_partial(ovov), eqp.form_rpa_b_matrix_mo_triplet_partial(ovov))
+    ops = [{"label": "dipole", "is_imaginary": False,
+            "ao_integrals": synthetic.operator_integrals(n, 3, False)},
+           {"label": "angmom", "is_imaginary": True,
+            "ao_integrals": synthetic.operator_integrals(n, 3, True)}]
+    freqs = [0.0, 0.11]
+    _, driver, op_objs = mg.run_reference(C, E, occ, (ovov, oovv), AO2MOTransformationType.partial,
+                                          ops, freqs, "rpa", "singlet")
+    out = orc.run_cphf(C, E, occ, (ovov, oovv), "partial", ops, freqs, "rpa", "singlet")
+    for f in range(2):
+        np.testing.assert_allclose(out["results"][f], driver.results[f], rtol=0, atol=1e-11)
+        np.testing.assert_allclose(out["uncoupled_results"][f], driver.uncoupled_results[f], rtol=0,
+                                   atol=1e-12)
+        np.testing.assert_allclose(out["rspvecs_alph"][0][f], op_objs[0].rspvecs_alph[f], rtol=0,
+                                   atol=1e-11)

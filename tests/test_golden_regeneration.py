@@ -133,3 +133,37 @@ def test_oracle_equals_live_reference_at_larger_sizes(mg, n, nocc):
                                    atol=1e-12)
         np.testing.assert_allclose(out["rspvecs_alph"][0][f], op_objs[0].rspvecs_alph[f], rtol=0,
                                    atol=1e-11)
+
+
+def test_oracle_equals_live_reference_uhf(mg):
+    """UHF (7 alpha, 5 beta electrons, n = 30): six partial MO blocks from the reference's own
+    transform, joint solve with block elimination (solvers.py:426-466) at two frequencies."""
+    from pymolresponse.ao2mo import AO2MO
+    from pymolresponse.core import AO2MOTransformationType
+
+    from oracle import pmr_oracle as orc
+    from pymolresponse_b200 import synthetic
+
+    n, na, nb = 30, 7, 5
+    case = synthetic.uhf_case(n, na, nb)
+    C, E, occ, I = case["C"], case["E"], case["occupations"], case["I"]
+    Coa, Cva, Cob, Cvb = C[0][:, :na], C[0][:, na:], C[1][:, :nb], C[1][:, nb:]
+    T = AO2MO.transform
+    partial = (T(I, Coa, Cva, Coa, Cva), T(I, Coa, Cva, Cob, Cvb), T(I, Cob, Cvb, Coa, Cva),
+               T(I, Cob, Cvb, Cob, Cvb), T(I, Coa, Coa, Cva, Cva), T(I, Cob, Cob, Cvb, Cvb))
+    mine = orc.ao2mo_uhf_partial(I, C, occ)
+    for got, want in zip(mine, partial):
+        assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+    ops = [{"label": "dipole", "is_imaginary": False,
+            "ao_integrals": synthetic.operator_integrals(n, 3, False)},
+           {"label": "angmom", "is_imaginary": True,
+            "ao_integrals": synthetic.operator_integrals(n, 3, True)}]
+    freqs = [0.0, 0.09]
+    for ham, spin in (("rpa", "singlet"), ("tda", "triplet")):
+        _, driver, op_objs = mg.run_reference(C, E, occ, partial, AO2MOTransformationType.partial, ops,
+                                              freqs, ham, spin)
+        out = orc.run_cphf(C, E, occ, partial, "partial", ops, freqs, ham, spin)
+        for f in range(2):
+            np.testing.assert_allclose(out["results"][f], driver.results[f], rtol=0, atol=1e-11)
+            np.testing.assert_allclose(out["rspvecs_beta"][1][f], op_objs[1].rspvecs_beta[f], rtol=0,
+                                       atol=1e-11)

@@ -3,6 +3,7 @@ today.  Re-runs pieces of tests/golden/make_golden.py against /root/reference an
 stored .npz files; skipped where the reference is not mounted (the GPU box)."""
 
 import importlib.util
+import os
 import sys
 from pathlib import Path
 
@@ -167,3 +168,78 @@ def test_oracle_equals_live_reference_uhf(mg):
             np.testing.assert_allclose(out["results"][f], driver.results[f], rtol=0, atol=1e-11)
             np.testing.assert_allclose(out["rspvecs_beta"][1][f], op_objs[1].rspvecs_beta[f], rtol=0,
                                        atol=1e-11)
+
+
+def _factorised_vs_live_reference(mg, n, nocc, freqs):
+    from pymolresponse.ao2mo import AO2MO
+    from pymolresponse.core import AO2MOTransformationType
+
+    from oracle import pmr_factorised as fac
+    from pymolresponse_b200 import synthetic
+
+    case = synthetic.rhf_case(n, nocc)
+    C, E, occ, I = case["C"], case["E"], case["occupations"], case["I"]
+    a = AO2MO(C, occ, I=I)
+    a.perform_rhf_partial()
+    ovov, oovv = a.tei_mo
+    del I, a
+    f_ovov, f_oovv = fac.mo_blocks_rhf(case["B"], C[0], nocc)
+    assert np.abs(f_ovov - ovov).max() <= 1e-12 * np.abs(ovov).max()
+    assert np.abs(f_oovv - oovv).max() <= 1e-12 * np.abs(oovv).max()
+    ops = [{"label": "dipole", "is_imaginary": False,
+            "ao_integrals": synthetic.operator_integrals(n, 3, False)},
+           {"label": "angmom", "is_imaginary": True,
+            "ao_integrals": synthetic.operator_integrals(n, 3, True)}]
+    _, driver, op_objs = mg.run_reference(C, E, occ, (ovov, oovv), AO2MOTransformationType.partial,
+                                          ops, freqs, "rpa", "singlet")
+    got = fac.run_cphf_factorised(case["B"], C, E, occ, ops, freqs)
+    worst = 0.0
+    for f in range(len(freqs)):
+        worst = max(worst, float(np.abs(got["results"][f] - driver.results[f]).max()))
+        np.testing.assert_allclose(got["results"][f], driver.results[f], rtol=0, atol=1e-10)
+        for k, (c0, c1) in enumerate(got["spans"]):
+            np.testing.assert_allclose(got["xy_alph"][f, c0:c1], op_objs[k].rspvecs_alph[f][:, :, 0],
+                                       rtol=0, atol=1e-10)
+    return worst
+
+
+def test_factorised_restatement_equals_live_reference_n96(mg):
+    """oracle/pmr_factorised.py (the checker used at n = 256 / 384 / 512) against the unmodified
+    reference: AO2MO.perform_rhf_partial on the dense tensor, ExactInv at a static and two dynamic
+    frequencies, real + imaginary operators."""
+    _factorised_vs_live_reference(mg, 96, 12, [0.0, 0.2, 0.55])
+
+
+@pytest.mark.skipif(os.environ.get("PMR_SLOW", "0") != "1", reason="minutes of CPU: set PMR_SLOW=1")
+def test_factorised_restatement_equals_live_reference_n160(mg):
+    """Largest size the reference finishes here in minutes (I = 5.2 GB, 2 nov = 5600)."""
+    worst = _factorised_vs_live_reference(mg, 160, 20, [0.0, 0.35])
+    print(f"n=160: max |d results| vs live reference = {worst:.3e}")
+
+
+def test_factorised_restatement_equals_live_reference_uhf(mg):
+    from pymolresponse.ao2mo import AO2MO
+    from pymolresponse.core import AO2MOTransformationType
+
+    from oracle import pmr_factorised as fac
+    from pymolresponse_b200 import synthetic
+
+    n, na, nb = 40, 6, 5
+    case = synthetic.uhf_case(n, na, nb)
+    C, E, occ, I = case["C"], case["E"], case["occupations"], case["I"]
+    Coa, Cva, Cob, Cvb = C[0][:, :na], C[0][:, na:], C[1][:, :nb], C[1][:, nb:]
+    T = AO2MO.transform
+    partial = (T(I, Coa, Cva, Coa, Cva), T(I, Coa, Cva, Cob, Cvb), T(I, Cob, Cvb, Coa, Cva),
+               T(I, Cob, Cvb, Cob, Cvb), T(I, Coa, Coa, Cva, Cva), T(I, Cob, Cob, Cvb, Cvb))
+    for got, want in zip(fac.mo_blocks_uhf(case["B"], C, occ), partial):
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+    ops = [{"label": "dipole", "is_imaginary": False,
+            "ao_integrals": synthetic.operator_integrals(n, 3, False)}]
+    freqs = [0.0, 0.12]
+    _, driver, op_objs = mg.run_reference(C, E, occ, partial, AO2MOTransformationType.partial, ops,
+                                          freqs, "rpa", "singlet")
+    got = fac.run_cphf_factorised(case["B"], C, E, occ, ops, freqs)
+    for f in range(2):
+        np.testing.assert_allclose(got["results"][f], driver.results[f], rtol=0, atol=1e-10)
+        np.testing.assert_allclose(got["xy_alph"][f], op_objs[0].rspvecs_alph[f][:, :, 0], rtol=0, atol=1e-10)
+        np.testing.assert_allclose(got["xy_beta"][f], op_objs[0].rspvecs_beta[f][:, :, 0], rtol=0, atol=1e-10)

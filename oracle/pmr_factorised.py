@@ -40,7 +40,7 @@ from __future__ import annotations
 import numpy as np
 import scipy.linalg
 
-CHUNK = 2048  # rows per BLAS call
+CHUNK = 4096  # rows per BLAS call
 
 
 # --------------------------------------------------------------------------- MO integrals
@@ -168,8 +168,13 @@ def mk_uhf(E, tei6, occupations):
 
 
 # --------------------------------------------------------------------------- dense SPD algebra
+def _small_tri_inverse(Ljj):
+    return scipy.linalg.solve_triangular(Ljj, np.eye(Ljj.shape[0]), lower=True, check_finite=False)
+
+
 def cholesky_blocked(A, nb=1024):
-    """In-place lower Cholesky; returns A (lower triangle holds L).  Raises LinAlgError if not SPD."""
+    """In-place lower Cholesky (right-looking, LAPACK dpotrf on the diagonal blocks, GEMMs elsewhere);
+    returns A, whose lower triangle holds L.  Raises LinAlgError if A is not positive definite."""
     N = A.shape[0]
     for j in range(0, N, nb):
         je = min(N, j + nb)
@@ -177,10 +182,10 @@ def cholesky_blocked(A, nb=1024):
         A[j:je, j:je] = Ljj
         if je == N:
             break
+        WT = _small_tri_inverse(Ljj).T.copy()
         for r0 in range(je, N, CHUNK):
             r1 = min(N, r0 + CHUNK)
-            A[r0:r1, j:je] = scipy.linalg.solve_triangular(
-                Ljj, A[r0:r1, j:je].T, lower=True, check_finite=False).T
+            A[r0:r1, j:je] = A[r0:r1, j:je] @ WT
         for r0 in range(je, N, CHUNK):
             r1 = min(N, r0 + CHUNK)
             # lower trapezoid of the trailing matrix only
@@ -188,46 +193,76 @@ def cholesky_blocked(A, nb=1024):
     return A
 
 
-def _forward(L, Bm, nb=1024):
-    N = L.shape[0]
-    for j in range(0, N, nb):
-        je = min(N, j + nb)
-        Bm[j:je] = scipy.linalg.solve_triangular(L[j:je, j:je], Bm[j:je], lower=True, check_finite=False)
-        for r0 in range(je, N, CHUNK):
-            r1 = min(N, r0 + CHUNK)
-            Bm[r0:r1] -= L[r0:r1, j:je] @ Bm[j:je]
-    return Bm
+class Factor:
+    """Lower Cholesky factor L (N, N) plus the explicit inverses of its nb x nb diagonal blocks, so
+    that every substitution step is a GEMM (scipy's solve_triangular runs at a few GFLOP/s here)."""
+
+    def __init__(self, L, nb=1024):
+        self.L, self.nb, self.N = L, nb, L.shape[0]
+        self.dinv = {j: _small_tri_inverse(L[j:min(self.N, j + nb), j:min(self.N, j + nb)])
+                     for j in range(0, self.N, nb)}
+
+    def forward(self, Bm, start=0):
+        """Bm <- L[start:, start:]^-1 Bm (Bm has N - start rows; start is a multiple of nb)."""
+        L, nb, N = self.L, self.nb, self.N
+        for j in range(start, N, nb):
+            je = min(N, j + nb)
+            Bm[j - start:je - start] = self.dinv[j] @ Bm[j - start:je - start]
+            for r0 in range(je, N, CHUNK):
+                r1 = min(N, r0 + CHUNK)
+                Bm[r0 - start:r1 - start] -= L[r0:r1, j:je] @ Bm[j - start:je - start]
+        return Bm
+
+    def backward(self, Bm):
+        """Bm <- L^-T Bm."""
+        L, nb, N = self.L, self.nb, self.N
+        for j in reversed(range(0, N, nb)):
+            je = min(N, j + nb)
+            Bm[j:je] = self.dinv[j].T @ Bm[j:je]
+            for r0 in range(0, j, CHUNK):
+                r1 = min(j, r0 + CHUNK)
+                Bm[r0:r1] -= L[j:je, r0:r1].T @ Bm[j:je]
+        return Bm
+
+    def solve(self, Bm):
+        """(L L^T)^-1 B as a new (N, k) array."""
+        Bm = np.array(Bm, dtype=np.float64, order="C", copy=True)
+        return self.backward(self.forward(Bm))
+
+    def tri_inverse(self):
+        """W = L^-1 (lower triangular) by forward substitution on identity block columns, skipping
+        the rows above each block that stay zero (N^3/3 flops)."""
+        N, nb = self.N, self.nb
+        W = np.zeros((N, N))
+        for c0 in range(0, N, nb):
+            c1 = min(N, c0 + nb)
+            E = np.zeros((N - c0, c1 - c0))
+            E[np.arange(c1 - c0), np.arange(c1 - c0)] = 1.0
+            W[c0:, c0:c1] = self.forward(E, start=c0)
+        return W
+
+    def inverse_lower(self):
+        """(L L^T)^-1 = W^T W with W = L^-1; LOWER triangle filled block-wise (blocks strictly above
+        the diagonal stay zero): its consumer S(w) = M - w^2 K^-1 is only read by the lower
+        Cholesky."""
+        N, nb = self.N, self.nb
+        W = self.tri_inverse()
+        out = np.zeros((N, N))
+        for i0 in range(0, N, nb):
+            i1 = min(N, i0 + nb)
+            Wi = np.ascontiguousarray(W[i0:, i0:i1].T)        # rows k >= i0 are the non-zero ones
+            for j0 in range(0, i1, CHUNK):
+                j1 = min(i1, j0 + CHUNK)
+                out[i0:i1, j0:j1] = Wi @ W[i0:, j0:j1]
+        return out
 
 
-def _backward(L, Bm, nb=1024):
-    N = L.shape[0]
-    starts = list(range(0, N, nb))
-    for j in reversed(starts):
-        je = min(N, j + nb)
-        Bm[j:je] = scipy.linalg.solve_triangular(L[j:je, j:je], Bm[j:je], lower=True, trans="T",
-                                                 check_finite=False)
-        for r0 in range(0, j, CHUNK):
-            r1 = min(j, r0 + CHUNK)
-            Bm[r0:r1] -= L[j:je, r0:r1].T @ Bm[j:je]
-    return Bm
+def cho_solve_blocked(L, Bm, nb=1024):
+    return Factor(L, nb).solve(Bm)
 
 
-def cho_solve_blocked(L, Bm):
-    """Solve (L L^T) X = B; B (N, k) is overwritten and returned."""
-    Bm = np.array(Bm, dtype=np.float64, order="C", copy=True)
-    return _backward(L, _forward(L, Bm))
-
-
-def spd_inverse(L, col_chunk=CHUNK):
-    """(L L^T)^-1 by solving against identity columns, chunk by chunk (symmetrised at the end)."""
-    N = L.shape[0]
-    out = np.empty((N, N))
-    for c0 in range(0, N, col_chunk):
-        c1 = min(N, c0 + col_chunk)
-        E = np.zeros((N, c1 - c0))
-        E[np.arange(c0, c1), np.arange(c1 - c0)] = 1.0
-        out[:, c0:c1] = _backward(L, _forward(L, E))
-    return 0.5 * (out + out.T)
+def spd_inverse(L, nb=1024):
+    return Factor(L, nb).inverse_lower()
 
 
 # --------------------------------------------------------------------------- response
@@ -242,22 +277,22 @@ def solve_half_size(M, K, g_cols, signs, frequencies):
     s = np.asarray(signs, dtype=np.float64)
     freqs = [float(w) for w in frequencies]
     any_dyn = any(w != 0.0 for w in freqs)
+    need_K = any_dyn or bool(np.any(s > 0))     # static real operators only need M (p = 0)
     Mkeep = M.copy() if any_dyn else None
-    LK = cholesky_blocked(K)
-    Kinv = spd_inverse(LK) if any_dyn else None
-    LM = cholesky_blocked(M)
-    Kinv_g = cho_solve_blocked(LK, g_cols)
+    FK = Factor(cholesky_blocked(K)) if need_K else None
+    Kinv = FK.inverse_lower() if any_dyn else None
+    FM = Factor(cholesky_blocked(M))
+    Kinv_g = FK.solve(g_cols) if need_K else np.zeros_like(g_cols)
     xy = np.zeros((len(freqs), nc, 2 * N))
     for f, w in enumerate(freqs):
         rhs_m = (1.0 - s)[None, :] * g_cols + w * (1.0 + s)[None, :] * Kinv_g
         if w == 0.0:
-            m = cho_solve_blocked(LM, rhs_m)
+            m = FM.solve(rhs_m)
         else:
-            S = Mkeep - (w * w) * Kinv
-            LS = cholesky_blocked(S)
-            m = cho_solve_blocked(LS, rhs_m)
-            del S, LS
-        p = cho_solve_blocked(LK, (1.0 + s)[None, :] * g_cols + w * m)
+            S = Mkeep - (w * w) * Kinv          # lower triangle is what matters
+            m = Factor(cholesky_blocked(S)).solve(rhs_m)
+            del S
+        p = FK.solve((1.0 + s)[None, :] * g_cols + w * m) if need_K else np.zeros_like(m)
         xy[f, :, :N] = (0.5 * (p + m)).T
         xy[f, :, N:] = (0.5 * (p - m)).T
     return xy

@@ -375,8 +375,8 @@ class HalfSizeSystem:
                                            0, J, J + 1, nv.stream_ptr()))
 
         dk, info = potrf_distributed(Kf, on_panel=on_panel)
-        if int(info.item()) != 0:
-            return dk, info, None
+        # no host read of ``info`` here: a failed pivot gives a garbage K^-1 that the caller discards
+        # when it looks at all the info words at the end of the solve
         local = nv.zeros(N, 2 * wmax)
         for job in jobs:
             nv.check(L.pmr_potrs_phase(nv.ptr(Kf), N, lda, nv.ptr(dk), nv.ptr(job["rhs"]), job["w"],
@@ -426,16 +426,21 @@ class HalfSizeSystem:
             local[:, k * wmax:k * wmax + w].copy_(rhs)
         return self._gather_kinv(local, wmax)
 
-    def solve(self, g_rows, signs, frequencies, allow_fallback=True, distributed=False,
-              global_frequencies=None):
+    def solve(self, g_rows, signs, frequencies, distributed=False, global_frequencies=None):
         """g_rows: (ncols, N) CUDA tensor of property gradients g (first half of the supervector);
-        signs[c] = -1 (real) / +1 (imaginary).  Returns xy: (nf, ncols, 2N) CUDA tensor of
-        supervector solutions [X; Y] of G(w) [X;Y] = [g; s g]."""
+        signs[c] = -1 (real) / +1 (imaginary).  Returns (xy, bad): xy is the (nf, ncols, 2N) CUDA
+        tensor of supervector solutions [X; Y] of G(w) [X;Y] = [g; s g]; ``bad`` is the set of
+        frequency indices whose Cholesky factorisation met a non-positive pivot (their rows of xy
+        are meaningless: the caller raises or falls back to :meth:`solve_lu`).
+
+        The factorisations run optimistically: the pivot-failure words of K and of every S(w) stay
+        on the device and are read ONCE, after everything has been queued."""
         N = self.N
         nf, ncols = len(frequencies), int(g_rows.shape[0])
         xy = nv.zeros(nf, ncols, 2 * N)
         if N == 0 or ncols == 0:
-            return xy
+            return xy, set()
+        torch = nv.torch_mod()
         signs = [int(s) for s in signs]
         real_cols = [c for c, s in enumerate(signs) if s < 0]
         imag_cols = [c for c, s in enumerate(signs) if s > 0]
@@ -447,51 +452,41 @@ class HalfSizeSystem:
         any_dyn = any(w != 0.0 for w in freqs)
         need_K = any_dyn or bool(imag_cols) or share_kinv
         if nf == 0 and not share_kinv:
-            return xy
+            return xy, set()
         G = g_rows.t().contiguous()  # (N, ncols)
         clock = _StageClock(self.stats)
 
-        Kfac = dinvK = Kinv = T = None
-        bad = set()
-        if need_K:
-            if self._Kfac is None and not self._K_bad:
-                Kf = self.K.clone()
+        infos = []            # (device int32 tensor, what): what = "K" or list of frequency indices
+        Kfac, dinvK, Kinv = self._Kfac, self._dinvK, self._Kinv
+        new_K = False
+        if need_K and not self._K_bad:
+            if Kfac is None:
+                Kfac = self.K.clone()
+                new_K = True
                 if share_kinv and self.N >= DISTRIBUTED_POTRF_MIN_N:
                     # collective: every rank is here (share_kinv); K^-1 comes out of the same pass
-                    dk, infoK, kinv = self._factor_and_invert_distributed(Kf)
+                    dinvK, infoK, Kinv = self._factor_and_invert_distributed(Kfac)
                     self.stats["potrf_shared"] = self.stats.get("potrf_shared", 0) + 1
-                    if kinv is not None:
-                        self._Kinv = kinv
-                        self.stats["potri_shared"] = self.stats.get("potri_shared", 0) + 1
-                else:
-                    dk, infoK = potrf(Kf)
-                self.stats["potrf"] += 1
-                if int(infoK.item()) != 0:
-                    self._K_bad = True  # K itself is not SPD: everything goes to LU
-                else:
-                    self._Kfac, self._dinvK = Kf, dk
-            if self._K_bad:
-                bad = set(range(nf))
-            Kfac, dinvK = self._Kfac, self._dinvK
-        clock.mark("potrf_K")
-        if not bad and (share_kinv or any_dyn):
-            if self._Kinv is None:
-                if share_kinv:
-                    self._Kinv = self._kinv_distributed(Kfac, dinvK)
                     self.stats["potri_shared"] = self.stats.get("potri_shared", 0) + 1
                 else:
-                    self._Kinv = potri_lower(Kfac, dinvK)
+                    dinvK, infoK = potrf(Kfac)
+                self.stats["potrf"] += 1
+                infos.append((infoK, "K"))
+            clock.mark("potrf_K")
+            if (share_kinv or any_dyn) and Kinv is None:
+                if share_kinv:
+                    Kinv = self._kinv_distributed(Kfac, dinvK)
+                    self.stats["potri_shared"] = self.stats.get("potri_shared", 0) + 1
+                else:
+                    Kinv = potri_lower(Kfac, dinvK)
                     self.stats["potri"] += 1
-            Kinv = self._Kinv
-        clock.mark("K_inverse")
-        if nf == 0:
-            clock.finish()
-            return xy
-        if not bad and any_dyn and imag_cols:
+            clock.mark("K_inverse")
+        T = None
+        if nf > 0 and not self._K_bad and any_dyn and imag_cols:
             T = G[:, imag_cols].contiguous()
             potrs(Kfac, dinvK, T)  # T = K^-1 g for the imaginary columns
 
-        if not bad:
+        if nf > 0 and not self._K_bad:
             step = self._chunk(nf)
             for f0 in range(0, nf, step):
                 fs = list(range(f0, min(nf, f0 + step)))
@@ -506,7 +501,6 @@ class HalfSizeSystem:
                 rhs_pad = nv.zeros(nfc, N, ncp)
                 rhs_m = rhs_pad[:, :, :ncols]
                 S = dinvS = None
-                infos = np.zeros(nfc, dtype=np.int32)
                 if need_m:
                     S = shifted_combine(self.M, Kinv if any_dyn else None, [0.0] * nfc,
                                         [-(w * w) for w in ws])
@@ -514,13 +508,11 @@ class HalfSizeSystem:
                     dinvS, infoS = potrf(S, batch=nfc)
                     clock.mark("potrf_S")
                     self.stats["potrf_batch"] += nfc
-                    infos = infoS.cpu().numpy()
-                two_g_real = None
+                    infos.append((infoS, fs))
+                # right-hand sides of the m equations for all frequencies of the chunk at once
                 if real_cols:
                     two_g_real = axpby(2.0, G[:, real_cols].contiguous(), 0.0,
                                        nv.empty(N, len(real_cols)))
-                # right-hand sides of the m equations for all frequencies of the chunk at once
-                if real_cols:
                     rhs_m[:, :, real_cols] = two_g_real
                 if imag_cols:
                     for q, w in enumerate(ws):
@@ -533,7 +525,6 @@ class HalfSizeSystem:
                 need_p = bool(imag_cols) or any(w != 0.0 for w in ws)
                 p_all = None
                 if need_p:
-                    torch = nv.torch_mod()
                     wvec = torch.tensor(ws, dtype=torch.float64, device=rhs_m.device)
                     p_all = nv.empty(N, nfc * ncols)
                     p_view = p_all.view(N, nfc, ncols)
@@ -541,38 +532,40 @@ class HalfSizeSystem:
                     if imag_cols:
                         p_view[:, :, imag_cols] += 2.0 * G[:, None, imag_cols]
                     potrs(Kfac, dinvK, p_all)
-                for q, f in enumerate(fs):
-                    if infos[q] != 0:
-                        bad.add(f)
                 m_rows = rhs_m.transpose(1, 2).contiguous()                    # (nfc, ncols, N)
                 p_rows = (p_all.view(N, nfc, ncols).permute(1, 2, 0).contiguous()
                           if p_all is not None else None)
-                null = C.c_void_p(0)
-                if not any(infos):
-                    # xy[f0 : f0 + nfc] is one contiguous (nfc * ncols, 2N) block
-                    nv.check(nv.lib().pmr_pm_to_xy(
-                        nv.ptr(p_rows) if p_rows is not None else null, nv.ptr(m_rows),
-                        nfc * ncols, N, N, N, nv.ptr(xy[f0]), 2 * N, nv.stream_ptr()))
-                else:
-                    for q, f in enumerate(fs):
-                        if infos[q] == 0:
-                            nv.check(nv.lib().pmr_pm_to_xy(
-                                nv.ptr(p_rows[q]) if p_rows is not None else null, nv.ptr(m_rows[q]),
-                                ncols, N, N, N, nv.ptr(xy[f]), 2 * N, nv.stream_ptr()))
+                # xy[f0 : f0 + nfc] is one contiguous (nfc * ncols, 2N) block
+                nv.check(nv.lib().pmr_pm_to_xy(
+                    nv.ptr(p_rows) if p_rows is not None else C.c_void_p(0), nv.ptr(m_rows),
+                    nfc * ncols, N, N, N, nv.ptr(xy[f0]), 2 * N, nv.stream_ptr()))
                 del S, dinvS, rhs_m, rhs_pad, p_all
                 clock.mark("solves")
 
-        if bad:
-            if not allow_fallback:
-                raise LinAlgError(
-                    "orbital Hessian is not positive definite at frequencies "
-                    f"{[freqs[f] for f in sorted(bad)]} (Cholesky failed)")
-            for f in sorted(bad):
-                xy[f].copy_(self.solve_lu(g_rows, signs, freqs[f]))
-                self.stats["lu_fallback"] += 1
-        clock.mark("lu_fallback")
+        # ---- one host read of every pivot-failure word
+        bad = set()
+        if self._K_bad:
+            bad = set(range(nf))
+        elif infos:
+            flat = torch.cat([t.reshape(-1) for t, _ in infos]).cpu().numpy()
+            pos = 0
+            for t, what in infos:
+                cnt = int(t.numel())
+                vals = flat[pos:pos + cnt]
+                pos += cnt
+                if what == "K":
+                    if int(vals[0]) != 0:
+                        self._K_bad = True      # K itself is not SPD: everything goes to LU
+                        bad = set(range(nf))
+                else:
+                    bad.update(f for f, v in zip(what, vals) if int(v) != 0)
+        if new_K and not self._K_bad:
+            self._Kfac, self._dinvK = Kfac, dinvK
+        if not self._K_bad and Kinv is not None:
+            self._Kinv = Kinv
+        clock.mark("info_readback")
         clock.finish()
-        return xy
+        return xy, bad
 
     def solve_lu(self, g_rows, signs, w):
         """General path: LU with partial pivoting on the full super-Hessian G(w)."""

@@ -18,6 +18,8 @@
 #include <cstdlib>
 #include <vector>
 
+#include <cuda.h>  // CUtensorMap types only: the encoder is fetched through cudaGetDriverEntryPoint
+
 #include "pmr_common.cuh"
 
 namespace pmr {
@@ -31,6 +33,7 @@ namespace {
 
 constexpr int BK = 16;
 constexpr int PAD = 4;
+constexpr int TMA_STAGES_64 = 4;  // 4 x 24 KiB per CTA, two CTAs per SM
 
 struct GemmArgs {
   int M, N, K;
@@ -605,6 +608,261 @@ int launch_bulk_cfg(GemmArgs a, int batch1, int batch2, cudaStream_t st) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// TMA tensor-map variant for k-CONTIGUOUS operands (A stored [m][k], B stored [n][k]): the layout of
+// every Cholesky trailing update (C -= P P^T), the dominant kernel of the step.  One elected lane of a
+// producer warp issues ONE cp.async.bulk.tensor (SASS UTMALDG) per operand and stage -- a BM x 16 and
+// a BN x 16 box of a 4-D tensor map {k, row, batch2, batch1} -- tracked by the stage's "full"
+// mbarrier; out-of-range rows / k are zero-filled by the TMA unit, so every M/N/K edge is legal.
+// Shared memory is dense (128-byte rows, no padding) with the hardware 128-byte swizzle: the 16-byte
+// chunk c of row r lives at chunk c ^ (r & 7), which makes the per-lane 64-bit fragment loads of the
+// m8n8k4 shapes bank-conflict free (8 rows x 32 bytes of a warp's request fall on 4 distinct chunk
+// pairs, two rows each: the two-wavefront minimum of a 256-byte request).  The math warps never
+// touch global memory or a CTA-wide barrier in the main loop, exactly as in dgemm_bulk_kernel.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            int c3, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, "
+      "{%2, %3, %4, %5}], [%6];\n" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+      "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int BM, int BN, int WM, int WN, int NSTAGE, int MINB>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32 + 32, MINB)
+dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                 const GemmArgs p) {
+  constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
+  constexpr int NWC = WARPS_M * WARPS_N;
+  constexpr int MI = WM / 8, NI = WN / 8;
+  constexpr int ROWB = BK * 8;                       // 128 bytes per tile row
+  constexpr int A_BYTES = BM * ROWB, B_BYTES = BN * ROWB, STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long full_bar[NSTAGE];
+  __shared__ __align__(8) unsigned long long empty_bar[NSTAGE];
+  // the swizzle pattern is a function of the shared-memory ADDRESS: tiles start on 1 KiB boundaries
+  unsigned char* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int tm = blockIdx.x % p.tiles_m, tn = blockIdx.x / p.tiles_m;
+  const int bm0 = tm * BM, bn0 = tn * BN;
+  const bool lower = (p.flags & PMR_GEMM_LOWER) != 0;
+  if (lower && bn0 > bm0 + BM - 1) return;
+
+  const long long b1 = blockIdx.z, b2 = blockIdx.y;
+  double* Cb = p.C + b1 * p.c_b1 + b2 * p.c_b2;
+
+  int kt_begin = 0;
+  int kt_end = (p.K + BK - 1) / BK;
+  if (p.flags & PMR_GEMM_KSTART_M) kt_begin = bm0 / BK;
+  if (p.flags & PMR_GEMM_KEND_M) kt_end = min(kt_end, (min(p.K, bm0 + BM) + BK - 1) / BK);
+  const int KT = max(kt_end - kt_begin, 0);
+  const int kbase = kt_begin * BK;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], NWC);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == NWC) {
+    // ===== producer warp: one elected lane feeds the ring =====
+    if (lane == 0) {
+      // a batch stride of 0 (one operand shared by the whole batch) is a dimension of extent 1
+      const int a2 = p.a_b2 ? (int)b2 : 0, a1 = p.a_b1 ? (int)b1 : 0;
+      const int bb2 = p.b_b2 ? (int)b2 : 0, bb1 = p.b_b1 ? (int)b1 : 0;
+      for (int kt = 0; kt < KT; ++kt) {
+        const int slot = kt % NSTAGE;
+        if (kt >= NSTAGE) mbar_wait(&empty_bar[slot], ((kt / NSTAGE) - 1) & 1);
+        mbar_expect_tx(&full_bar[slot], STAGE_BYTES);
+        unsigned char* As = tiles + slot * STAGE_BYTES;
+        const int k0 = kbase + kt * BK;
+        tma_load_4d(As, &mapA, k0, bm0, a2, a1, &full_bar[slot]);
+        tma_load_4d(As + A_BYTES, &mapB, k0, bn0, bb2, bb1, &full_bar[slot]);
+      }
+    }
+    return;
+  }
+
+  // ===== math warps =====
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp % WARPS_M) * WM;
+  const int wn0 = (warp / WARPS_M) * WN;
+  const bool warp_active = !(lower && bn0 + wn0 > bm0 + wm0 + WM - 1);
+  const double alpha = p.alpha;
+  const bool use_beta = (p.beta != 0.0);
+  const double ratio = use_beta ? p.beta / alpha : 0.0;
+  double acc[MI][NI][2];
+#pragma unroll
+  for (int mi = 0; mi < MI; ++mi) {
+    const int m = bm0 + wm0 + mi * 8 + g;
+#pragma unroll
+    for (int ni = 0; ni < NI; ++ni) {
+      acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+      if (use_beta && warp_active) {
+        const int n = bn0 + wn0 + ni * 8 + 2 * t;
+        if (m < p.M && n < p.N) {
+          const bool ok1 = (n + 1 < p.N) && (!lower || n + 1 <= m);
+          const bool ok0 = (!lower || n <= m);
+          const double* c = Cb + (long long)m * p.c_sm + (long long)n * p.c_sn;
+          if (p.c_vec2 && ok0 && ok1) {
+            const double2 o = *reinterpret_cast<const double2*>(c);
+            acc[mi][ni][0] = ratio * o.x;
+            acc[mi][ni][1] = ratio * o.y;
+          } else {
+            if (ok0) acc[mi][ni][0] = ratio * c[0];
+            if (ok1) acc[mi][ni][1] = ratio * c[p.c_sn];
+          }
+        }
+      }
+    }
+  }
+
+  // byte offset of element (row = 8 q + g, k = 4 kk + t) inside a tile: rows are 128 bytes, the
+  // 16-byte chunk (2 kk + t/2) is XOR-ed with g (= row & 7: wm0, wn0 and 8 q are multiples of 8)
+  int koff[BK / 4];
+#pragma unroll
+  for (int kk = 0; kk < BK / 4; ++kk) koff[kk] = g * ROWB + (((2 * kk + (t >> 1)) ^ g) << 4) + ((t & 1) << 3);
+
+  for (int kt = 0; kt < KT; ++kt) {
+    const int slot = kt % NSTAGE;
+    mbar_wait(&full_bar[slot], (kt / NSTAGE) & 1);
+    if (warp_active) {
+      const unsigned char* As = tiles + slot * STAGE_BYTES + wm0 * ROWB;
+      const unsigned char* Bs = tiles + slot * STAGE_BYTES + A_BYTES + wn0 * ROWB;
+#pragma unroll
+      for (int kk = 0; kk < BK / 4; ++kk) {
+        double a[MI], b[NI];
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi)
+          a[mi] = *reinterpret_cast<const double*>(As + mi * 8 * ROWB + koff[kk]);
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni)
+          b[ni] = *reinterpret_cast<const double*>(Bs + ni * 8 * ROWB + koff[kk]);
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < NI; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[slot]);  // this warp is done reading the slot
+  }
+  if (!warp_active) return;
+
+#pragma unroll
+  for (int mi = 0; mi < MI; ++mi) {
+    const int m = bm0 + wm0 + mi * 8 + g;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int ni = 0; ni < NI; ++ni) {
+      const int n = bn0 + wn0 + ni * 8 + 2 * t;
+      if (n >= p.N) continue;
+      const bool ok1 = (n + 1 < p.N) && (!lower || n + 1 <= m);
+      const bool ok0 = (!lower || n <= m);
+      double* c = Cb + (long long)m * p.c_sm + (long long)n * p.c_sn;
+      if (p.c_vec2 && ok0 && ok1) {
+        double2 v;
+        v.x = alpha * acc[mi][ni][0];
+        v.y = alpha * acc[mi][ni][1];
+        *reinterpret_cast<double2*>(c) = v;
+      } else {
+        if (ok0) c[0] = alpha * acc[mi][ni][0];
+        if (ok1) c[p.c_sn] = alpha * acc[mi][ni][1];
+      }
+    }
+  }
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      sym = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(sym);
+  }();
+  return fn;
+}
+
+// 4-D map {k, rows, batch2, batch1} over a k-contiguous operand; box = 16 x box_rows x 1 x 1
+static bool make_operand_map(CUtensorMap* map, const double* base, int rows, int K, long long ld,
+                             int batch2, long long s_b2, int batch1, long long s_b1, int box_rows) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return false;
+  const cuuint64_t fallback = (cuuint64_t)ld * 8ull * (cuuint64_t)std::max(rows, 1);
+  cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(s_b2 ? batch2 : 1),
+                        (cuuint64_t)(s_b1 ? batch1 : 1)};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 8ull, s_b2 ? (cuuint64_t)s_b2 * 8ull : fallback,
+                           s_b1 ? (cuuint64_t)s_b1 * 8ull : fallback};
+  for (int i = 0; i < 3; ++i)
+    if (strides[i] % 16 != 0 || strides[i] >= (1ull << 40)) return false;
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1u, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(base), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// returns 0 on launch, >0 when the operands cannot be described by a tensor map (caller falls back
+// to the cp.async kernel), <0 on error
+template <int BM, int BN, int WM, int WN, int NSTAGE, int MINB>
+int launch_tma_cfg(GemmArgs a, int batch1, int batch2, cudaStream_t st) {
+  constexpr int NT = (BM / WM) * (BN / WN) * 32 + 32;
+  constexpr int SMEM = NSTAGE * (BM + BN) * BK * 8 + 1024;
+  CUtensorMap mapA, mapB;
+  if (!make_operand_map(&mapA, a.A, a.M, a.K, a.a_ld, batch2, a.a_b2, batch1, a.a_b1, BM) ||
+      !make_operand_map(&mapB, a.B, a.N, a.K, a.b_ld, batch2, a.b_b2, batch1, a.b_b1, BN))
+    return 1;
+  auto kern = dgemm_tma_kernel<BM, BN, WM, WN, NSTAGE, MINB>;
+  static thread_local bool configured = false;
+  if (!configured) {
+    PMR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  a.tiles_m = (a.M + BM - 1) / BM;
+  a.tiles_n = (a.N + BN - 1) / BN;
+  PMR_REQUIRE((long long)a.tiles_m * a.tiles_n < (1LL << 31), "dgemm: too many tiles");
+  PMR_REQUIRE(batch1 <= 65535 && batch2 <= 65535, "dgemm: batch count above 65535");
+  dim3 grid((unsigned)((long long)a.tiles_m * a.tiles_n), (unsigned)batch2, (unsigned)batch1);
+  ProfRecord rec{};
+  if (g_prof_on) {
+    cudaEventCreate(&rec.e0);
+    cudaEventCreate(&rec.e1);
+    const bool lower = (a.flags & PMR_GEMM_LOWER) != 0;
+    const double nb = (double)batch1 * batch2;
+    const double nn = std::min(a.M, a.N);
+    const double mn = lower ? 0.5 * nn * (nn + 1.0) + ((double)a.M - nn) * nn : (double)a.M * a.N;
+    double kk = a.K;
+    if (a.flags & PMR_GEMM_KSTART_M) kk = 0.5 * a.K;
+    rec.flops = 2.0 * mn * kk * nb;
+    rec.bytes = 8.0 * nb * (mn * (a.beta != 0.0 ? 2.0 : 1.0) + (double)a.M * a.K + (double)a.N * a.K);
+    rec.cls = (BN == 128 ? 0 : (BN == 64 ? 2 : 4)) + (lower ? 1 : 0);
+    cudaEventRecord(rec.e0, st);
+  }
+  kern<<<grid, NT, SMEM, st>>>(mapA, mapB, a);
+  if (g_prof_on) {
+    cudaEventRecord(rec.e1, st);
+    g_prof.push_back(rec);
+  }
+  PMR_CHECK_LAUNCH("dgemm_tma_kernel");
+  return 0;
+}
+
 template <int BM, int BN, int WM, int WN, int NSTAGE, int MINB>
 int launch_bulk(const GemmArgs& a, bool akc, bool bkc, int b1, int b2, cudaStream_t st) {
   if (akc && bkc) return launch_bulk_cfg<BM, BN, WM, WN, true, true, NSTAGE, MINB, true, 2>(a, b1, b2, st);
@@ -709,6 +967,17 @@ int gemm(const pmr_gemm_t& g0, cudaStream_t st) {
     if (bn == 128) return launch_bulk<128, 128, 32, 32, 4, 1>(a, akc, bkc, g.batch1, g.batch2, st);
     if (bn == 64) return launch_bulk<128, 64, 32, 32, 3, 2>(a, akc, bkc, g.batch1, g.batch2, st);
     return launch_bulk<128, 32, 32, 32, 4, 2>(a, akc, bkc, g.batch1, g.batch2, st);
+  }
+  // k-contiguous operands on both sides (C -= P P^T trailing updates, S = L_M^T L ...): tensor-map TMA
+  // feed, PMR_GEMM_NO_TMA=1 keeps them on the cp.async ring (comparison runs)
+  static const bool allow_tma = [] { const char* e = getenv("PMR_GEMM_NO_TMA"); return !(e && atoi(e)); }();
+  if (allow_tma && akc && bkc && a.a_vec2 && a.b_vec2 && g.K > 0 && !(g.flags & PMR_GEMM_C_ALIASES_A) &&
+      g.C2 == nullptr) {
+    int r;
+    if (bn == 128) r = launch_tma_cfg<128, 128, 32, 32, 4, 1>(a, g.batch1, g.batch2, st);
+    else if (bn == 64) r = launch_tma_cfg<128, 64, 32, 32, TMA_STAGES_64, 2>(a, g.batch1, g.batch2, st);
+    else r = launch_tma_cfg<128, 32, 32, 32, 4, 2>(a, g.batch1, g.batch2, st);
+    if (r <= 0) return r;   // > 0: not expressible as a tensor map, fall through
   }
   // EXPERIMENT (PMR_GEMM_WS=1): warp-specialised cp.async producers + mbarriers for the k-contiguous
   // layouts.  Measured on B200 it is not faster than the plain ring (8192^3: 32.4 vs 33.7 TFLOP/s;

@@ -217,6 +217,23 @@ def allgather_columns(X, n_cols_total: int):
     return out
 
 
+def any_rank(flag: bool) -> bool:
+    """True on every rank if ``flag`` is true on at least one (collective agreement on a failure
+    before the next data-path collective)."""
+    if not is_initialized():
+        return bool(flag)
+    import torch
+
+    d = dist()
+    if d.get_backend() == "gloo" or not torch.cuda.is_available():
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32)
+    else:
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32,
+                         device=torch.device("cuda", torch.cuda.current_device()))
+    d.all_reduce(t, op=d.ReduceOp.MAX)
+    return bool(int(t.item()))
+
+
 def barrier() -> None:
     if is_initialized():
         dist().barrier()

@@ -52,6 +52,8 @@ class Operator:
         self.rspvecs_beta = []
         # device-resident mirrors (torch CUDA tensors) used by the solvers and drivers
         self._dev = {}
+        self._dev_src = {}       # host object each device mirror was made from (identity check)
+        self._custom = set()     # spins whose supervector the caller replaced after form_rhs
         self._rspvecs_alph_dev = []
         self._rspvecs_beta_dev = []
 
@@ -112,6 +114,8 @@ class Operator:
             else:
                 setattr(self, f"mo_integrals_ai_{tag}", rhs_ai[:, :, None])
                 setattr(self, f"mo_integrals_ai_supervector_{tag}", rhs[:, :, None])
+            self._dev_src[f"super_{tag}"] = getattr(self, f"mo_integrals_ai_supervector_{tag}")
+            self._custom.discard(tag)
 
     def form_rhs_geometric(self, *args, **kwargs):
         """Nuclear-displacement right-hand sides need psi4 derivative integrals
@@ -120,10 +124,21 @@ class Operator:
 
     # ------------------------------------------------------------------ device mirrors
     def supervector_dev(self, tag: str):
-        """(ncomp, 2nov) CUDA tensor of the supervectors; uploads the NumPy attribute if the
-        caller replaced it after ``form_rhs``."""
+        """(ncomp, 2nov) CUDA tensor of the supervectors.  The reference multiplies by whatever
+        ``mo_integrals_ai_supervector_*`` holds when the solver runs (solvers.py:407-410), so a
+        caller that REASSIGNS the attribute after ``form_rhs`` (as ``form_rhs_geometric`` does,
+        operators.py:127-149) gets the new right-hand side: the mirror is re-uploaded when the
+        attribute is a different object (in-place edits of the old array are not seen)."""
         key = f"super_{tag}"
-        if key not in self._dev:
-            host = getattr(self, f"mo_integrals_ai_supervector_{tag}")
-            self._dev[key] = nv.to_dev(host)[:, :, 0].contiguous()
+        host = getattr(self, f"mo_integrals_ai_supervector_{tag}", None)
+        if key not in self._dev or (host is not None and self._dev_src.get(key) is not host):
+            t = host if nv.is_device_array(host) else nv.to_dev(host)
+            self._dev[key] = t[:, :, 0].contiguous()
+            self._dev_src[key] = host
+            self._custom.add(tag)
         return self._dev[key]
+
+    def has_standard_supervector(self, tag: str) -> bool:
+        """True while the supervector is the ``[g; -+g]`` that ``form_rhs`` built."""
+        self.supervector_dev(tag)
+        return tag not in self._custom

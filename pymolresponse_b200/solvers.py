@@ -193,7 +193,7 @@ class _HessianBlocks:
             self._tei_mo_dev = [nv.to_dev(t) for t in self.tei_mo]
         return self._tei_mo_dev
 
-    def _assemble_rhf(self, hamiltonian, spin, want_ab):
+    def _assemble_rhf(self, hamiltonian, spin, want_ab, want_mk=True):
         """-> (M, K, A, B); A/B only when want_ab (LU fallback, explicit_hessian)."""
         nocc, nvirt, _, _ = self.occupations
         nov = nocc * nvirt
@@ -209,19 +209,20 @@ class _HessianBlocks:
         tda = hamiltonian == Hamiltonian.TDA
         if tda:
             terms = (terms[0], terms[1], bl.absent(), bl.absent())
-        A = B = None
+        A = B = M = K = None
         if tda:
             A, _ = bl.run(nocc, nvirt, nocc, nvirt, terms, eps, "P")
             M = K = A
         else:
-            M = nv.empty(nov, nov)
-            K = nv.empty(nov, nov)
-            bl.run(nocc, nvirt, nocc, nvirt, terms, eps, "PQ", out_mode=1, out0=M, out1=K, ld=nov)
+            if want_mk:
+                M = nv.empty(nov, nov)
+                K = nv.empty(nov, nov)
+                bl.run(nocc, nvirt, nocc, nvirt, terms, eps, "PQ", out_mode=1, out0=M, out1=K, ld=nov)
             if want_ab:
                 A, B = bl.run(nocc, nvirt, nocc, nvirt, terms, eps, "PQ")
         return M, K, A, B
 
-    def _assemble_uhf(self, hamiltonian, spin, want_ab):
+    def _assemble_uhf(self, hamiltonian, spin, want_ab, want_mk=True):
         """Joint (nov_a + nov_b) matrices [[ss_a, os_a],[os_b, ss_b]] -> (M, K, A, B)."""
         na, va, nb, vb = self.occupations
         nova, novb = na * va, nb * vb
@@ -265,14 +266,15 @@ class _HessianBlocks:
                 bl.run(ox, vx, oy, vy, terms(name), eps, "PQ", out_mode=mode, out0=out0, out1=out1,
                        ld=nt, off0=off, off1=off)
 
-        A = B = None
+        A = B = M = K = None
         if tda:
             A = nv.empty(nt, nt)
             fill(A, None, 0)
             M = K = A
         else:
-            M, K = nv.empty(nt, nt), nv.empty(nt, nt)
-            fill(M, K, 1)
+            if want_mk:
+                M, K = nv.empty(nt, nt), nv.empty(nt, nt)
+                fill(M, K, 1)
             if want_ab:
                 A, B = nv.empty(nt, nt), nv.empty(nt, nt)
                 fill(A, B, 0)
@@ -316,7 +318,7 @@ class ExactLineqSolver(LineqSolver, _HessianBlocks, ABC):
         assert isinstance(frequency, float)
         self._last_call = (hamiltonian, spin, frequency)
         _, _, A, B = (self._assemble_uhf if self.is_uhf else self._assemble_rhf)(
-            hamiltonian, spin, True)
+            hamiltonian, spin, True, want_mk=False)
         if hamiltonian == Hamiltonian.TDA:
             B = None
         if not self.is_uhf:
@@ -367,11 +369,52 @@ class ExactLineqSolver(LineqSolver, _HessianBlocks, ABC):
         eng.shift_diagonal(eye, N, 1.0)
         return nv.to_host(eng.getrs(Gd, ipiv, eye))
 
+    @staticmethod
+    def _gpu_inverse_cholesky(G: np.ndarray) -> np.ndarray:
+        """G^-1 through the Cholesky factor, raising like ``scipy.linalg.cholesky`` when G is not
+        positive definite (reference solvers.py:527-530)."""
+        Gd = nv.to_dev(G).clone()
+        dinv, info = eng.potrf(Gd)
+        if int(info.item()) != 0:
+            raise np.linalg.LinAlgError(
+                f"{int(info.item())}-th leading minor of the array is not positive definite")
+        low = eng.potri_lower(Gd, dinv).tril()
+        return nv.to_host(low + low.tril(-1).t())
+
     @property
     def explicit_hessian_inv(self):
         if self._explicit_hessian_inv is None and self.explicit_hessian is not None:
             self.invert_explicit_hessian()
         return self._explicit_hessian_inv
+
+    # UHF Schur-complement inverses (reference solvers.py:519-520): the reference sets them in
+    # ``invert_explicit_hessian`` on every run; here they are materialised on first access
+    _left_alph = None
+    _left_beta = None
+
+    @property
+    def left_alph(self):
+        if self._left_alph is None and self.is_uhf and self.explicit_hessian is not None:
+            self.invert_explicit_hessian()
+        if self._left_alph is None:
+            raise AttributeError("left_alph")
+        return self._left_alph
+
+    @left_alph.setter
+    def left_alph(self, value):
+        self._left_alph = value
+
+    @property
+    def left_beta(self):
+        if self._left_beta is None and self.is_uhf and self.explicit_hessian is not None:
+            self.invert_explicit_hessian()
+        if self._left_beta is None:
+            raise AttributeError("left_beta")
+        return self._left_beta
+
+    @left_beta.setter
+    def left_beta(self, value):
+        self._left_beta = value
 
     @explicit_hessian_inv.setter
     def explicit_hessian_inv(self, value):
@@ -409,40 +452,62 @@ class ExactLineqSolver(LineqSolver, _HessianBlocks, ABC):
         self._solve_frequencies(ham, spin, [w])
 
     def _gradient_rows(self):
-        """All operators' property gradients g stacked as rows, plus their supervector signs."""
+        """All operators' property gradients g stacked as rows, plus their supervector signs and a
+        plan [(first row, ncomp, custom)] for :meth:`_store_xy`.  A supervector the caller replaced
+        after ``form_rhs`` is a general [u; l]: it is split into a real-type column (u - l)/2 with
+        sign -1 and an imaginary-type column (u + l)/2 with sign +1 (the equations are linear)."""
         na, va, nb, vb = self.occupations
         nova, novb = na * va, nb * vb
-        rows, signs = [], []
+        torch = nv.torch_mod()
+        rows, signs, plan = [], [], []
         for op in self.operators:
-            ga = op.supervector_dev("alph")[:, :nova]
-            if self.is_uhf:
-                gb = op.supervector_dev("beta")[:, :novb]
-                rows.append(nv.torch_mod().cat((ga, gb), dim=1))
+            tags = ("alph", "beta") if self.is_uhf else ("alph",)
+            halves = []
+            for tag, nov in zip(tags, (nova, novb)):
+                sv = op.supervector_dev(tag)
+                halves.append((sv[:, :nov], sv[:, nov:]))
+            upper = torch.cat([h[0] for h in halves], dim=1) if self.is_uhf else halves[0][0]
+            ncomp = int(upper.shape[0])
+            custom = not all(op.has_standard_supervector(tag) for tag in tags)
+            plan.append((len(signs), ncomp, custom))
+            if not custom:
+                rows.append(upper)
+                signs += [+1 if op.is_imaginary else -1] * ncomp
             else:
-                rows.append(ga)
-            signs += [+1 if op.is_imaginary else -1] * int(ga.shape[0])
+                lower = torch.cat([h[1] for h in halves], dim=1) if self.is_uhf else halves[0][1]
+                rows.append(0.5 * (upper - lower))
+                rows.append(0.5 * (upper + lower))
+                signs += [-1] * ncomp + [+1] * ncomp
         if not rows:
-            return None, signs
-        return nv.torch_mod().cat(rows, dim=0).contiguous(), signs
+            return None, signs, plan
+        return torch.cat(rows, dim=0).contiguous(), signs, plan
 
     def _solve_xy(self, hamiltonian, spin, frequencies, distributed=False, global_frequencies=None):
         """(nf, ncols, 2N) CUDA tensor of [X;Y] for the given frequencies (this rank's share)."""
         if getattr(self, "_prepared_for", None) != (hamiltonian, spin):
             self._prepare(hamiltonian, spin, want_ab=False)
         system = self._system
-        g_rows, signs = self._gradient_rows()
+        g_rows, signs, plan = self._gradient_rows()
+        self._plan = plan
         if g_rows is None:
             return None
-        try:
-            xy = system.solve(g_rows, signs, frequencies, allow_fallback=False,
-                              distributed=distributed, global_frequencies=global_frequencies)
-        except eng.LinAlgError:
+        xy, bad = system.solve(g_rows, signs, frequencies, distributed=distributed,
+                               global_frequencies=global_frequencies)
+        if bad:
+            freqs = [float(w) for w in frequencies]
             if not self._allow_lu_fallback:
-                raise
-            # pivoted LU on the full G(w) needs the A and B blocks themselves
-            self._prepare(hamiltonian, spin, want_ab=True)
-            system = self._system
-            xy = system.solve(g_rows, signs, frequencies, allow_fallback=True)
+                self.solve_stats = dict(system.stats)
+                raise eng.LinAlgError(
+                    "orbital Hessian is not positive definite at frequencies "
+                    f"{[freqs[f] for f in sorted(bad)]} (Cholesky failed)")
+            # pivoted LU on the full G(w) for the failed frequencies only; it needs the A and B
+            # blocks themselves, assembled now (M, K and their factors stay as they are)
+            if system.A is None:
+                assemble = self._assemble_uhf if self.is_uhf else self._assemble_rhf
+                _, _, system.A, system.B = assemble(hamiltonian, spin, True, want_mk=False)
+            for f in sorted(bad):
+                xy[f].copy_(system.solve_lu(g_rows, signs, freqs[f]))
+                system.stats["lu_fallback"] += 1
         self.solve_stats = dict(system.stats)
         return xy
 
@@ -452,10 +517,10 @@ class ExactLineqSolver(LineqSolver, _HessianBlocks, ABC):
         nt = nova + novb if self.is_uhf else nova
         torch = nv.torch_mod()
         for f in range(n_frequencies):
-            c0 = 0
-            for op in self.operators:
-                nc = int(op.supervector_dev("alph").shape[0])
+            for op, (c0, nc, custom) in zip(self.operators, self._plan):
                 blk = xy[f][c0:c0 + nc]
+                if custom:
+                    blk = blk + xy[f][c0 + nc:c0 + 2 * nc]
                 if self.is_uhf:
                     X, Y = blk[:, :nt], blk[:, nt:]
                     self._append_rspvecs(op, "alph",
@@ -464,7 +529,6 @@ class ExactLineqSolver(LineqSolver, _HessianBlocks, ABC):
                                          torch.cat((X[:, nova:], Y[:, nova:]), dim=1).contiguous())
                 else:
                     self._append_rspvecs(op, "alph", blk.contiguous())
-                c0 += nc
 
     def _solve_frequencies(self, hamiltonian, spin, frequencies):
         """Solve every frequency (dealt round-robin to the ranks when torch.distributed is up and
@@ -474,9 +538,19 @@ class ExactLineqSolver(LineqSolver, _HessianBlocks, ABC):
         rank, world = pd.rank_world()
         if world > 1 and getattr(self, "distribute_frequencies", False):
             mine = pd.round_robin(len(frequencies), rank, world)
-            xy_local = self._solve_xy(hamiltonian, spin, [frequencies[i] for i in mine],
-                                      distributed=True, global_frequencies=list(frequencies))
-            if xy_local is None:
+            xy_local, err = None, None
+            try:
+                xy_local = self._solve_xy(hamiltonian, spin, [frequencies[i] for i in mine],
+                                          distributed=True, global_frequencies=list(frequencies))
+            except np.linalg.LinAlgError as e:
+                err = e
+            # agree on failure BEFORE the gather: a rank that raised alone would leave the others
+            # waiting in the collective (the reference raises cleanly, solvers.py:527)
+            if pd.any_rank(err is not None):
+                raise err if err is not None else eng.LinAlgError(
+                    "orbital Hessian is not positive definite at a frequency owned by another rank "
+                    "(Cholesky failed)")
+            if not self.operators:
                 return
             xy = pd.gather_round_robin([xy_local[k] for k in range(len(mine))], len(frequencies))
         else:
@@ -508,6 +582,7 @@ class ExactLineqSolver(LineqSolver, _HessianBlocks, ABC):
             self._solve_frequencies(hamiltonian, spin, freqs)
             self._explicit_hessian = None
             self._explicit_hessian_inv = None
+            self._left_alph = self._left_beta = None
             self._lazy_hessian = (hamiltonian, spin, freqs[-1])
             self._last_call = (hamiltonian, spin, freqs[-1])
 
@@ -566,7 +641,7 @@ class ExactInvCholesky(ExactLineqSolver):
 
     def invert_explicit_hessian(self) -> None:
         assert self.explicit_hessian is not None
-        self._invert_with(self._gpu_inverse)
+        self._invert_with(self._gpu_inverse_cholesky)
 
 
 class IterativeLinEqSolver(LineqSolver):

@@ -87,6 +87,53 @@ def test_dgemm_bulk_copy_path(a_kc, b_kc, shape, monkeypatch):
     assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
 
 
+@pytest.mark.parametrize("shape", [(1000, 96, 256), (130, 34, 70), (4096, 32, 512), (258, 200, 18),
+                                   (131, 77, 48), (640, 640, 512), (129, 129, 2)])
+def test_dgemm_tma_tensor_map_path(shape):
+    """Both operands k-contiguous with even leading dimensions: the cp.async.bulk.tensor (tensor-map
+    TMA, 128-byte swizzle) producer/consumer kernel; ragged M / N / K edges are zero-filled by the
+    TMA unit.  Compared with the cp.async ring (PMR_GEMM_NO_TMA is read once per process, so the
+    cross-check is against NumPy)."""
+    M, N, K = shape
+    for pad in (0, 2, 6):
+        got, want, _ = _gemm_case(M, N, K, True, True, pad_a=pad, pad_b=pad, alpha=-1.0, beta=1.0, seed=41)
+        assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+    got, want, _ = _gemm_case(M, N, K, True, True, alpha=2.0, beta=0.0, seed=42)
+    assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+
+
+def test_dgemm_tma_batched_shared_operand_and_lower():
+    """Tensor-map path with a two-level batch, one operand shared by the batch (stride 0 -> extent-1
+    dimension of the map) and the lower-triangular store of the Cholesky trailing update."""
+    nv = _nv()
+    r = _rng(17)
+    b1, b2, M, K = 3, 2, 300, 64
+    P = r.standard_normal((b1, b2, M, K))
+    Q = r.standard_normal((b2, M, K))            # shared across b1
+    C0 = r.standard_normal((b1, b2, M, M))
+    Pd, Qd, Cd = nv.to_dev(P), nv.to_dev(Q), nv.to_dev(C0).clone()
+    nv.dgemm(M, M, K, -1.0, Pd, 0, K, 1, Qd, 0, 1, K, 1.0, Cd, 0, M, 1, batch1=b1, batch2=b2,
+             a_b=(b2 * M * K, M * K), b_b=(0, M * K), c_b=(b2 * M * M, M * M), flags=nv.GEMM_LOWER)
+    want = C0 - np.einsum("xymk,ynk->xymn", P, Q)
+    got = nv.to_host(Cd)
+    low = np.tril(np.ones((M, M), dtype=bool))
+    assert np.abs(got[..., low] - want[..., low]).max() <= 1e-12 * np.abs(want).max()
+    assert np.array_equal(got[..., ~low], C0[..., ~low])
+    # sub-matrix views of one big matrix (offsets, leading dimension of the parent), as in potrf
+    N = 700
+    S = r.standard_normal((N, N))
+    Sd = nv.to_dev(S).clone()
+    r0, j0, kw = 256, 128, 128
+    rows = N - r0
+    nv.dgemm(rows, rows, kw, -1.0, Sd, r0 * N + j0, N, 1, Sd, r0 * N + j0, 1, N, 1.0,
+             Sd, r0 * N + r0, N, 1, flags=nv.GEMM_LOWER)
+    want = S.copy()
+    upd = S[r0:, r0:] - S[r0:, j0:j0 + kw] @ S[r0:, j0:j0 + kw].T
+    lowr = np.tril(np.ones((rows, rows), dtype=bool))
+    want[r0:, r0:][lowr] = upd[lowr]
+    assert np.abs(nv.to_host(Sd) - want).max() <= 1e-12 * np.abs(want).max()
+
+
 def test_dgemm_lower_flag_leaves_upper_untouched():
     nv = _nv()
     got, want, C0 = _gemm_case(260, 260, 48, True, True, alpha=-1.0, beta=1.0,

@@ -79,6 +79,51 @@ for freqs in ([0.0, 0.1, 0.2], [0.3], [0.0]):
     if any(w != 0.0 for w in freqs):
         assert solver.solve_stats.get("potri_shared", 0) == 1 and solver.solve_stats["potri"] == 0
         assert solver.solve_stats.get("potrf_shared", 0) == 1
+# one frequency above the first pole (owned by rank 1): ExactInv falls back to LU there and the
+# gather still completes; ExactInvCholesky raises LinAlgError on EVERY rank (no rank left waiting)
+freqs = [0.1, 1.9, 0.2]
+ref = orc.run_cphf(case["C"], case["E"], case["occupations"], tei_ref, "partial",
+                   [{"ao_integrals": Or, "is_imaginary": False}], freqs)
+for cls in (solvers.ExactInv, solvers.ExactInvCholesky):
+    solver = cls(case["C"], case["E"], case["occupations"])
+    solver.distribute_frequencies = True
+    solver.tei_mo = a.tei_mo
+    driver = cphf.CPHF(solver)
+    driver.add_operator(operators.Operator(label="dipole", is_imaginary=False, ao_integrals=Or))
+    driver.set_frequencies(freqs)
+    try:
+        driver.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet, program=None, program_obj=None)
+        raised = False
+    except np.linalg.LinAlgError:
+        raised = True
+    assert raised == (cls is solvers.ExactInvCholesky), (cls, raised, rank)
+    if not raised:
+        for f in range(3):
+            assert np.abs(driver.results[f] - ref["results"][f]).max() <= 1e-9, f
+# UHF, dense nu-sharded: perform_uhf_partial(reduce=True) -> the pyscf 6-tuple on every rank
+nu_, na_, nb_ = 22, 4, 3
+ucase = synthetic.uhf_case(nu_, na_, nb_)
+ulo, uhi = pd.shard_range(nu_, rank, world)
+ua = AO2MO(ucase["C"], ucase["occupations"], I=np.ascontiguousarray(ucase["I"][:, ulo:uhi]),
+           nu_range=(ulo, uhi), device_results=True, reduce=True)
+ua.perform_uhf_partial()
+utei_ref = orc.ao2mo_uhf_partial(ucase["I"], ucase["C"], ucase["occupations"])
+assert len(ua.tei_mo) == 6
+for got, want in zip(ua.tei_mo, utei_ref):
+    assert tuple(got.shape) == want.shape
+    assert np.abs(got.cpu().numpy() - want).max() <= 1e-12 * np.abs(want).max()
+usolver = solvers.ExactInv(ucase["C"], ucase["E"], ucase["occupations"])
+usolver.distribute_frequencies = True
+usolver.tei_mo = ua.tei_mo
+udriver = cphf.CPHF(usolver)
+Ou = synthetic.operator_integrals(nu_, 3, False)
+udriver.add_operator(operators.Operator(label="dipole", is_imaginary=False, ao_integrals=Ou))
+udriver.set_frequencies([0.0, 0.12])
+udriver.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet, program=None, program_obj=None)
+uref = orc.run_cphf(ucase["C"], ucase["E"], ucase["occupations"], utei_ref, "partial",
+                    [{"ao_integrals": Ou, "is_imaginary": False}], [0.0, 0.12])
+for f in range(2):
+    assert np.abs(udriver.results[f] - uref["results"][f]).max() <= 1e-9
 pd.barrier()
 dist.destroy_process_group()
 print("ok", rank)

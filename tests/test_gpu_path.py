@@ -892,3 +892,91 @@ def test_solvers_share_hessian(golden_dir):
     for f in range(len(g["frequencies"])):
         np.testing.assert_allclose(d2.results[f], ref[f][:3, :3], rtol=0, atol=1e-10)
     np.testing.assert_allclose(d1.results[0], ref[0][3:, 3:], rtol=0, atol=1e-10)
+
+
+# ------------------------------------------------------------------------- round-2 API fixes
+def test_lu_fallback_only_for_failed_frequencies(golden_dir):
+    """Three frequencies, one above the first pole: the Cholesky results of the good ones are kept,
+    LU runs once, M / K and the factor of K are not rebuilt."""
+    from pymolresponse_b200 import synthetic
+
+    g = np.load(golden_dir / "synthetic_rhf_n10.npz")
+    n, o = int(g["n"]), int(g["nocc"])
+    case = synthetic.rhf_case(n, o, build_eri=False)
+    ops = [{"ao_integrals": synthetic.operator_integrals(n, 3, False), "is_imaginary": False},
+           {"ao_integrals": synthetic.operator_integrals(n, 2, True), "is_imaginary": True}]
+    freqs = [0.0, 1.9, 0.2]
+    tei = (g["ovov"], g["oovv"])
+    ref = orc.run_cphf(case["C"], case["E"], case["occupations"], tei, "partial", ops, freqs)
+    solver, driver, objs = _run(case["C"], case["E"], case["occupations"], tei, "partial", ops, freqs,
+                                "rpa", "singlet")
+    assert solver.solve_stats["lu_fallback"] == 1
+    assert solver.solve_stats["potrf"] == 1 and solver.solve_stats["potrf_batch"] == 3
+    for f in range(3):
+        np.testing.assert_allclose(driver.results[f], ref["results"][f], rtol=0, atol=1e-9)
+        for k in range(2):
+            assert np.abs(objs[k].rspvecs_alph[f] - ref["rspvecs_alph"][k][f]).max() <= 1e-9
+
+
+def test_replaced_supervector_is_honoured(golden_dir):
+    """The reference multiplies G^-1 by whatever ``mo_integrals_ai_supervector_alph`` holds when the
+    solver runs (solvers.py:407-410): a caller that reassigns it after form_rhs (as
+    form_rhs_geometric does) must get the response to the NEW, general [u; l] right-hand side."""
+    from pymolresponse_b200 import cphf, operators, solvers, synthetic
+    from pymolresponse_b200.core import Hamiltonian, Spin
+
+    g = np.load(golden_dir / "synthetic_rhf_n10.npz")
+    n, o = int(g["n"]), int(g["nocc"])
+    nov = o * (n - o)
+    case = synthetic.rhf_case(n, o, build_eri=False)
+    tei = (g["ovov"], g["oovv"])
+    w = 0.15
+    solver = solvers.ExactInv(case["C"], case["E"], case["occupations"])
+    solver.tei_mo = tei
+    driver = cphf.CPHF(solver)
+    op = operators.Operator(label="dipole", is_imaginary=False,
+                            ao_integrals=synthetic.operator_integrals(n, 3, False))
+    driver.add_operator(op)
+    rng = np.random.default_rng(8)
+    new_rhs = rng.standard_normal((3, 2 * nov, 1))
+    op.mo_integrals_ai_supervector_alph = new_rhs
+    driver.set_frequencies([w])
+    driver.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet, program=None, program_obj=None)
+    G = orc.explicit_hessian_rhf(case["E"], tei, "partial", o, "rpa", "singlet", w)
+    want = np.linalg.solve(G, new_rhs[:, :, 0].T).T
+    assert np.abs(op.rspvecs_alph[0][:, :, 0] - want).max() <= 1e-10
+    np.testing.assert_allclose(driver.results[0], 2.0 * new_rhs[:, :, 0] @ want.T, rtol=0, atol=1e-9)
+
+
+def test_cholesky_explicit_inverse_raises_and_uhf_left_blocks(golden_dir):
+    from pymolresponse_b200 import solvers, synthetic
+
+    g = np.load(golden_dir / "synthetic_rhf_n10.npz")
+    n, o = int(g["n"]), int(g["nocc"])
+    case = synthetic.rhf_case(n, o, build_eri=False)
+    ops = [{"ao_integrals": synthetic.operator_integrals(n, 3, False), "is_imaginary": False}]
+    tei = (g["ovov"], g["oovv"])
+    s = solvers.ExactInvCholesky(case["C"], case["E"], case["occupations"])
+    s.tei_mo = tei
+    _, H, S = _enums()
+    s.form_explicit_hessian(H["rpa"], S["singlet"], 0.1)
+    s.invert_explicit_hessian()
+    assert np.abs(s.explicit_hessian_inv @ s.explicit_hessian - np.eye(s.explicit_hessian.shape[0])).max() <= 1e-11
+    s.form_explicit_hessian(H["rpa"], S["singlet"], 1.9)       # above the first pole: indefinite
+    with pytest.raises(np.linalg.LinAlgError):
+        s.invert_explicit_hessian()
+    # UHF: left_alph / left_beta are readable right after run(), as in the reference
+    gu = np.load(golden_dir / "synthetic_uhf_n9.npz")
+    nu, na, nb = int(gu["n"]), int(gu["na"]), int(gu["nb"])
+    ucase = synthetic.uhf_case(nu, na, nb, build_eri=False)
+    uops = [{"ao_integrals": synthetic.operator_integrals(nu, 3, False), "is_imaginary": False}]
+    utei = tuple(gu[f"partial_{k}"] for k in range(6))
+    for cls in (solvers.ExactInv, solvers.ExactInvCholesky):
+        su, _, _ = _run(ucase["C"], ucase["E"], ucase["occupations"], utei, "partial", uops, [0.1],
+                        "rpa", "singlet", solver_cls=cls)
+        G4 = orc.explicit_hessian_uhf(ucase["E"], utei, "partial", ucase["occupations"], "rpa",
+                                      "singlet", 0.1)
+        left_a = np.linalg.inv(G4[0] - G4[1] @ np.linalg.inv(G4[3]) @ G4[2])
+        left_b = np.linalg.inv(G4[3] - G4[2] @ np.linalg.inv(G4[0]) @ G4[1])
+        assert np.abs(su.left_alph - left_a).max() <= 1e-10
+        assert np.abs(su.left_beta - left_b).max() <= 1e-10

@@ -85,8 +85,10 @@ def test_blocked_spd_algebra_against_lapack():
     assert np.abs(np.tril(L) - Lref).max() <= 1e-12
     Bm = rng.standard_normal((N, 5))
     np.testing.assert_allclose(fac.cho_solve_blocked(L, Bm), np.linalg.solve(A, Bm), rtol=0, atol=1e-11)
-    Ainv = fac.spd_inverse(L, col_chunk=700)
-    assert np.abs(Ainv @ A - np.eye(N)).max() <= 1e-11
+    Ainv = fac.spd_inverse(L, nb=700)
+    assert np.abs(np.triu(Ainv, 701)).max() == 0.0          # only the lower triangle is filled
+    Afull = np.tril(Ainv) + np.tril(Ainv, -1).T
+    assert np.abs(Afull @ A - np.eye(N)).max() <= 1e-11
     bad = A.copy()
     bad[10, 10] = -1.0
     with pytest.raises(np.linalg.LinAlgError):

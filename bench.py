@@ -683,7 +683,7 @@ def bench_workload(w, args, rank, world, local, torch, peak64, do_e2e=True, do_c
         "stage_ms": stages, "solve_stats": {k: v for k, v in (res.get("stats") or {}).items() if k != "ms"},
         "fraction_of_fp64_peak": (F / (ms * 1e-3) / 1e12) / (world * peak64) if peak64 else None,
     }
-    del res, system
+    del res
     torch.cuda.empty_cache()
     return record, gpu
 

@@ -254,6 +254,39 @@ int pmr_cphf_update(double* x, const double* x_old, const double* rhs, const dou
                     double* maxdiff /* device, ncomp */, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Matrix-free block PCG for the iterative path (replaces the fixed-point loop of
+ * IterativeLinEqSolver._run, solvers.py:603-637, when method="cg"): solves
+ *   [[K, -w], [-w, M]] [p; m] = [(1+s) g; (1-s) g],  K = A + B_ref, M = A - B_ref
+ * for k systems at once without forming A or B: sigma = H d comes from three pmr_dgemm calls on
+ * the MO blocks (U = (ia|jb) d, W = (ib|ja) d, V = (ij|ab) d; explicit_equations_partial.py:34-38,
+ * 92-96) and the kernels below.  Vectors are (nov, 2k) row-major, columns [0,k) = p parts,
+ * [k,2k) = m parts; `w` is a device array of k frequencies; all CG scalars are device arrays.
+ *   pmr_iter_permute_ov_rows   Zp[(b,j),:] = Z[(j,b),:]            (operand order of the W GEMM)
+ *   pmr_iter_sigma_combine     rows [row0,row0+rows) of sigma from local U/V/W rows and global d:
+ *                              q_p = cK U_p - V_p + sK W_p + D d_p - w d_m,
+ *                              q_m = cM U_m - V_m + sM W_m + D d_m - w d_p   (D = e_a - e_i)
+ *   pmr_iter_precond           y = P^-1 r, P = [[D,-w],[-w,D]] (the uncoupled Hessian,
+ *                              cphf.py:94-96: the reference's initial guess, solvers.py:606-611)
+ *   pmr_iter_coldot            out[c] = sum_rows X[:,c] Y[:,c] + X[:,k+c] Y[:,k+c] (deterministic)
+ *   pmr_iter_update_zr         alpha = rho/dq;  z += alpha d;  r -= alpha q
+ *   pmr_iter_update_d          beta = rho_new/rho_old;  d = y + beta d
+ * ---------------------------------------------------------------------------------------- */
+int pmr_iter_permute_ov_rows(const double* Z, int no, int nv, int ncols, double* Zp, void* stream);
+int pmr_iter_sigma_combine(const double* U, const double* V, const double* W, const double* Z,
+                           const double* ediff, const double* w, long long row0, long long rows,
+                           int k, double cK, double sK, double cM, double sM, double* q,
+                           void* stream);
+int pmr_iter_precond(const double* r, const double* ediff, const double* w, long long nov, int k,
+                     double* y, void* stream);
+long long pmr_iter_coldot_workspace(long long nov, int k);
+int pmr_iter_coldot(const double* X, const double* Y, long long nov, int k, double* out,
+                    double* work, void* stream);
+int pmr_iter_update_zr(double* z, double* r, const double* d, const double* q, const double* rho,
+                       const double* dq, long long nov, int k, void* stream);
+int pmr_iter_update_d(double* d, const double* y, const double* rho_new, const double* rho_old,
+                      long long nov, int k, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * AO ERI upload exploiting the 8-fold permutational symmetry (host buffer in, full tensor in HBM).
  * Replaces the plain host->device copy of the (n,n,n,n) tensor the reference hands to
  * AO2MO.__init__ (pymolresponse/ao2mo.py:18-33; the tensors come from pyscf int2e / psi4 ao_eri,

@@ -13,24 +13,32 @@ from pymolresponse_b200 import _native as nv
 ABSENT = None
 
 
-def _ovov_direct(t, coef):
+# ``i_lo``: the tensor holds only the occupied rows [i_lo, i_lo + t.shape[0]) of the block (row-block
+# sharded Hessian); the kernel addresses with the GLOBAL i, so the base pointer is moved back by
+# i_lo rows (it is only dereferenced for i inside the range the launch covers).
+
+
+def _ovov_direct(t, coef, i_lo=0):
     """(i,a,j,b) -> ovov[i,a,j,b]"""
     _, v, o2, v2 = t.shape
-    return nv.term(t, 0, s_i=v * o2 * v2, s_a=o2 * v2, s_j=v2, s_b=1, coef=coef)
+    s_i = v * o2 * v2
+    return nv.term(t, -i_lo * s_i, s_i=s_i, s_a=o2 * v2, s_j=v2, s_b=1, coef=coef)
 
 
-def _ovov_swap13(t, coef):
+def _ovov_swap13(t, coef, i_lo=0):
     """(i,a,j,b) -> ovov[i,b,j,a]  (swapaxes(1,3), explicit_equations_partial.py:93)"""
-    o, v, o2, v2 = t.shape
-    assert o == o2 and v == v2
-    return nv.term(t, 0, s_i=v * o * v, s_b=o * v, s_j=v, s_a=1, coef=coef)
+    _, v, o, v2 = t.shape
+    assert v == v2
+    s_i = v * o * v
+    return nv.term(t, -i_lo * s_i, s_i=s_i, s_b=o * v, s_j=v, s_a=1, coef=coef)
 
 
-def _oovv_swap12(t, coef):
+def _oovv_swap12(t, coef, i_lo=0):
     """(i,a,j,b) -> oovv[i,j,a,b]  (swapaxes(1,2), explicit_equations_partial.py:35)"""
-    o, o2, v, v2 = t.shape
-    assert o == o2 and v == v2
-    return nv.term(t, 0, s_i=o * v * v, s_j=v * v, s_a=v, s_b=1, coef=coef)
+    _, o, v, v2 = t.shape
+    assert v == v2
+    s_i = o * v * v
+    return nv.term(t, -i_lo * s_i, s_i=s_i, s_j=v * v, s_a=v, s_b=1, coef=coef)
 
 
 def _full(t, pattern, ox, oy, coef):
@@ -55,9 +63,9 @@ def absent():
     return nv.term(None)
 
 
-def partial_terms(kind, ovov, oovv):
+def partial_terms(kind, ovov, oovv, i_lo=0):
     """(p1, p2, q1, q2) for kind in {'singlet','triplet','ss','os'}; tensors may be None when the
-    corresponding output is not requested."""
+    corresponding output is not requested.  ``i_lo``: first occupied row held by row-sharded tensors."""
     a = absent()
     if kind == "singlet":
         c = 2.0
@@ -68,12 +76,12 @@ def partial_terms(kind, ovov, oovv):
     else:
         raise ValueError(kind)
     if kind == "os":
-        p1 = _ovov_direct(ovov, 1.0) if ovov is not None else a
-        return p1, absent(), (_ovov_direct(ovov, 1.0) if ovov is not None else a), absent()
-    p1 = _ovov_direct(ovov, c) if (ovov is not None and c != 0.0) else a
-    p2 = _oovv_swap12(oovv, 1.0) if oovv is not None else absent()
-    q1 = _ovov_direct(ovov, c) if (ovov is not None and c != 0.0) else absent()
-    q2 = _ovov_swap13(ovov, 1.0) if ovov is not None else absent()
+        p1 = _ovov_direct(ovov, 1.0, i_lo) if ovov is not None else a
+        return p1, absent(), (_ovov_direct(ovov, 1.0, i_lo) if ovov is not None else a), absent()
+    p1 = _ovov_direct(ovov, c, i_lo) if (ovov is not None and c != 0.0) else a
+    p2 = _oovv_swap12(oovv, 1.0, i_lo) if oovv is not None else absent()
+    q1 = _ovov_direct(ovov, c, i_lo) if (ovov is not None and c != 0.0) else absent()
+    q2 = _ovov_swap13(ovov, 1.0, i_lo) if ovov is not None else absent()
     return p1, p2, q1, q2
 
 
@@ -104,23 +112,27 @@ def split_energies(E_MO, nocc):
 
 
 def run(no_x, nv_x, no_y, nv_y, terms, eps, want, out_mode=0, out0=None, out1=None, ld=None,
-        off0=0, off1=0):
+        off0=0, off1=0, i_lo=0, i_hi=None):
     """Launch the assembly kernel.  ``want`` in {'P','Q','PQ'} selects which outputs exist when
-    out0/out1 are not supplied.  Returns (out0, out1) device tensors (None where not produced)."""
+    out0/out1 are not supplied.  Returns (out0, out1) device tensors (None where not produced).
+    ``[i_lo, i_hi)``: only these occupied rows are produced; supplied outputs then hold the row block
+    alone ((i_hi - i_lo) * nv_x rows), as do the row-sharded input tensors behind ``terms``."""
     p1, p2, q1, q2 = terms
-    novx, novy = no_x * nv_x, no_y * nv_y
+    novy = no_y * nv_y
+    i_hi = no_x if i_hi is None else i_hi
     if out0 is None and out1 is None:
         if "P" in want:
-            out0 = nv.empty(novx, novy)
+            out0 = nv.empty((i_hi - i_lo) * nv_x, novy)
         if "Q" in want:
-            out1 = nv.empty(novx, novy)
+            out1 = nv.empty((i_hi - i_lo) * nv_x, novy)
         ld = novy
     if "P" not in want and out_mode == 0:
         p1, p2 = absent(), absent()
     if "Q" not in want and out_mode == 0:
         q1, q2 = absent(), absent()
     eo, ev = eps if eps is not None else (None, None)
-    if novx * novy > 0:
+    if (i_hi - i_lo) * nv_x * novy > 0:
+        shift = -i_lo * nv_x * (ld if ld is not None else novy)   # outputs are addressed with global i
         nv.assemble(no_x, nv_x, no_y, nv_y, p1, p2, q1, q2, eo, ev, out_mode, out0, out1,
-                    ld0=ld, ld1=ld, out0_off=off0, out1_off=off1)
+                    ld0=ld, ld1=ld, out0_off=off0 + shift, out1_off=off1 + shift, i_lo=i_lo, i_hi=i_hi)
     return out0, out1

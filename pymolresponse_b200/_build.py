@@ -14,7 +14,7 @@ CSRC = PKG / "csrc"
 LIBDIR = PKG / "_lib"
 LIB = LIBDIR / "libpmr_b200.so"
 
-SOURCES = ["pmr_gemm.cu", "pmr_factor.cu", "pmr_assemble.cu", "pmr_ao2mo.cu", "pmr_misc.cu", "pmr_eri.cu", "pmr_eig.cu"]
+SOURCES = ["pmr_gemm.cu", "pmr_factor.cu", "pmr_assemble.cu", "pmr_ao2mo.cu", "pmr_misc.cu", "pmr_eri.cu", "pmr_eig.cu", "pmr_iter.cu"]
 
 
 def nvcc_path() -> str:

@@ -135,6 +135,14 @@ SYMBOLS = {
     "pmr_axpby": (C.c_int, [c_ll, c_ll, C.c_double, c_dp, c_ll, C.c_double, c_dp, c_ll, c_dp]),
     "pmr_uncoupled_divide": (C.c_int, [c_dp, C.c_int, c_ll, c_dp, C.c_double, c_dp, c_dp]),
     "pmr_jk_contract": (C.c_int, [c_dp, C.c_int, c_dp, C.c_int, c_dp, c_dp, c_dp]),
+    "pmr_iter_permute_ov_rows": (C.c_int, [c_dp, C.c_int, C.c_int, C.c_int, c_dp, c_dp]),
+    "pmr_iter_sigma_combine": (C.c_int, [c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_ll, c_ll, C.c_int,
+                                         C.c_double, C.c_double, C.c_double, C.c_double, c_dp, c_dp]),
+    "pmr_iter_precond": (C.c_int, [c_dp, c_dp, c_dp, c_ll, C.c_int, c_dp, c_dp]),
+    "pmr_iter_coldot_workspace": (c_ll, [c_ll, C.c_int]),
+    "pmr_iter_coldot": (C.c_int, [c_dp, c_dp, c_ll, C.c_int, c_dp, c_dp, c_dp]),
+    "pmr_iter_update_zr": (C.c_int, [c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_ll, C.c_int, c_dp]),
+    "pmr_iter_update_d": (C.c_int, [c_dp, c_dp, c_dp, c_dp, c_ll, C.c_int, c_dp]),
 }
 
 

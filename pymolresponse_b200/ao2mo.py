@@ -68,6 +68,10 @@ def partial_blocks_dev(I_slab, nu_lo, Cbra, nocc_bra, kets, want_oovv, nu_block=
     (ij|ab) chain stops after its two occupied quarters, the half-transformed (ij|la si) is
     reduce-scattered over i, every rank finishes the two virtual quarters for its own i only and the
     rows are all-gathered -- the o^2 n^2 (v + v^2/n) tail flops are not repeated on every rank.
+
+    ``reduce="scatter"`` (row-block-sharded Hessian): every block comes back as this rank's occupied
+    rows ``distributed.shard_range(o1, rank, world)`` only -- (ia|jb) is reduce-scattered over i
+    (half the traffic of the all-reduce) and the all-gather of (ij|ab) is dropped.
     """
     from pymolresponse_b200 import _engine as eng
     from pymolresponse_b200 import distributed as pd
@@ -91,6 +95,7 @@ def partial_blocks_dev(I_slab, nu_lo, Cbra, nocc_bra, kets, want_oovv, nu_block=
         kd[k].ldc2 = int(Ck.stride(0))
         kd[k].o2, kd[k].v2 = o2, v2
         kd[k].ovov = nv.ptr(out)
+    scatter = (reduce == "scatter") and pd.rank_world()[1] > 1
     split_tail = bool(reduce and want_oovv and pd.rank_world()[1] > 1)
     if split_tail:
         oovv = nv.zeros(o1, o1, n, n)       # receives the half-transformed (i j|la si)
@@ -106,8 +111,12 @@ def partial_blocks_dev(I_slab, nu_lo, Cbra, nocc_bra, kets, want_oovv, nu_block=
     del ws
     clock.mark("transform")
     if reduce:
-        pd.allreduce_blocks(outs)
-        clock.mark("allreduce_ovov")
+        if scatter:
+            outs = [pd.reduce_scatter_rows(t, o1) for t in outs]
+            clock.mark("reduce_scatter_ovov")
+        else:
+            pd.allreduce_blocks(outs)
+            clock.mark("allreduce_ovov")
         if split_tail:
             Y_loc = pd.reduce_scatter_rows(oovv, o1)            # (rows, o1, n, n), summed over ranks
             clock.mark("reduce_scatter_oovv")
@@ -120,8 +129,11 @@ def partial_blocks_dev(I_slab, nu_lo, Cbra, nocc_bra, kets, want_oovv, nu_block=
                 nv.check(L.pmr_ao2mo_oovv_tail(nv.ptr(Y_loc), n, nv.ptr(Cbra, o1), ldc1, rows, o1, v1,
                                                nv.ptr(loc), 0, nv.ptr(tws), tw, nv.stream_ptr()))
             clock.mark("oovv_tail")
-            oovv = pd.allgather_rows(loc, o1)
-            clock.mark("allgather_oovv")
+            if scatter:
+                oovv = loc
+            else:
+                oovv = pd.allgather_rows(loc, o1)
+                clock.mark("allgather_oovv")
         elif want_oovv:
             pd.allreduce_blocks([oovv])
     clock.finish()
@@ -173,7 +185,12 @@ class AO2MO:
         self.device_results = device_results
         self.nu_range = nu_range
         self.nu_block = nu_block
-        self.reduce = reduce  # complete the blocks over torch.distributed ranks (nu-sharded I)
+        # complete the blocks over torch.distributed ranks (nu-sharded I): True = every rank gets the
+        # whole blocks, "scatter" = every rank keeps its occupied rows only (see ``row_ranges``)
+        assert reduce in (False, True, "scatter")
+        self.reduce = reduce
+        #: per spin, the occupied rows [lo, hi) the blocks of ``tei_mo`` hold (None: all rows)
+        self.row_ranges = None
         assert ao_symmetry in ("s1", "s8")
         self.ao_symmetry = ao_symmetry
         self.df_factor = df_factor
@@ -258,6 +275,7 @@ class AO2MO:
         Ca = self._C_dev(0)
         (ovov,), oovv = partial_blocks_dev(I, lo, Ca, self.nocc_alph, [(Ca, self.nocc_alph)], True,
                                            self.nu_block, self.reduce)
+        self._set_row_ranges()
         self.tei_mo = self._out((ovov, oovv))
 
     def perform_uhf_full(self) -> None:
@@ -297,7 +315,18 @@ class AO2MO:
                                                   self.nu_block, self.reduce)
         (bbaa, bbbb), oovv_b = partial_blocks_dev(I, lo, Cb, nb, [(Ca, na), (Cb, nb)], True,
                                                   self.nu_block, self.reduce)
+        self._set_row_ranges()
         self.tei_mo = self._out((aaaa, aabb, bbaa, bbbb, oovv_a, oovv_b))
+
+    def _set_row_ranges(self):
+        from pymolresponse_b200 import distributed as pd
+
+        rank, world = pd.rank_world()
+        if self.reduce == "scatter" and world > 1:
+            self.row_ranges = (pd.shard_range(self.nocc_alph, rank, world),
+                               pd.shard_range(self.nocc_beta, rank, world))
+        else:
+            self.row_ranges = None
 
 
 def flops_rhf_partial_df(n: int, o: int, naux: int) -> float:

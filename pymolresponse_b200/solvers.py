@@ -69,6 +69,9 @@ class Solver(ABC):
         self.device_results = False
         # "s8": form_tei_mo may assume the 8-fold symmetry of the AO ERI tensor (see ao2mo.py)
         self.ao_symmetry = "s1"
+        # row-block-sharded Hessian: ``tei_mo`` holds only this rank's occupied rows of every block
+        # (AO2MO(reduce="scatter").row_ranges): (lo, hi) for RHF, ((lo, hi), (lo, hi)) for UHF
+        self.tei_mo_rows = None
 
     # ---------------------------------------------------------------- MO integrals
     explicit_hessian = None
@@ -200,6 +203,9 @@ class _HessianBlocks:
         tei = self._tei_dev()
         kind = _kind(spin, False)
         eps = bl.split_energies(self.moenergies[0], nocc)
+        rows = self._row_ranges()
+        if rows is not None:
+            return self._assemble_rhf_rows(hamiltonian, kind, eps, rows[0], want_ab, want_mk)
         if self.tei_mo_type == AO2MOTransformationType.full:
             assert len(tei) == 1
             terms = bl.full_terms(kind, tei[0], nocc, nocc)
@@ -222,6 +228,59 @@ class _HessianBlocks:
                 A, B = bl.run(nocc, nvirt, nocc, nvirt, terms, eps, "PQ")
         return M, K, A, B
 
+    def _row_ranges(self):
+        from pymolresponse_b200 import distributed as pd
+
+        rows = getattr(self, "tei_mo_rows", None)
+        if rows is None or pd.rank_world()[1] == 1:
+            return None
+        if isinstance(rows[0], int):
+            rows = (tuple(rows), tuple(rows))
+        return rows
+
+    @staticmethod
+    def _gather_row_blocks(loc, ri, nv_x, ncols, no_total):
+        """Row block (ri * nv_x, ncols) of every rank -> the whole (no_total * nv_x, ncols) matrix."""
+        from pymolresponse_b200 import distributed as pd
+
+        return pd.allgather_rows(loc.view(ri, nv_x * ncols), no_total).view(no_total * nv_x, ncols)
+
+    def _assemble_rhf_rows(self, hamiltonian, kind, eps, rows, want_ab, want_mk):
+        """Row-block-sharded assembly (north_star: 'the ov Hessian over row blocks'): this rank forms
+        the rows of its occupied indices [i_lo, i_hi) from its rows of (ia|jb) and (ij|ab) -- both
+        index swaps of the A/B formulas stay inside a row block -- and the row blocks are all-gathered
+        because every rank factorises its own frequencies."""
+        nocc, nvirt, _, _ = self.occupations
+        nov = nocc * nvirt
+        i_lo, i_hi = rows
+        ri = i_hi - i_lo
+        assert self.tei_mo_type == AO2MOTransformationType.partial, "row sharding: partial blocks only"
+        tei = self._tei_dev()
+        assert tuple(tei[0].shape) == (ri, nvirt, nocc, nvirt) and tuple(tei[1].shape) == (ri, nocc, nvirt, nvirt)
+        terms = bl.partial_terms(kind, tei[0], tei[1], i_lo)
+        tda = hamiltonian == Hamiltonian.TDA
+        if tda:
+            terms = (terms[0], terms[1], bl.absent(), bl.absent())
+        A = B = M = K = None
+
+        def gather(t):
+            return self._gather_row_blocks(t, ri, nvirt, nov, nocc)
+
+        if tda:
+            A_loc, _ = bl.run(nocc, nvirt, nocc, nvirt, terms, eps, "P", i_lo=i_lo, i_hi=i_hi)
+            A = gather(A_loc)
+            M = K = A
+        else:
+            if want_mk:
+                M_loc, K_loc = nv.empty(ri * nvirt, nov), nv.empty(ri * nvirt, nov)
+                bl.run(nocc, nvirt, nocc, nvirt, terms, eps, "PQ", out_mode=1, out0=M_loc, out1=K_loc,
+                       ld=nov, i_lo=i_lo, i_hi=i_hi)
+                M, K = gather(M_loc), gather(K_loc)
+            if want_ab:
+                A_loc, B_loc = bl.run(nocc, nvirt, nocc, nvirt, terms, eps, "PQ", i_lo=i_lo, i_hi=i_hi)
+                A, B = gather(A_loc), gather(B_loc)
+        return M, K, A, B
+
     def _assemble_uhf(self, hamiltonian, spin, want_ab, want_mk=True):
         """Joint (nov_a + nov_b) matrices [[ss_a, os_a],[os_b, ss_b]] -> (M, K, A, B)."""
         na, va, nb, vb = self.occupations
@@ -235,7 +294,7 @@ class _HessianBlocks:
         eps_a = bl.split_energies(self.moenergies[0], na)
         eps_b = bl.split_energies(self.moenergies[1], nb)
 
-        def terms(block):
+        def terms(block, i_lo=0):
             if full:
                 aaaa, aabb, bbaa, bbbb = tei
                 t = {"aa": (kind, aaaa, na, na), "bb": (kind, bbbb, nb, nb),
@@ -245,26 +304,45 @@ class _HessianBlocks:
                 ovov_aaaa, ovov_aabb, ovov_bbaa, ovov_bbbb, oovv_aaaa, oovv_bbbb = tei
                 t = {"aa": (kind, ovov_aaaa, oovv_aaaa), "bb": (kind, ovov_bbbb, oovv_bbbb),
                      "ab": ("os", ovov_aabb, None), "ba": ("os", ovov_bbaa, None)}[block]
-                out = bl.partial_terms(*t)
+                out = bl.partial_terms(*t, i_lo)
             if tda:
                 out = (out[0], out[1], bl.absent(), bl.absent())
             return out
+
+        rows = self._row_ranges()
+        if rows is not None:
+            assert not full, "row sharding: partial blocks only"
+            (ia_lo, ia_hi), (ib_lo, ib_hi) = rows
+        else:
+            (ia_lo, ia_hi), (ib_lo, ib_hi) = (0, na), (0, nb)
 
         def fill(out0, out1, mode):
             # offsets of the four blocks inside an (nt x nt) matrix
             blocks = (("aa", na, va, na, va, eps_a, 0), ("bb", nb, vb, nb, vb, eps_b, nova * nt + nova),
                       ("ab", na, va, nb, vb, None, nova), ("ba", nb, vb, na, va, None, nova * nt))
             for name, ox, vx, oy, vy, eps, off in blocks:
+                i_lo, i_hi = (ia_lo, ia_hi) if name[0] == "a" else (ib_lo, ib_hi)
                 if name in ("ab", "ba") and spin == Spin.triplet:
                     # no Coulomb term, hence no opposite-spin coupling (solvers.py:272-285)
-                    rows, cols = ox * vx, oy * vy
+                    cols = oy * vy
                     r0, c0 = divmod(off, nt)
                     for o in (out0, out1):
                         if o is not None:
-                            o[r0:r0 + rows, c0:c0 + cols].zero_()
+                            o[r0 + i_lo * vx:r0 + i_hi * vx, c0:c0 + cols].zero_()
                     continue
-                bl.run(ox, vx, oy, vy, terms(name), eps, "PQ", out_mode=mode, out0=out0, out1=out1,
-                       ld=nt, off0=off, off1=off)
+                # a sharded rank fills only its occupied rows [i_lo, i_hi) of the (nt x nt) matrix
+                # (global row addressing, so the offsets are those of the full matrix)
+                bl.run(ox, vx, oy, vy, terms(name, i_lo if rows is not None else 0), eps, "PQ",
+                       out_mode=mode, out0=out0, out1=out1, ld=nt,
+                       off0=off + i_lo * vx * nt, off1=off + i_lo * vx * nt, i_lo=i_lo, i_hi=i_hi)
+            if rows is not None:
+                # exchange the row blocks: alpha rows and beta rows of every output
+                for o in (out0, out1):
+                    if o is None:
+                        continue
+                    for r0, vx, ox, (lo, hi) in ((0, va, na, (ia_lo, ia_hi)), (nova, vb, nb, (ib_lo, ib_hi))):
+                        loc = o[r0 + lo * vx:r0 + hi * vx].contiguous()
+                        o[r0:r0 + ox * vx].copy_(self._gather_row_blocks(loc, hi - lo, vx, nt, ox))
 
         A = B = M = K = None
         if tda:
@@ -645,26 +723,193 @@ class ExactInvCholesky(ExactLineqSolver):
 
 
 class IterativeLinEqSolver(LineqSolver):
-    """Fixed-point CPHF with J/K builds (reference solvers.py:558-660), RHF only.
+    """Iterative CPHF (reference solvers.py:558-660), RHF only.
 
-    ``jk_generator`` is any :class:`pymolresponse_b200.integrals.JK`; with the GPU ``JKDense``
-    both J/K builds of every operator component are ONE pass of ``pmr_jk_contract`` over the AO
-    ERI tensor per iteration (the reference makes 2 * ncomp separate JK calls, solvers.py:618-619).
+    Two methods:
+
+    * ``method="fixed_point"`` (default when a ``jk_generator`` is given): the reference's loop,
+      AO-direct with J/K builds.  With the GPU ``JKDense`` both J/K builds of every operator
+      component are ONE pass of ``pmr_jk_contract`` over the AO ERI tensor per iteration (the
+      reference makes 2 * ncomp separate JK calls, solvers.py:618-619).  Same initial guess, same
+      update, same signed convergence measure, same iteration counts.
+    * ``method="cg"`` (default when ``jk_generator`` is None): matrix-free block preconditioned
+      conjugate gradients on ``[[K,-w],[-w,M]] [p;m] = rhs`` with sigma applied from the MO blocks
+      (ia|jb), (ij|ab) by DMMA GEMMs -- no orbital Hessian, no AO tensor in the loop; every operator
+      component and frequency is a column of ONE block iteration.  The MO blocks may be sharded over
+      ranks by rows (``tei_mo_rows``): each rank applies its rows of sigma, the row blocks are
+      all-gathered once per iteration.  Response vectors follow the reference iterative solver's
+      convention (its X/Y halves correspond to the exact solver's at -w), so
+      either method is a drop-in for the other.
     """
 
-    def __init__(self, mocoeffs, moenergies, occupations, jk_generator: JK, *, maxiter: int = 40,
-                 conv: float = 1.0e-9) -> None:
+    def __init__(self, mocoeffs, moenergies, occupations, jk_generator: JK | None = None, *,
+                 maxiter: int = 40, conv: float = 1.0e-9, method: str | None = None) -> None:
         super().__init__(mocoeffs, moenergies, occupations)
         self.jk_generator = jk_generator
         self.maxiter = maxiter
         self.conv = conv
         self.iterations = []
+        if method is None:
+            method = "fixed_point" if jk_generator is not None else "cg"
+        assert method in ("fixed_point", "cg")
+        self.method = method
+        #: (i_lo, i_hi): ``tei_mo`` holds only these occupied rows of (ia|jb) and (ij|ab)
+        self.tei_mo_rows = None
+        self.residuals = []
 
     def run(self, hamiltonian: Hamiltonian, spin: Spin, program: Program | None,
             program_obj: Any) -> None:
         assert self.frequencies
+        if self.method == "cg":
+            if self.is_uhf:
+                raise RuntimeError
+            if not self.tei_mo:
+                if program is None:
+                    msg = "Program must be specified for computing 2-electron integrals in MO basis"
+                    raise RuntimeError(msg)
+                self.form_tei_mo(program, program_obj, AO2MOTransformationType.partial)
+            self._run_cg(hamiltonian, spin, [float(w) for w in self.frequencies])
+            return
         for frequency in self.frequencies:
             self._run(hamiltonian, spin, frequency, self.maxiter, self.conv)
+
+    # ------------------------------------------------------------------ matrix-free block PCG
+    def _run_cg(self, hamiltonian: Hamiltonian, spin: Spin, freqs) -> None:
+        import ctypes as C
+
+        from pymolresponse_b200 import distributed as pd
+
+        assert self.tei_mo_type == AO2MOTransformationType.partial and len(self.tei_mo) == 2, (
+            "the matrix-free path works from the partial blocks (ia|jb), (ij|ab)")
+        torch = nv.torch_mod()
+        L = nv.lib()
+        nocc, nvirt, _, _ = self.occupations
+        nov = nocc * nvirt
+        ovov, oovv = (nv.to_dev(t) for t in self.tei_mo)
+        i_lo, i_hi = self.tei_mo_rows if self.tei_mo_rows is not None else (0, nocc)
+        ri = i_hi - i_lo
+        assert tuple(ovov.shape) == (ri, nvirt, nocc, nvirt) and tuple(oovv.shape) == (ri, nocc, nvirt, nvirt)
+        sharded = self.tei_mo_rows is not None and pd.rank_world()[1] > 1
+        if sharded:
+            assert (i_lo, i_hi) == pd.shard_range(nocc, *pd.rank_world()), (
+                "row-sharded MO blocks must follow distributed.shard_range over the occupied index")
+        else:
+            assert (i_lo, i_hi) == (0, nocc), "a single rank needs all rows of the MO blocks"
+        ops = list(self.operators)
+        if not ops or nov == 0:
+            return
+        # columns: frequency-major, then operator, then component; reference-iterative convention:
+        # its vectors at w are the exact solver's at -w (times -1 for imaginary operators)
+        g_cols, signs, w_cols, flips = [], [], [], []
+        for w in freqs:
+            for op in ops:
+                g = op.supervector_dev("alph")[:, :nov]
+                s_ = +1.0 if op.is_imaginary else -1.0
+                for c in range(int(g.shape[0])):
+                    g_cols.append(g[c])
+                    signs.append(s_)
+                    w_cols.append(-w)
+                    flips.append(-1.0 if op.is_imaginary else 1.0)
+        k = len(g_cols)
+        Gm = torch.stack(g_cols, dim=1).contiguous()                   # (nov, k)
+        sg = torch.tensor(signs, dtype=torch.float64, device=Gm.device)
+        wdev = torch.tensor(w_cols, dtype=torch.float64, device=Gm.device)
+        b = torch.cat(((1.0 + sg)[None, :] * Gm, (1.0 - sg)[None, :] * Gm), dim=1).contiguous()
+        eo, ev = bl.split_energies(self.moenergies[0], nocc)
+        ediff = nv.empty(nov)
+        nv.check(L.pmr_energy_differences(nv.ptr(eo), nocc, nv.ptr(ev), nvirt, nv.ptr(ediff),
+                                          nv.stream_ptr()))
+        c = {Spin.singlet: 2.0, Spin.triplet: 0.0}[spin]
+        if hamiltonian == Hamiltonian.TDA:
+            cK, sK, cM, sM = c, 0.0, c, 0.0
+        else:
+            cK, sK, cM, sM = 0.0, 1.0, 2.0 * c, -1.0
+        need_U, need_W = (cK != 0.0 or cM != 0.0), (sK != 0.0 or sM != 0.0)
+        k2 = 2 * k
+        rows_loc = ri * nvirt
+        U = nv.zeros(rows_loc, k2) if need_U else None
+        V = nv.zeros(rows_loc, k2)
+        W = nv.zeros(rows_loc, k2) if need_W else None
+        Zp = nv.empty(nov, k2) if need_W else None
+        q_loc = nv.empty(rows_loc, k2)
+        null = C.c_void_p(0)
+
+        def sigma(Z):
+            """H Z for the (nov, 2k) block Z."""
+            if rows_loc > 0:
+                if need_U:   # (ia|jb) . Z : one GEMM, A k-contiguous
+                    nv.dgemm(rows_loc, k2, nov, 1.0, ovov, 0, nov, 1, Z, 0, k2, 1, 0.0, U, 0, k2, 1)
+                if need_W:   # sum_{b,j} (ib|ja) Z[j,b] : per i, A^T with K index (b,j), stride nvirt
+                    nv.check(L.pmr_iter_permute_ov_rows(nv.ptr(Z), nocc, nvirt, k2, nv.ptr(Zp),
+                                                        nv.stream_ptr()))
+                    nv.dgemm(nvirt, k2, nov, 1.0, ovov, 0, 1, nvirt, Zp, 0, k2, 1, 0.0, W, 0, k2, 1,
+                             batch1=ri, a_b=(nov * nvirt, 0), b_b=(0, 0), c_b=(nvirt * k2, 0))
+                # sum_{j,b} (ij|ab) Z[j,b] : per (i, j) a (v x v) block, accumulated over j
+                for j in range(nocc):
+                    nv.dgemm(nvirt, k2, nvirt, 1.0, oovv, j * nvirt * nvirt, nvirt, 1,
+                             Z, j * nvirt * k2, k2, 1, 0.0 if j == 0 else 1.0, V, 0, k2, 1,
+                             batch1=ri, a_b=(nocc * nvirt * nvirt, 0), b_b=(0, 0), c_b=(nvirt * k2, 0))
+                nv.check(L.pmr_iter_sigma_combine(
+                    nv.ptr(U) if need_U else null, nv.ptr(V), nv.ptr(W) if need_W else null, nv.ptr(Z),
+                    nv.ptr(ediff), nv.ptr(wdev), i_lo * nvirt, rows_loc, k, cK, sK, cM, sM,
+                    nv.ptr(q_loc), nv.stream_ptr()))
+            if sharded:
+                return pd.allgather_rows(q_loc.view(ri, nvirt * k2), nocc).view(nov, k2)
+            return q_loc
+
+        work = nv.empty(int(L.pmr_iter_coldot_workspace(nov, k)))
+
+        def dots(X, Y):
+            out = nv.empty(k)
+            nv.check(L.pmr_iter_coldot(nv.ptr(X), nv.ptr(Y), nov, k, nv.ptr(out), nv.ptr(work),
+                                       nv.stream_ptr()))
+            return out
+
+        def precond(R):
+            Y = nv.empty(nov, k2)
+            nv.check(L.pmr_iter_precond(nv.ptr(R), nv.ptr(ediff), nv.ptr(wdev), nov, k, nv.ptr(Y),
+                                        nv.stream_ptr()))
+            return Y
+
+        z = precond(b)                               # uncoupled guess (solvers.py:606-611)
+        r = eng.axpby(-1.0, sigma(z), 1.0, b.clone())
+        y = precond(r)
+        d = y.clone()
+        rho = dots(r, y)
+        bnorm2 = dots(b, b).clamp_min(1e-300)
+        converged, its, rel = False, 0, None
+        # enough sweeps for machine precision below the first pole; ``maxiter`` keeps its meaning
+        for it in range(1, max(self.maxiter, 1) + 1):
+            its = it
+            q = sigma(d)
+            dq = dots(d, q)
+            nv.check(L.pmr_iter_update_zr(nv.ptr(z), nv.ptr(r), nv.ptr(d), nv.ptr(q), nv.ptr(rho),
+                                          nv.ptr(dq), nov, k, nv.stream_ptr()))
+            rel = float(torch.sqrt((dots(r, r) / bnorm2).max()).item())   # one host read per sweep
+            if rel * rel < self.conv:
+                converged = True
+                break
+            y = precond(r)
+            rho_new = dots(r, y)
+            nv.check(L.pmr_iter_update_d(nv.ptr(d), nv.ptr(y), nv.ptr(rho_new), nv.ptr(rho), nov, k,
+                                         nv.stream_ptr()))
+            rho = rho_new
+        self.iterations.append(its if converged else -1)
+        self.residuals.append(rel)
+        if not converged:
+            return      # the reference silently appends nothing (solvers.py:638-660)
+        flip = torch.tensor(flips, dtype=torch.float64, device=z.device)
+        p_rows = (z[:, :k] * flip[None, :]).t().contiguous()      # (k, nov)
+        m_rows = (z[:, k:] * flip[None, :]).t().contiguous()
+        xy = nv.empty(k, 2 * nov)
+        nv.check(L.pmr_pm_to_xy(nv.ptr(p_rows), nv.ptr(m_rows), k, nov, nov, nov, nv.ptr(xy), 2 * nov,
+                                nv.stream_ptr()))
+        col = 0
+        for _w in freqs:
+            for op in ops:
+                nc = int(op.supervector_dev("alph").shape[0])
+                self._append_rspvecs(op, "alph", xy[col:col + nc].contiguous())
+                col += nc
 
     def _run(self, hamiltonian: Hamiltonian, spin: Spin, omega: float, maxiter: int,
              conv: float) -> None:

@@ -124,6 +124,70 @@ uref = orc.run_cphf(ucase["C"], ucase["E"], ucase["occupations"], utei_ref, "par
                     [{"ao_integrals": Ou, "is_imaginary": False}], [0.0, 0.12])
 for f in range(2):
     assert np.abs(udriver.results[f] - uref["results"][f]).max() <= 1e-9
+# ---- row-block-sharded Hessian: AO2MO(reduce="scatter") keeps only this rank's occupied rows of
+# every block; the solver assembles its rows of M / K and all-gathers them (RHF and UHF); the
+# matrix-free PCG solver applies sigma row block by row block with one all-gather per iteration
+a2 = AO2MO(case["C"], case["occupations"], I=np.ascontiguousarray(case["I"][:, lo:hi]),
+           nu_range=(lo, hi), device_results=True, reduce="scatter")
+a2.perform_rhf_partial()
+(ilo, ihi), _ = a2.row_ranges
+assert (ilo, ihi) == pd.shard_range(o, rank, world)
+assert np.abs(a2.tei_mo[0].cpu().numpy() - tei_ref[0][ilo:ihi]).max() <= 1e-12 * np.abs(tei_ref[0]).max()
+assert np.abs(a2.tei_mo[1].cpu().numpy() - tei_ref[1][ilo:ihi]).max() <= 1e-12 * np.abs(tei_ref[1]).max()
+freqs = [0.0, 0.1, 0.2]
+spec = [{"ao_integrals": Or, "is_imaginary": False}, {"ao_integrals": Oi, "is_imaginary": True}]
+ref = orc.run_cphf(case["C"], case["E"], case["occupations"], tei_ref, "partial", spec, freqs)
+neg = orc.run_cphf(case["C"], case["E"], case["occupations"], tei_ref, "partial", spec, [-w for w in freqs])
+solver = solvers.ExactInv(case["C"], case["E"], case["occupations"])
+solver.distribute_frequencies = True
+solver.tei_mo = a2.tei_mo
+solver.tei_mo_rows = a2.row_ranges[0]
+driver = cphf.CPHF(solver)
+ops = [operators.Operator(label="dipole", is_imaginary=False, ao_integrals=Or),
+       operators.Operator(label="angmom", is_imaginary=True, ao_integrals=Oi)]
+for op in ops:
+    driver.add_operator(op)
+driver.set_frequencies(freqs)
+driver.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet, program=None, program_obj=None)
+A_ref, B_ref = orc.rhf_ab(case["E"], tei_ref, "partial", o, "rpa", "singlet")
+assert np.abs(solver._system.M.cpu().numpy() - (A_ref - B_ref)).max() <= 1e-12 * np.abs(A_ref).max()
+assert np.abs(solver._system.K.cpu().numpy() - (A_ref + B_ref)).max() <= 1e-12 * np.abs(A_ref).max()
+for f in range(3):
+    assert np.abs(driver.results[f] - ref["results"][f]).max() <= 1e-9
+it = solvers.IterativeLinEqSolver(case["C"], case["E"], case["occupations"], maxiter=80, conv=1e-26)
+it.tei_mo = a2.tei_mo
+it.tei_mo_rows = a2.row_ranges[0]
+idrv = cphf.CPHF(it)
+iops = [operators.Operator(label="dipole", is_imaginary=False, ao_integrals=Or),
+        operators.Operator(label="angmom", is_imaginary=True, ao_integrals=Oi)]
+for op in iops:
+    idrv.add_operator(op)
+idrv.set_frequencies(freqs)
+idrv.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet, program=None, program_obj=None)
+assert it.iterations[-1] > 0, it.residuals
+for f in range(3):
+    assert np.abs(iops[0].rspvecs_alph[f] - neg["rspvecs_alph"][0][f]).max() <= 1e-10
+    assert np.abs(iops[1].rspvecs_alph[f] + neg["rspvecs_alph"][1][f]).max() <= 1e-10
+    assert np.abs(idrv.results[f][:3, :3] - ref["results"][f][:3, :3]).max() <= 1e-8
+# UHF, row sharded (ragged: 4 alpha / 3 beta occupied over 2 ranks)
+ua2 = AO2MO(ucase["C"], ucase["occupations"], I=np.ascontiguousarray(ucase["I"][:, ulo:uhi]),
+            nu_range=(ulo, uhi), device_results=True, reduce="scatter")
+ua2.perform_uhf_partial()
+(al, ah), (bl_, bh) = ua2.row_ranges
+for k, (r0, r1) in enumerate(((al, ah), (al, ah), (bl_, bh), (bl_, bh), (al, ah), (bl_, bh))):
+    want = utei_ref[k][r0:r1]
+    assert tuple(ua2.tei_mo[k].shape) == want.shape, k
+    assert np.abs(ua2.tei_mo[k].cpu().numpy() - want).max() <= 1e-12 * np.abs(utei_ref[k]).max(), k
+us2 = solvers.ExactInv(ucase["C"], ucase["E"], ucase["occupations"])
+us2.distribute_frequencies = True
+us2.tei_mo = ua2.tei_mo
+us2.tei_mo_rows = ua2.row_ranges
+ud2 = cphf.CPHF(us2)
+ud2.add_operator(operators.Operator(label="dipole", is_imaginary=False, ao_integrals=Ou))
+ud2.set_frequencies([0.0, 0.12])
+ud2.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet, program=None, program_obj=None)
+for f in range(2):
+    assert np.abs(ud2.results[f] - uref["results"][f]).max() <= 1e-9
 pd.barrier()
 dist.destroy_process_group()
 print("ok", rank)

@@ -980,3 +980,109 @@ def test_cholesky_explicit_inverse_raises_and_uhf_left_blocks(golden_dir):
         left_b = np.linalg.inv(G4[3] - G4[2] @ np.linalg.inv(G4[0]) @ G4[1])
         assert np.abs(su.left_alph - left_a).max() <= 1e-10
         assert np.abs(su.left_beta - left_b).max() <= 1e-10
+
+
+# ------------------------------------------------------------------------- matrix-free block PCG
+def test_iterative_cg_matches_reference_iterative_vectors(golden_dir):
+    """method="cg": same response vectors as the reference's fixed-point IterativeLinEqSolver
+    (golden vectors generated by the unmodified reference, solvers.py:603-637), from the MO blocks."""
+    from pymolresponse_b200 import cphf, operators, solvers, synthetic
+    from pymolresponse_b200.core import Hamiltonian, Spin
+
+    g = np.load(golden_dir / "synthetic_rhf_n10.npz")
+    n, o = int(g["n"]), int(g["nocc"])
+    case = synthetic.rhf_case(n, o, build_eri=False)
+    it = solvers.IterativeLinEqSolver(case["C"], case["E"], case["occupations"], maxiter=60, conv=1e-26)
+    assert it.method == "cg"
+    it.tei_mo = (g["ovov"], g["oovv"])
+    drv = cphf.CPHF(it)
+    op = operators.Operator(label="dipole", is_imaginary=False,
+                            ao_integrals=synthetic.operator_integrals(n, 3, False))
+    drv.add_operator(op)
+    drv.set_frequencies([0.0, 0.05])
+    drv.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet, program=None, program_obj=None)
+    assert it.iterations[-1] > 0
+    np.testing.assert_allclose(np.stack(op.rspvecs_alph), g["iterative_rspvecs"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(np.stack(drv.results), g["iterative_results"], rtol=0, atol=1e-10)
+
+
+@pytest.mark.parametrize("ham,spin", [("rpa", "singlet"), ("rpa", "triplet"), ("tda", "singlet")])
+def test_iterative_cg_vs_exact_and_oracle_iterative(ham, spin):
+    """nbasis = 64 (nov = 448): property tensors of the PCG path against ExactInv on the same MO
+    blocks (<= 1e-8), response vectors against the exact ones at -w (the reference iterative solver's
+    convention), real + imaginary operators, three frequencies in one block iteration, starting from
+    the AO tensor (form_tei_mo)."""
+    from pymolresponse_b200 import cphf, operators, solvers, synthetic
+    from pymolresponse_b200.core import Program
+
+    _, H, S = _enums()
+    n, o = 64, 8
+    nov = o * (n - o)
+    case = synthetic.rhf_case(n, o)
+    Or, Oi = synthetic.operator_integrals(n, 3, False), synthetic.operator_integrals(n, 2, True)
+    freqs = [0.0, 0.2, 0.5]
+    it = solvers.IterativeLinEqSolver(case["C"], case["E"], case["occupations"], maxiter=80, conv=1e-26)
+    drv = cphf.CPHF(it)
+    ops = [operators.Operator(label="dipole", is_imaginary=False, ao_integrals=Or),
+           operators.Operator(label="angmom", is_imaginary=True, ao_integrals=Oi)]
+    for op in ops:
+        drv.add_operator(op)
+    drv.set_frequencies(freqs)
+    drv.run(hamiltonian=H[ham], spin=S[spin], program=Program.Arrays, program_obj=case["I"])
+    assert it.iterations[-1] > 0 and it.residuals[-1] < 1e-12
+    tei = orc.ao2mo_rhf_partial(case["I"], case["C"], o)
+    spec = [{"ao_integrals": Or, "is_imaginary": False}, {"ao_integrals": Oi, "is_imaginary": True}]
+    ref = orc.run_cphf(case["C"], case["E"], case["occupations"], tei, "partial", spec, freqs, ham, spin)
+    neg = orc.run_cphf(case["C"], case["E"], case["occupations"], tei, "partial", spec,
+                       [-w for w in freqs], ham, spin)
+    for f in range(3):
+        # the real-real block is independent of the +-w convention (SURVEY.md A.5 item 7); for an
+        # imaginary operator the reference's iterative algorithm returns the NEGATIVE of the exact
+        # vectors (checked with the oracle port: 2 P.R^T = -results of ExactInv), mirrored here
+        assert np.abs(drv.results[f][:3, :3] - ref["results"][f][:3, :3]).max() <= 1e-8
+        assert np.abs(drv.results[f][3:, 3:] + ref["results"][f][3:, 3:]).max() <= 1e-8
+        assert np.abs(ops[0].rspvecs_alph[f] - neg["rspvecs_alph"][0][f]).max() <= 1e-10
+        assert np.abs(ops[1].rspvecs_alph[f] + neg["rspvecs_alph"][1][f]).max() <= 1e-10
+        assert ops[0].rspvecs_alph[f].shape == (3, 2 * nov, 1)
+    if ham == "rpa" and spin == "singlet":
+        # and the reference's own fixed-point algorithm (oracle port, dense JK) on one operator
+        vec, _ = orc.iterative_rhf(case["C"], case["E"], case["occupations"], Or, 0.2,
+                                   orc.DenseJK(case["I"]), maxiter=200, conv=1e-26)
+        assert np.abs(ops[0].rspvecs_alph[1] - vec).max() <= 1e-10
+
+
+def test_row_block_assembly_matches_full_matrices():
+    """pmr_assemble's [i_lo, i_hi) row range with row-sharded inputs (only the occupied rows a rank
+    owns): every row block is bit-identical to the same rows of the full A / B / M / K, for ragged
+    splits, the fast (even nvirt) and the generic (odd nvirt) kernels, ss / os kinds."""
+    from pymolresponse_b200 import _blocks as bl
+    from pymolresponse_b200 import _native as nv
+
+    r = np.random.default_rng(21)
+    for o, v in ((5, 12), (4, 7)):
+        nov = o * v
+        ovov = r.standard_normal((o, v, o, v))
+        oovv = r.standard_normal((o, o, v, v))
+        E = np.diag(np.sort(r.standard_normal(o + v)))
+        eps = bl.split_energies(E, o)
+        full_A = orc.a_singlet_partial(E, ovov, oovv)
+        full_B = orc.b_singlet_partial(ovov)
+        for lo, hi in ((0, 2), (2, 3), (3, o)):
+            t0, t1 = nv.to_dev(ovov[lo:hi]), nv.to_dev(oovv[lo:hi])
+            terms = bl.partial_terms("singlet", t0, t1, lo)
+            A, B = bl.run(o, v, o, v, terms, eps, "PQ", i_lo=lo, i_hi=hi)
+            assert tuple(A.shape) == ((hi - lo) * v, nov)
+            assert np.array_equal(nv.to_host(A), full_A[lo * v:hi * v])
+            assert np.array_equal(nv.to_host(B), full_B[lo * v:hi * v])
+            M, K = nv.empty((hi - lo) * v, nov), nv.empty((hi - lo) * v, nov)
+            bl.run(o, v, o, v, terms, eps, "PQ", out_mode=1, out0=M, out1=K, ld=nov, i_lo=lo, i_hi=hi)
+            assert np.array_equal(nv.to_host(M), (full_A - full_B)[lo * v:hi * v])
+            assert np.array_equal(nv.to_host(K), (full_A + full_B)[lo * v:hi * v])
+        # rectangular opposite-spin block, rows sharded
+        xxyy = r.standard_normal((o, v, 3, v + 1))
+        full_os = orc.a_singlet_os_partial(xxyy)
+        lo, hi = 1, 4
+        terms = bl.partial_terms("os", nv.to_dev(xxyy[lo:hi]), None, lo)
+        A_os, B_os = bl.run(o, v, 3, v + 1, terms, None, "PQ", i_lo=lo, i_hi=hi)
+        assert np.array_equal(nv.to_host(A_os), full_os[lo * v:hi * v])
+        assert np.array_equal(nv.to_host(B_os), -full_os[lo * v:hi * v])

@@ -50,6 +50,8 @@ struct GemmArgs {
   int a_vec2, b_vec2, c_vec2;
   double* C2;  // optional second (differently strided) copy of the result
   long long c2_sm, c2_sn, c2_b1, c2_b2;
+  int tri_rows;  // tensor-map kernel, LOWER: tile rows that are narrower than the matrix
+  int c_late;    // tensor-map kernel: add the old C tile in the epilogue (L2-prefetched) 
 };
 
 template <int BM, int BN, int WM, int WN, bool AKC, bool BKC, int NSTAGE>
@@ -630,7 +632,7 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
-template <int BM, int BN, int WM, int WN, int NSTAGE, int MINB>
+template <int BM, int BN, int WM, int WN, int NSTAGE, int MINB, bool LOWER>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32 + 32, MINB)
 dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const GemmArgs p) {
@@ -647,10 +649,29 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int tm = blockIdx.x % p.tiles_m, tn = blockIdx.x / p.tiles_m;
+  constexpr bool lower = LOWER;
+  int tm, tn;
+  if (lower) {
+    // only the tiles that touch the lower triangle are launched: row tm has R (tm + 1) of them
+    // (R = BM / BN) until the row is as wide as the matrix; tri_rows rows are of that kind
+    constexpr int R = BM / BN;
+    const int bid = (int)blockIdx.x;
+    const int tri_count = R * p.tri_rows * (p.tri_rows + 1) / 2;
+    if (bid < tri_count) {
+      tm = (int)((sqrtf(1.0f + 8.0f * (float)bid / (float)R) - 1.0f) * 0.5f);
+      while (R * (tm + 1) * (tm + 2) / 2 <= bid) ++tm;
+      while (R * tm * (tm + 1) / 2 > bid) --tm;
+      tn = bid - R * tm * (tm + 1) / 2;
+    } else {
+      const int rest = bid - tri_count;
+      tm = p.tri_rows + rest / p.tiles_n;
+      tn = rest % p.tiles_n;
+    }
+  } else {
+    tm = blockIdx.x % p.tiles_m;
+    tn = blockIdx.x / p.tiles_m;
+  }
   const int bm0 = tm * BM, bn0 = tn * BN;
-  const bool lower = (p.flags & PMR_GEMM_LOWER) != 0;
-  if (lower && bn0 > bm0 + BM - 1) return;
 
   const long long b1 = blockIdx.z, b2 = blockIdx.y;
   double* Cb = p.C + b1 * p.c_b1 + b2 * p.c_b2;
@@ -698,7 +719,19 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const bool warp_active = !(lower && bn0 + wn0 > bm0 + wm0 + WM - 1);
   const double alpha = p.alpha;
   const bool use_beta = (p.beta != 0.0);
-  const double ratio = use_beta ? p.beta / alpha : 0.0;
+  // c_late: the old C tile is only PREFETCHED into L2 here and added in the epilogue, so the first
+  // DMMA does not wait for a DRAM round trip; otherwise it is loaded into the accumulators now
+  const bool c_late = use_beta && p.c_late && p.c_vec2;
+  const double ratio = (use_beta && !c_late) ? p.beta / alpha : 0.0;
+  if (c_late && warp_active) {
+#pragma unroll
+    for (int h = 0; h < WM / 16; ++h) {
+      const int m = bm0 + wm0 + (lane >> 1) + 16 * h;
+      const int n = bn0 + wn0 + (lane & 1) * 16;
+      if (m < p.M && n < p.N && (!lower || n <= m))
+        asm volatile("prefetch.global.L2 [%0];\n" ::"l"(Cb + (long long)m * p.c_sm + n));
+    }
+  }
   double acc[MI][NI][2];
 #pragma unroll
   for (int mi = 0; mi < MI; ++mi) {
@@ -706,7 +739,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
     for (int ni = 0; ni < NI; ++ni) {
       acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-      if (use_beta && warp_active) {
+      if (use_beta && !c_late && warp_active) {
         const int n = bn0 + wn0 + ni * 8 + 2 * t;
         if (m < p.M && n < p.N) {
           const bool ok1 = (n + 1 < p.N) && (!lower || n + 1 <= m);
@@ -757,10 +790,24 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   }
   if (!warp_active) return;
 
+  const double beta_late = c_late ? p.beta : 0.0;
 #pragma unroll
   for (int mi = 0; mi < MI; ++mi) {
     const int m = bm0 + wm0 + mi * 8 + g;
     if (m >= p.M) continue;
+    double2 old[NI];
+    if (c_late) {
+#pragma unroll
+      for (int ni = 0; ni < NI; ++ni) {
+        const int n = bn0 + wn0 + ni * 8 + 2 * t;
+        old[ni] = make_double2(0.0, 0.0);
+        if (n < p.N && (!lower || n <= m)) {
+          const double* c = Cb + (long long)m * p.c_sm + n;
+          if (n + 1 < p.N && (!lower || n + 1 <= m)) old[ni] = *reinterpret_cast<const double2*>(c);
+          else old[ni].x = c[0];
+        }
+      }
+    }
 #pragma unroll
     for (int ni = 0; ni < NI; ++ni) {
       const int n = bn0 + wn0 + ni * 8 + 2 * t;
@@ -768,6 +815,10 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const bool ok1 = (n + 1 < p.N) && (!lower || n + 1 <= m);
       const bool ok0 = (!lower || n <= m);
       double* c = Cb + (long long)m * p.c_sm + (long long)n * p.c_sn;
+      if (c_late) {
+        acc[mi][ni][0] = fma(beta_late / alpha, old[ni].x, acc[mi][ni][0]);
+        acc[mi][ni][1] = fma(beta_late / alpha, old[ni].y, acc[mi][ni][1]);
+      }
       if (p.c_vec2 && ok0 && ok1) {
         double2 v;
         v.x = alpha * acc[mi][ni][0];
@@ -820,15 +871,15 @@ static bool make_operand_map(CUtensorMap* map, const double* base, int rows, int
 
 // returns 0 on launch, >0 when the operands cannot be described by a tensor map (caller falls back
 // to the cp.async kernel), <0 on error
-template <int BM, int BN, int WM, int WN, int NSTAGE, int MINB>
-int launch_tma_cfg(GemmArgs a, int batch1, int batch2, cudaStream_t st) {
+template <int BM, int BN, int WM, int WN, int NSTAGE, int MINB, bool LOWER>
+int launch_tma_lower(GemmArgs a, int batch1, int batch2, cudaStream_t st) {
   constexpr int NT = (BM / WM) * (BN / WN) * 32 + 32;
   constexpr int SMEM = NSTAGE * (BM + BN) * BK * 8 + 1024;
   CUtensorMap mapA, mapB;
   if (!make_operand_map(&mapA, a.A, a.M, a.K, a.a_ld, batch2, a.a_b2, batch1, a.a_b1, BM) ||
       !make_operand_map(&mapB, a.B, a.N, a.K, a.b_ld, batch2, a.b_b2, batch1, a.b_b1, BN))
     return 1;
-  auto kern = dgemm_tma_kernel<BM, BN, WM, WN, NSTAGE, MINB>;
+  auto kern = dgemm_tma_kernel<BM, BN, WM, WN, NSTAGE, MINB, LOWER>;
   static thread_local bool configured = false;
   if (!configured) {
     PMR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -838,7 +889,15 @@ int launch_tma_cfg(GemmArgs a, int batch1, int batch2, cudaStream_t st) {
   a.tiles_n = (a.N + BN - 1) / BN;
   PMR_REQUIRE((long long)a.tiles_m * a.tiles_n < (1LL << 31), "dgemm: too many tiles");
   PMR_REQUIRE(batch1 <= 65535 && batch2 <= 65535, "dgemm: batch count above 65535");
-  dim3 grid((unsigned)((long long)a.tiles_m * a.tiles_n), (unsigned)batch2, (unsigned)batch1);
+  long long ntiles = (long long)a.tiles_m * a.tiles_n;
+  if (a.flags & PMR_GEMM_LOWER) {
+    constexpr int R = BM / BN;
+    a.tri_rows = std::min(a.tiles_m, a.tiles_n / R);     // rows with R (tm + 1) <= tiles_n
+    ntiles = (long long)R * a.tri_rows * (a.tri_rows + 1) / 2 + (long long)(a.tiles_m - a.tri_rows) * a.tiles_n;
+  }
+  static const int c_late = [] { const char* e = getenv("PMR_GEMM_C_LATE"); return e ? atoi(e) : 0; }();
+  a.c_late = c_late;
+  dim3 grid((unsigned)ntiles, (unsigned)batch2, (unsigned)batch1);
   ProfRecord rec{};
   if (g_prof_on) {
     cudaEventCreate(&rec.e0);
@@ -861,6 +920,12 @@ int launch_tma_cfg(GemmArgs a, int batch1, int batch2, cudaStream_t st) {
   }
   PMR_CHECK_LAUNCH("dgemm_tma_kernel");
   return 0;
+}
+
+template <int BM, int BN, int WM, int WN, int NSTAGE, int MINB>
+int launch_tma_cfg(const GemmArgs& a, int batch1, int batch2, cudaStream_t st) {
+  if (a.flags & PMR_GEMM_LOWER) return launch_tma_lower<BM, BN, WM, WN, NSTAGE, MINB, true>(a, batch1, batch2, st);
+  return launch_tma_lower<BM, BN, WM, WN, NSTAGE, MINB, false>(a, batch1, batch2, st);
 }
 
 template <int BM, int BN, int WM, int WN, int NSTAGE, int MINB>

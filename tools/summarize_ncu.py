@@ -20,12 +20,16 @@ def launches(path, out, note=""):
     rows = list(csv.DictReader(lines))
     agg = collections.OrderedDict()
     for r in rows:
+        if "Metric Name" in r and not r["Metric Name"].startswith("gpu__time_duration"):
+            continue
         k = short(r["Kernel Name"])
         t = float(r["Metric Value"].replace(",", ""))
         if r["Metric Unit"] in ("us", "usecond"):
             t *= 1e3
         elif r["Metric Unit"] in ("ms", "msecond"):
             t *= 1e6
+        elif r["Metric Unit"] in ("s", "second"):
+            t *= 1e9
         a = agg.setdefault(k, [0, 0.0])
         a[0] += 1
         a[1] += t
@@ -80,8 +84,43 @@ def full(rep, out):
             f.write("\n")
 
 
+def traffic(path, out, label, pattern, note=""):
+    """Per-launch DRAM bytes (read + write) of the launches whose kernel name matches ``pattern``
+    from a multi-metric launch list (gpu__time_duration.sum, dram__bytes_read.sum,
+    dram__bytes_write.sum) -> {label: {...}} merged into the JSON file ``out``."""
+    import json
+    import os
+
+    lines = [l for l in open(path) if not l.startswith("==")]
+    rows = list(csv.DictReader(lines))
+    per = collections.OrderedDict()
+    for r in rows:
+        if not re.search(pattern, r["Kernel Name"]):
+            continue
+        v = float(r["Metric Value"].replace(",", ""))
+        unit = r["Metric Unit"].lower()
+        if r["Metric Name"].startswith("dram__bytes"):
+            mult = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
+            per.setdefault(r["ID"], [0.0, 0.0])[0] += v * mult
+        elif r["Metric Name"].startswith("gpu__time_duration"):
+            mult = {"ns": 1e-6, "nsecond": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0}.get(unit, 1e-6)
+            per.setdefault(r["ID"], [0.0, 0.0])[1] += v * mult
+    n = len(per)
+    data = {}
+    if os.path.exists(out):
+        data = json.load(open(out))
+    data[label] = {"dram_bytes_per_launch": sum(v[0] for v in per.values()) / max(1, n), "launches": n,
+                   "total_dram_bytes": sum(v[0] for v in per.values()),
+                   "total_ms_under_ncu": sum(v[1] for v in per.values()),
+                   "source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum over the {n} launches matching "
+                             f"/{pattern}/ of one bench.py run ({os.path.basename(path)}); {note}"}
+    json.dump(data, open(out, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "launches":
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5], sys.argv[6] if len(sys.argv) > 6 else "")
+    elif sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
     else:
         full(sys.argv[2], sys.argv[3])

@@ -173,6 +173,20 @@ void pmr_set_lookahead(int on);
 void pmr_set_transposed_panels(int on);
 int pmr_potrf(double* A, int N, long long lda, int batch, long long stride_a, double* dinv,
               int* info /* device, batch ints */, void* stream);
+/* Same factorisation of the leading N x N block of a (rows x N) matrix, rows >= N: the rows below
+ * the square ride through every panel solve and trailing update, so right-hand sides stored there
+ * (one per ROW) leave as Y^T with L Y = B -- the forward substitution of G^-1 . rhs
+ * (solvers.py:407-410) costs no extra pass over the factor; finish with pmr_potrs_ex(phases = 2). */
+int pmr_potrf_rows(double* A, int N, int rows, long long lda, int batch, long long stride_a,
+                   double* dinv, int* info, void* stream);
+/* pmr_potrs with the two substitutions selectable: phases 1 = forward (B -> work, work holds Y as
+ * (N, nrhs) per matrix), 2 = backward (work -> B), 3 = both. */
+int pmr_potrs_ex(const double* L, int N, long long lda, int batch, long long stride_l,
+                 const double* dinv, double* B, int nrhs, long long ldb, long long stride_b,
+                 double* work, int phases, void* stream);
+/* A[c][r] = A[r][c] for r > c: completes a symmetric matrix of which only the lower triangle was
+ * computed (K^-1 from pmr_potri_lower, then used as a plain GEMM operand: p = w K^-1 m). */
+int pmr_symmetrize_lower(double* A, int N, long long lda, void* stream);
 /* Factor ONE 512-wide block column (columns [j0, j0+512), j0 % 512 == 0) of a single matrix whose
  * rows j0.. already carry the updates of the block columns to its left; `dinv` / `info` as in
  * pmr_potrf (info must be zeroed by the caller once).  Multi-GPU building block. */

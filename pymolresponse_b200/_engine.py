@@ -48,6 +48,45 @@ def potrf(A, batch=1):
     return dinv, info
 
 
+def potrf_rows(A, N, batch=1):
+    """Batched lower Cholesky of the leading (N, N) block of (batch, rows, N) matrices whose rows
+    N.. hold right-hand sides (one per row): they come out forward-substituted (pmr_potrf_rows)."""
+    L = nv.lib()
+    rows = int(A.shape[-2])
+    assert int(A.shape[-1]) == N and rows >= N
+    lda = int(A.stride(-2))
+    stride = int(A.stride(0)) if A.dim() == 3 else 0
+    torch = nv.torch_mod()
+    dinv = nv.empty(batch, max(1, int(L.pmr_potrf_dinv_doubles(N))))
+    info = torch.zeros(batch, dtype=torch.int32, device=nv.device())
+    nv.check(L.pmr_potrf_rows(nv.ptr(A), N, rows, lda, batch, stride, nv.ptr(dinv), nv.ptr(info),
+                              nv.stream_ptr()))
+    return dinv, info
+
+
+def potrs_backward(Lfac, N, dinv, Y, batch=1):
+    """L^T X = Y for (batch, N, nrhs) / (N, nrhs) contiguous Y (the forward-substituted right-hand
+    sides); returns X in a new tensor of the same shape.  Lfac may carry extra rows (stride only)."""
+    L = nv.lib()
+    nrhs = int(Y.shape[-1])
+    X = nv.empty(*Y.shape)
+    if N == 0 or nrhs == 0:
+        return X
+    lda = int(Lfac.stride(-2))
+    sl = int(Lfac.stride(0)) if Lfac.dim() == 3 else 0
+    sb = int(X.stride(0)) if X.dim() == 3 else 0
+    assert Y.is_contiguous()
+    nv.check(L.pmr_potrs_ex(nv.ptr(Lfac), N, lda, batch, sl, nv.ptr(dinv), nv.ptr(X), nrhs,
+                            int(X.stride(-2)), sb, nv.ptr(Y), 2, nv.stream_ptr()))
+    return X
+
+
+def symmetrize_lower(A):
+    nv.check(nv.lib().pmr_symmetrize_lower(nv.ptr(A), int(A.shape[0]), int(A.stride(0)),
+                                           nv.stream_ptr()))
+    return A
+
+
 OUTER_BLOCK = 512  # outer block width of pmr_potrf / pmr_potrf_panel
 DISTRIBUTED_POTRF_MIN_N = 4 * OUTER_BLOCK  # below this the redundant single-rank factorisation wins
 
@@ -202,16 +241,17 @@ def potri_lower(Lfac, dinv):
     return out
 
 
-def shifted_combine(M, W, shift_a, shift_b):
-    """S_f(lower) = M + shift_a[f] I + shift_b[f] W for all f -> (nf, N, N)."""
+def shifted_combine(M, W, shift_a, shift_b, extra_rows=0):
+    """S_f(lower) = M + shift_a[f] I + shift_b[f] W for all f -> (nf, N + extra_rows, N); the extra
+    rows (right-hand sides for pmr_potrf_rows) are left for the caller to fill."""
     L = nv.lib()
     N = int(M.shape[0])
     nf = len(shift_a)
-    S = nv.empty(nf, N, N)
+    S = nv.empty(nf, N + extra_rows, N)
     nv.check(L.pmr_shifted_combine(nv.ptr(M), nv.ptr(W) if W is not None else C.c_void_p(0), N,
                                    int(M.stride(0)), int(W.stride(0)) if W is not None else N,
-                                   _darr(shift_a), _darr(shift_b), nf, nv.ptr(S), N, N * N,
-                                   nv.stream_ptr()))
+                                   _darr(shift_a), _darr(shift_b), nf, nv.ptr(S), N,
+                                   (N + extra_rows) * N, nv.stream_ptr()))
     return S
 
 
@@ -466,6 +506,7 @@ class HalfSizeSystem:
                 if share_kinv and self.N >= DISTRIBUTED_POTRF_MIN_N:
                     # collective: every rank is here (share_kinv); K^-1 comes out of the same pass
                     dinvK, infoK, Kinv = self._factor_and_invert_distributed(Kfac)
+                    symmetrize_lower(Kinv)
                     self.stats["potrf_shared"] = self.stats.get("potrf_shared", 0) + 1
                     self.stats["potri_shared"] = self.stats.get("potri_shared", 0) + 1
                 else:
@@ -480,11 +521,13 @@ class HalfSizeSystem:
                 else:
                     Kinv = potri_lower(Kfac, dinvK)
                     self.stats["potri"] += 1
+                # both triangles: K^-1 is then a plain GEMM operand (p = K^-1 r costs one pass over
+                # N^2 doubles instead of two latency-bound triangular sweeps over the factor)
+                symmetrize_lower(Kinv)
             clock.mark("K_inverse")
         T = None
         if nf > 0 and not self._K_bad and any_dyn and imag_cols:
-            T = G[:, imag_cols].contiguous()
-            potrs(Kfac, dinvK, T)  # T = K^-1 g for the imaginary columns
+            T = nv.matmul(Kinv, G[:, imag_cols].contiguous())  # T = K^-1 g for the imaginary columns
 
         if nf > 0 and not self._K_bad:
             step = self._chunk(nf)
@@ -498,30 +541,31 @@ class HalfSizeSystem:
                 # (vector loads in the GEMM: 64 x 7168^2 with 3 columns solves in 13.4 ms, with 4 in
                 # under 10); the padding column stays zero
                 ncp = ncols + (ncols & 1)
-                rhs_pad = nv.zeros(nfc, N, ncp)
-                rhs_m = rhs_pad[:, :, :ncols]
-                S = dinvS = None
+                # right-hand sides of the m equations, one per ROW: (nfc, ncp, N)
+                rhs_rows = nv.zeros(nfc, ncp, N)
+                if real_cols:
+                    rhs_rows[:, real_cols, :] = 2.0 * g_rows[real_cols]
+                if imag_cols and T is not None:
+                    wv = torch.tensor([2.0 * w for w in ws], dtype=torch.float64, device=G.device)
+                    rhs_rows[:, imag_cols, :] = wv[:, None, None] * T.t()[None, :, :]
                 if need_m:
+                    # S(w) with the right-hand sides appended as extra rows: the factorisation
+                    # forward-substitutes them on the way (pmr_potrf_rows), only L^T m = y remains
                     S = shifted_combine(self.M, Kinv if any_dyn else None, [0.0] * nfc,
-                                        [-(w * w) for w in ws])
+                                        [-(w * w) for w in ws], extra_rows=ncp)
+                    S[:, N:, :] = rhs_rows
                     clock.mark("shifted_combine")
-                    dinvS, infoS = potrf(S, batch=nfc)
+                    dinvS, infoS = potrf_rows(S, N, batch=nfc)
                     clock.mark("potrf_S")
                     self.stats["potrf_batch"] += nfc
                     infos.append((infoS, fs))
-                # right-hand sides of the m equations for all frequencies of the chunk at once
-                if real_cols:
-                    two_g_real = axpby(2.0, G[:, real_cols].contiguous(), 0.0,
-                                       nv.empty(N, len(real_cols)))
-                    rhs_m[:, :, real_cols] = two_g_real
-                if imag_cols:
-                    for q, w in enumerate(ws):
-                        if w != 0.0:
-                            rhs_m[q][:, imag_cols] = axpby(2.0 * w, T, 0.0,
-                                                           nv.empty(N, len(imag_cols)))
-                if need_m:
-                    potrs(S, dinvS, rhs_pad, batch=nfc)  # rhs_m now holds m_f
-                # p_f = K^-1 ((1+s) g + w m_f), every frequency a block of columns of ONE solve
+                    Y = S[:, N:, :].transpose(1, 2).contiguous()            # (nfc, N, ncp)
+                    rhs_pad = potrs_backward(S, N, dinvS, Y, batch=nfc)     # m_f
+                else:
+                    S = dinvS = None
+                    rhs_pad = nv.zeros(nfc, N, ncp)
+                rhs_m = rhs_pad[:, :, :ncols]
+                # p_f = K^-1 ((1+s) g + w m_f), every frequency a block of columns
                 need_p = bool(imag_cols) or any(w != 0.0 for w in ws)
                 p_all = None
                 if need_p:
@@ -531,7 +575,10 @@ class HalfSizeSystem:
                     p_view.copy_((rhs_m * wvec[:, None, None]).permute(1, 0, 2))
                     if imag_cols:
                         p_view[:, :, imag_cols] += 2.0 * G[:, None, imag_cols]
-                    potrs(Kfac, dinvK, p_all)
+                    if Kinv is not None:
+                        p_all = nv.matmul(Kinv, p_all)
+                    else:
+                        potrs(Kfac, dinvK, p_all)
                 m_rows = rhs_m.transpose(1, 2).contiguous()                    # (nfc, ncols, N)
                 p_rows = (p_all.view(N, nfc, ncols).permute(1, 2, 0).contiguous()
                           if p_all is not None else None)

@@ -99,6 +99,10 @@ SYMBOLS = {
     "pmr_set_lookahead": (None, [C.c_int]),
     "pmr_set_transposed_panels": (None, [C.c_int]),
     "pmr_potrf": (C.c_int, [c_dp, C.c_int, c_ll, C.c_int, c_ll, c_dp, c_dp, c_dp]),
+    "pmr_potrf_rows": (C.c_int, [c_dp, C.c_int, C.c_int, c_ll, C.c_int, c_ll, c_dp, c_dp, c_dp]),
+    "pmr_potrs_ex": (C.c_int, [c_dp, C.c_int, c_ll, C.c_int, c_ll, c_dp, c_dp, C.c_int, c_ll, c_ll,
+                               c_dp, C.c_int, c_dp]),
+    "pmr_symmetrize_lower": (C.c_int, [c_dp, C.c_int, c_ll, c_dp]),
     "pmr_potrf_panel": (C.c_int, [c_dp, C.c_int, c_ll, C.c_int, c_dp, c_dp, c_dp]),
     "pmr_potrs": (C.c_int, [c_dp, C.c_int, c_ll, C.c_int, c_ll, c_dp, c_dp, C.c_int, c_ll, c_ll,
                             C.c_int, C.c_int, c_dp, c_dp]),

@@ -195,6 +195,26 @@ __global__ void shifted_combine_kernel(const double* __restrict__ M, const doubl
   }
 }
 
+// A[c][r] = A[r][c] for r > c: 32 x 32 tiles through shared memory (both sides coalesced)
+__global__ void symmetrize_lower_kernel(double* __restrict__ A, int N, long long lda) {
+  __shared__ double tile[32][33];
+  // blockIdx.x enumerates the tiles (tr >= tc) of the lower triangle row by row
+  int tr = (int)((sqrtf(8.0f * (float)blockIdx.x + 1.0f) - 1.0f) * 0.5f);
+  while ((tr + 1) * (tr + 2) / 2 <= (int)blockIdx.x) ++tr;
+  while (tr * (tr + 1) / 2 > (int)blockIdx.x) --tr;
+  const int tc = (int)blockIdx.x - tr * (tr + 1) / 2;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8 threads
+  for (int q = ty; q < 32; q += 8) {
+    const int r = tr * 32 + q, c = tc * 32 + tx;
+    tile[q][tx] = (r < N && c < N) ? A[(long long)r * lda + c] : 0.0;
+  }
+  __syncthreads();
+  for (int q = ty; q < 32; q += 8) {
+    const int r = tc * 32 + q, c = tr * 32 + tx;   // destination (row in the column-tile range)
+    if (r < N && c < N && c > r) A[(long long)r * lda + c] = tile[tx][q];
+  }
+}
+
 __global__ void copy_block_kernel(const double* __restrict__ src, long long lds,
                                   double* __restrict__ dst, long long ldd, int rows, int cols) {
   const int r = blockIdx.y;
@@ -352,10 +372,15 @@ extern "C" long long pmr_potrf_dinv_doubles(int N) {
   return nblk * NB * NB;
 }
 
-extern "C" int pmr_potrf(double* A, int N, long long lda, int batch, long long stride_a,
-                         double* dinv, int* info, void* stream) {
+// Cholesky of the leading N x N block of a (rows x N) matrix, rows >= N; the rows below the square
+// are carried through every panel solve and trailing update, so on exit they hold Y^T with
+// L Y = (those rows)^T: right-hand sides stored as extra ROWS come out forward-substituted for free
+// (the forward pass of pmr_potrs would read the whole factor once more).
+extern "C" int pmr_potrf_rows(double* A, int N, int rows, long long lda, int batch,
+                              long long stride_a, double* dinv, int* info, void* stream) {
   cudaStream_t st = as_stream(stream);
   PMR_REQUIRE(N >= 0 && batch >= 1 && batch <= 65535, "potrf: bad N/batch");
+  PMR_REQUIRE(rows >= N, "potrf: rows < N");
   PMR_REQUIRE(A && dinv && info, "potrf: null pointer");
   PMR_REQUIRE(lda >= N, "potrf: lda < N");
   const long long dstride = pmr_potrf_dinv_doubles(N);
@@ -404,7 +429,7 @@ extern "C" int pmr_potrf(double* A, int N, long long lda, int batch, long long s
   const long long pt_one = (long long)NBO * ldp;   // one buffer of one matrix
   const long long pt_mat = 2 * pt_one;             // double-buffered (look-ahead)
   double* PT = nullptr;
-  const bool use_pt = g_transposed_panels && N > NB;
+  const bool use_pt = g_transposed_panels && N > NB && rows == N;
   if (use_pt) {
     static thread_local bool pool_kept = false;
     if (!pool_kept) {  // keep freed blocks in the stream-ordered pool instead of returning them to the OS
@@ -449,7 +474,7 @@ extern "C" int pmr_potrf(double* A, int N, long long lda, int batch, long long s
     for (int k0 = j0; k0 < jend; k0 += NB) {
       const int kb = k0 / NB;
       const int jb = std::min(NB, N - k0);
-      const int rest = N - k0 - jb;
+      const int rest = rows - k0 - jb;   // rows below the diagonal block (extra rows included)
       double* Akk = A + (long long)k0 * lda + k0;
       double* dk = dinv + (long long)kb * NB * NB;
       potf2_trtri_kernel<<<batch, POTF2_THREADS, smem, sp>>>(Akk, lda, stride_a, jb, dk, dstride,
@@ -470,11 +495,11 @@ extern "C" int pmr_potrf(double* A, int N, long long lda, int batch, long long s
           PMR_TRY(syrk(jblk, j0, k0 - j0, jb, k0 + jb, rest, k0 + jb, ncols, sp));
       }
     }
-    const int rest = N - jend;
+    const int rest = N - jend;          // columns still to be updated
     if (rest <= 0) break;
     const int kw = jend - j0;
     if (!lookahead) {
-      PMR_TRY(syrk(jblk, j0, 0, kw, jend, rest, jend, rest, st));
+      PMR_TRY(syrk(jblk, j0, 0, kw, jend, rows - jend, jend, rest, st));
       continue;
     }
     const int jnext = std::min(N, jend + NBO);
@@ -482,17 +507,22 @@ extern "C" int pmr_potrf(double* A, int N, long long lda, int batch, long long s
     cudaEvent_t panel_done = new_event(sa);
     // U1 (sa): columns of the next outer block, after U2 of the previous block (same region)
     if (u2_done_prev) PMR_CHECK_CUDA(cudaStreamWaitEvent(sa, u2_done_prev, 0));
-    PMR_TRY(syrk(jblk, j0, 0, kw, jend, rest, jend, w1, sa));
+    PMR_TRY(syrk(jblk, j0, 0, kw, jend, rows - jend, jend, w1, sa));
     // U2 (st): everything to the right of it, after the panel of this block
     const int rest2 = N - jnext;
     PMR_CHECK_CUDA(cudaStreamWaitEvent(st, panel_done, 0));
-    if (rest2 > 0) PMR_TRY(syrk(jblk, j0, 0, kw, jnext, rest2, jnext, rest2, st));
+    if (rest2 > 0) PMR_TRY(syrk(jblk, j0, 0, kw, jnext, rows - jnext, jnext, rest2, st));
     u2_done_prev = new_event(st);
   }
   if (lookahead) PMR_CHECK_CUDA(cudaStreamWaitEvent(st, new_event(sa), 0));
   if (PT) PMR_CHECK_CUDA(cudaFreeAsync(PT, st));
   for (cudaEvent_t e : events) cudaEventDestroy(e);
   return 0;
+}
+
+extern "C" int pmr_potrf(double* A, int N, long long lda, int batch, long long stride_a,
+                         double* dinv, int* info, void* stream) {
+  return pmr_potrf_rows(A, N, N, lda, batch, stride_a, dinv, info, stream);
 }
 
 // One outer block column of the blocked Cholesky, on its own: factor columns [j0, j0+512) of A
@@ -856,6 +886,15 @@ extern "C" int pmr_potrs(const double* L, int N, long long lda, int batch, long 
                     work, 1 | 2 | 4, 0, 1 << 30, as_stream(stream));
 }
 
+// phases: 1 = forward only (B -> work), 2 = backward only (work -> B), 3 = both; batched like pmr_potrs
+extern "C" int pmr_potrs_ex(const double* L, int N, long long lda, int batch, long long stride_l,
+                            const double* dinv, double* B, int nrhs, long long ldb,
+                            long long stride_b, double* work, int phases, void* stream) {
+  PMR_REQUIRE(phases >= 1 && phases <= 3, "potrs_ex: phases must be 1, 2 or 3");
+  return potrs_impl(L, N, lda, batch, stride_l, dinv, B, nrhs, ldb, stride_b, 0, 0, work,
+                    phases | 4, 0, 1 << 30, as_stream(stream));
+}
+
 extern "C" int pmr_potrs_phase(const double* L, int N, long long lda, const double* dinv, double* B,
                                int nrhs, long long ldb, int first_row, int lower_only, double* work,
                                int backward, int chunk_lo, int chunk_hi, void* stream) {
@@ -899,6 +938,18 @@ extern "C" int pmr_potri_lower(const double* L, int N, long long lda, const doub
   pmr_gemm_t s = make_gemm(N, N, N, 1.0, work, 1, ldw, work, ldw, 1, 0.0, out, ldo, 1);
   s.flags = PMR_GEMM_LOWER | PMR_GEMM_KSTART_M;
   PMR_TRY(gemm(s, st));
+  return 0;
+}
+
+extern "C" int pmr_symmetrize_lower(double* A, int N, long long lda, void* stream) {
+  PMR_REQUIRE(N >= 0 && lda >= N, "symmetrize_lower: bad N/lda");
+  if (N == 0) return 0;
+  PMR_REQUIRE(A != nullptr, "symmetrize_lower: null pointer");
+  const long long nt = (N + 31) / 32;
+  const long long blocks = nt * (nt + 1) / 2;
+  PMR_REQUIRE(blocks < (1LL << 31), "symmetrize_lower: grid too large");
+  symmetrize_lower_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(A, N, lda);
+  PMR_CHECK_LAUNCH("symmetrize_lower_kernel");
   return 0;
 }
 

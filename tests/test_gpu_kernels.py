@@ -428,3 +428,41 @@ def test_eri_slab_upload_ket_symmetry():
     assert int(nv.lib().pmr_eri_ket_s2_bytes(T.shape[0] * T.shape[1], n)) == 8 * int(keep.sum())
     got = nv.to_host(nv.upload_eri_slab_s2(np.where(keep, T, np.nan)))
     assert np.array_equal(got, T)
+
+
+@pytest.mark.parametrize("n,batch,nrhs", [(300, 1, 3), (700, 3, 4), (1537, 2, 1), (2560, 2, 6)])
+def test_potrf_rows_fuses_the_forward_substitution(n, batch, nrhs):
+    """pmr_potrf_rows: right-hand sides appended as extra ROWS leave the factorisation as
+    (L^-1 b)^T; pmr_potrs_ex(phases=2) finishes the solve.  Against NumPy, look-ahead path included."""
+    from pymolresponse_b200 import _engine as eng
+
+    nv = _nv()
+    r = _rng(n)
+    A = _spd(n, n + 1, batch)
+    Bm = r.standard_normal((batch, nrhs, n))
+    aug = np.concatenate((A, Bm), axis=1)                       # (batch, n + nrhs, n)
+    Sd = nv.to_dev(aug).clone()
+    dinv, info = eng.potrf_rows(Sd, n, batch=batch)
+    assert int(info.abs().sum().item()) == 0
+    got = nv.to_host(Sd)
+    for b in range(batch):
+        Lref = np.linalg.cholesky(A[b])
+        assert np.abs(np.tril(got[b, :n]) - Lref).max() <= 1e-11 * n
+        Yref = np.linalg.solve(Lref, Bm[b].T)                   # (n, nrhs)
+        assert np.abs(got[b, n:] - Yref.T).max() <= 1e-10 * n
+    Y = Sd[:, n:, :].transpose(1, 2).contiguous()
+    X = nv.to_host(eng.potrs_backward(Sd, n, dinv, Y, batch=batch))
+    for b in range(batch):
+        assert np.abs(A[b] @ X[b] - Bm[b].T).max() <= 1e-10 * n
+
+
+def test_symmetrize_lower():
+    from pymolresponse_b200 import _engine as eng
+
+    nv = _nv()
+    r = _rng(77)
+    for n in (1, 31, 32, 33, 257):
+        A = r.standard_normal((n, n))
+        got = nv.to_host(eng.symmetrize_lower(nv.to_dev(A).clone()))
+        want = np.tril(A) + np.tril(A, -1).T
+        assert np.array_equal(got, want)

@@ -11,5 +11,5 @@ PMR_GEMM_C_LATE=1 timeout -s KILL 300 python bench.py --steps 5 --warmup 3 --no-
 echo "bench clate rc=$?" >> gpurun_out/r02b_env.log
 timeout -s KILL 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r02b_launches.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-check > gpurun_out/r02b_ncu_bench.log 2>&1
 echo "ncu launches rc=$?" >> gpurun_out/r02b_env.log
-timeout -s KILL 400 ncu --set full --clock-control none --import-source on -k regex:dgemm_tma_kernel -s 2 -c 1 -f -o gpurun_out/r02b_trailing python tools/profile_kernels.py trailing > gpurun_out/r02b_ncu_trailing.log 2>&1
+timeout -s KILL 400 ncu --set full --clock-control none --import-source on -k regex:dgemm_tma_kernel -s 1 -c 1 -f -o gpurun_out/r02b_trailing python tools/profile_kernels.py trailing > gpurun_out/r02b_ncu_trailing.log 2>&1
 echo "ncu full rc=$?" >> gpurun_out/r02b_env.log

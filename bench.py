@@ -292,6 +292,9 @@ def build_inputs(w, rank, world, torch):
     return inp
 
 
+HESSIAN_ROWS = True   # N > 1: row-block-sharded MO blocks / Hessian assembly (--hessian rows)
+
+
 def one_step(w, inp, I, device_resident: bool, world: int, stage_ms: dict | None = None,
              ao_symmetry: str = "s1"):
     """One full property calculation through the public API.  ``I`` is a CUDA tensor (kernel
@@ -317,13 +320,17 @@ def one_step(w, inp, I, device_resident: bool, world: int, stage_ms: dict | None
     if w["input"] == "df":
         a = AO2MO(inp["C"], inp["occ"], df_factor=inp["B"], device_results=True)
     else:
-        a = AO2MO(inp["C"], inp["occ"], I=I, device_results=True, nu_range=nu_range, reduce=world > 1,
+        reduce = False if world == 1 else ("scatter" if HESSIAN_ROWS else True)
+        a = AO2MO(inp["C"], inp["occ"], I=I, device_results=True, nu_range=nu_range, reduce=reduce,
                   ao_symmetry=ao_symmetry)
     if w["kind"] == "uhf":
         a.perform_uhf_partial()
     else:
         a.perform_rhf_partial()
     tei = a.tei_mo
+    rows = a.row_ranges
+    if rows is not None and w["kind"] == "rhf":
+        rows = rows[0]
     del a
     mark("ao2mo")
     gen = integrals.IntegralsArrays({"dipole": inp["O_real"], "angmom_common_gauge": inp["O_imag"]})
@@ -333,6 +340,7 @@ def one_step(w, inp, I, device_resident: bool, world: int, stage_ms: dict | None
         s = s_mag = solvers.ExactInvCholesky(inp["C"], inp["E"], inp["occ"])
         s.device_results = device_resident
         s.tei_mo = tei
+        s.tei_mo_rows = rows
         mag = Magnetizability(Program.Arrays, gen, cphf.CPHF(s))
         mag.form_operators()
         mag.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet)
@@ -343,6 +351,7 @@ def one_step(w, inp, I, device_resident: bool, world: int, stage_ms: dict | None
     s.device_results = device_resident
     s.distribute_frequencies = world > 1
     s.tei_mo = tei
+    s.tei_mo_rows = rows
     if s_mag is not None:
         s_mag.share_hessian_with(s)   # same reference, Hamiltonian and spin: M, K, chol(K) built once
     pol = Polarizability(Program.Arrays, gen, cphf.CPHF(s), frequencies=[float(f) for f in w["pol_freqs"]])
@@ -500,7 +509,11 @@ def check_worker(spec_path: str):
              M_max=smp[-1][2], K_max=smp[-1][3])
 
 
-def run_check(w, gpu, timeout_s=1500):
+_T0 = time.time()
+WALL_BUDGET_S = 780.0     # the driver gives every bench invocation 870 s
+
+
+def run_check(w, gpu, timeout_s=None):
     """gpu: dict(polarizabilities: {freq index: (3,3)}, magnetizability or None, mk: callable
     (rows, cols) -> (M values, K values) or None).  Returns the ``check`` record."""
     tmp = tempfile.mkdtemp(prefix="pmr_check_")
@@ -514,6 +527,8 @@ def run_check(w, gpu, timeout_s=1500):
     rec = {"against": "oracle/pmr_factorised.py (factorised CPU restatement, LAPACK Cholesky)",
            "frequencies_checked": [w["pol_freqs"][i] for i in w["check_freqs"]],
            "tolerance_property_tensors": 1e-8, "tolerance_mk_rel": 1e-10}
+    if timeout_s is None:
+        timeout_s = max(30.0, WALL_BUDGET_S - (time.time() - _T0))
     try:
         t0 = time.perf_counter()
         r = subprocess.run([sys.executable, str(REPO / "bench.py"), "--check-worker", sp],
@@ -524,7 +539,8 @@ def run_check(w, gpu, timeout_s=1500):
             return rec
         cpu = np.load(spec["out"])
     except subprocess.TimeoutExpired:
-        rec["error"] = f"check worker exceeded {timeout_s} s"
+        rec["error"] = (f"check worker stopped after {timeout_s:.0f} s (wall budget of the bench run); "
+                        "run `python bench.py --workload ... --steps 1` for the check alone")
         return rec
     worst = 0.0
     for k, idx in enumerate(w["check_freqs"]):
@@ -631,10 +647,10 @@ def bench_workload(w, args, rank, world, local, torch, peak64, do_e2e=True, do_c
         names = ["gemm128x128", "gemm128x128_lower(trailing update)", "gemm128x64", "gemm128x64_lower",
                  "gemm128x32", "gemm128x32_lower"]
         for c in range(6):
-            cnt, tms, fl = buf[c * 4], buf[c * 4 + 1], buf[c * 4 + 2]
+            cnt, tms, fl, by = buf[c * 4], buf[c * 4 + 1], buf[c * 4 + 2], buf[c * 4 + 3]
             if cnt > 0:
                 prof[names[c]] = {"launches": int(cnt), "ms": tms, "tflops": fl / (tms * 1e-3) / 1e12,
-                                  "algorithmic_flops": fl}
+                                  "algorithmic_flops": fl, "algorithmic_bytes": by}
         if prof:
             top = max(prof, key=lambda k: prof[k]["ms"])
             a = prof[top]
@@ -645,6 +661,7 @@ def bench_workload(w, args, rank, world, local, torch, peak64, do_e2e=True, do_c
                         "traffic": tr.get("dram_bytes_per_launch") if tr else None,
                         "traffic_source": tr.get("source") if tr else None,
                         "algorithmic_flops_per_launch": a["algorithmic_flops"] / a["launches"],
+                        "algorithmic_bytes_per_launch": a["algorithmic_bytes"] / a["launches"],
                         "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run, "
                                        "burst; MEASURED_PEAKS.json has no FP64 figure; nominal B200 "
                                        "FP64 is 37-40 TFLOP/s",
@@ -742,25 +759,27 @@ def bench_e2e(w, args, inp, res, rank, world, torch, F, sync_all, max_over_ranks
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     diffs = []
 
-    def timed(I_host, sym):
+    def timed(I_host, sym, nsteps=None):
+        nsteps = steps if nsteps is None else nsteps
         one_step(w, inp, I_host, False, world, ao_symmetry=sym)
         sync_all()
         e0.record()
-        for _ in range(steps):
+        for _ in range(nsteps):
             r = one_step(w, inp, I_host, False, world, ao_symmetry=sym)
         e1.record()
         sync_all()
-        ms_e = max_over_ranks(e0.elapsed_time(e1) / steps)
+        ms_e = max_over_ranks(e0.elapsed_time(e1) / nsteps)
         diff = max([float(np.abs(np.asarray(a) - nv.to_host(b)).max())
                     for a, b in zip(r["polarizabilities"], res["polarizabilities"])] or [0.0])
         assert diff <= 1e-8, f"end-to-end and resident results differ by {diff}"
         diffs.append(diff)
         return ms_e
 
-    def rec(ms_e, h2d, pinned, upload):
+    def rec(ms_e, h2d, pinned, upload, nsteps=None):
         return {"value": F / (ms_e * 1e-3) / 1e12, "unit": UNIT, "ms_per_step": ms_e,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "pinned_host_input": bool(pinned), "upload": upload, "steps": steps}
+                "pinned_host_input": bool(pinned), "upload": upload,
+                "steps": steps if nsteps is None else nsteps}
 
     whole = int(I_pin.nbytes * world + small)
     variants = {}
@@ -779,9 +798,10 @@ def bench_e2e(w, args, inp, res, rank, world, torch, F, sync_all, max_over_ranks
     if not args.no_pageable and level >= 2:
         I_page = np.empty(I_pin.shape, dtype=np.float64)     # plain pageable NumPy array
         np.copyto(I_page, I_pin)
-        variants["s1_pageable"] = rec(timed(I_page, "s1"), whole, False,
+        npg = max(1, min(steps, 5))     # seconds per step: a few steps are enough
+        variants["s1_pageable"] = rec(timed(I_page, "s1", npg), whole, False,
                                       "whole AO ERI array from a plain pageable NumPy array "
-                                      "(ao_symmetry='s1'): the literal drop-in call")
+                                      "(ao_symmetry='s1'): the literal drop-in call", npg)
         del I_page
     e2e["variants"] = variants
     e2e["max_abs_diff_vs_resident"] = max(diffs) if diffs else None
@@ -891,6 +911,10 @@ def run_ours(args):
         "clocks": record["clocks"], "e2e": record["e2e"], "gpu_launches": record["gpu_launches"],
         "roofline": record["roofline"], "cpu_baseline": cpu, "same_config_sample": sample,
         "stage_ms": record["stage_ms"], "solve_stats": record["solve_stats"], "check": check,
+        "sharding": None if world == 1 else {
+            "ao_eri": "second index of the first AO pair (nu)", "frequencies": "round robin over ranks",
+            "orbital_hessian": "row blocks by occupied index, all-gathered" if HESSIAN_ROWS
+            else "replicated (blocks all-reduced)"},
     }
     if headline is not None:
         line["headline_config3"] = headline
@@ -935,6 +959,9 @@ def main():
     ap.add_argument("--no-config3", action="store_true", help="N = 8: skip the headline_config3 record")
     ap.add_argument("--no-config3-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0: as many as --steps")
+    ap.add_argument("--hessian", default="rows", choices=["rows", "replicated"],
+                    help="N > 1: assemble the orbital Hessian from row-block-sharded MO blocks (rows, "
+                         "all-gathered) or on every rank from all-reduced blocks (replicated)")
     ap.add_argument("--check-worker", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.check_worker:
@@ -942,6 +969,8 @@ def main():
         return
     if args.n and args.workload == "config5":
         args.workload = "custom"
+    global HESSIAN_ROWS
+    HESSIAN_ROWS = args.hessian == "rows"
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"
     _REAL_STDOUT = _claim_stdout()

@@ -330,8 +330,21 @@ class _StageClock:
         self.on = STAGE_TIMES
         self.sink = sink
         self.marks = []
+        self._range = None
         if self.on:
             self.mark("start")
+
+    def stage(self, name):
+        """Open the NVTX range ``pmr.<name>`` (closing the previous one): always on, a few hundred
+        nanoseconds per call."""
+        self._close()
+        self._range = nv.nvtx_range(name)
+        self._range.__enter__()
+
+    def _close(self):
+        if self._range is not None:
+            self._range.__exit__(None, None, None)
+            self._range = None
 
     def mark(self, name):
         if self.on:
@@ -340,6 +353,7 @@ class _StageClock:
             self.marks.append((name, e))
 
     def finish(self):
+        self._close()
         if not self.on or len(self.marks) < 2:
             return
         nv.torch_mod().cuda.synchronize()
@@ -496,6 +510,7 @@ class HalfSizeSystem:
         G = g_rows.t().contiguous()  # (N, ncols)
         clock = _StageClock(self.stats)
 
+        clock.stage("potrf_K")
         infos = []            # (device int32 tensor, what): what = "K" or list of frequency indices
         Kfac, dinvK, Kinv = self._Kfac, self._dinvK, self._Kinv
         new_K = False
@@ -514,6 +529,7 @@ class HalfSizeSystem:
                 self.stats["potrf"] += 1
                 infos.append((infoK, "K"))
             clock.mark("potrf_K")
+            clock.stage("K_inverse")
             if (share_kinv or any_dyn) and Kinv is None:
                 if share_kinv:
                     Kinv = self._kinv_distributed(Kfac, dinvK)
@@ -541,6 +557,7 @@ class HalfSizeSystem:
                 # (vector loads in the GEMM: 64 x 7168^2 with 3 columns solves in 13.4 ms, with 4 in
                 # under 10); the padding column stays zero
                 ncp = ncols + (ncols & 1)
+                clock.stage("shifted_combine")
                 # right-hand sides of the m equations, one per ROW: (nfc, ncp, N)
                 rhs_rows = nv.zeros(nfc, ncp, N)
                 if real_cols:
@@ -555,8 +572,10 @@ class HalfSizeSystem:
                                         [-(w * w) for w in ws], extra_rows=ncp)
                     S[:, N:, :] = rhs_rows
                     clock.mark("shifted_combine")
+                    clock.stage("potrf_S")
                     dinvS, infoS = potrf_rows(S, N, batch=nfc)
                     clock.mark("potrf_S")
+                    clock.stage("solves")
                     self.stats["potrf_batch"] += nfc
                     infos.append((infoS, fs))
                     Y = S[:, N:, :].transpose(1, 2).contiguous()            # (nfc, N, ncp)
@@ -590,6 +609,7 @@ class HalfSizeSystem:
                 clock.mark("solves")
 
         # ---- one host read of every pivot-failure word
+        clock.stage("info_readback")
         bad = set()
         if self._K_bad:
             bad = set(range(nf))

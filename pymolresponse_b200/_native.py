@@ -291,6 +291,31 @@ def ptr(t, offset_elems: int = 0):
     return C.c_void_p(t.data_ptr() + offset_elems * t.element_size())
 
 
+class nvtx_range:
+    """NVTX range around one stage of the hot path (tracing): shows up in
+    Nsight Systems / ncu --nvtx captures as ``pmr.<stage>``; a no-op without a CUDA build of torch."""
+
+    def __init__(self, name: str):
+        self.name = "pmr." + name
+        self.on = False
+
+    def __enter__(self):
+        try:
+            torch_mod().cuda.nvtx.range_push(self.name)
+            self.on = True
+        except Exception:
+            self.on = False
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            try:
+                torch_mod().cuda.nvtx.range_pop()
+            except Exception:
+                pass
+        return False
+
+
 def launch_count() -> int:
     return int(load_library().pmr_launch_count())
 

@@ -77,6 +77,7 @@ def partial_blocks_dev(I_slab, nu_lo, Cbra, nocc_bra, kets, want_oovv, nu_block=
     from pymolresponse_b200 import distributed as pd
 
     clock = eng._StageClock(LAST_STAGE)
+    clock.stage("ao2mo_transform")
     L = nv.lib()
     n, nu_cnt = int(I_slab.shape[0]), int(I_slab.shape[1])
     norb = int(Cbra.shape[1])
@@ -110,6 +111,7 @@ def partial_blocks_dev(I_slab, nu_lo, Cbra, nocc_bra, kets, want_oovv, nu_block=
         int(nu_block), nv.ptr(ws), ws_n, nv.stream_ptr()))
     del ws
     clock.mark("transform")
+    clock.stage("ao2mo_collectives")
     if reduce:
         if scatter:
             outs = [pd.reduce_scatter_rows(t, o1) for t in outs]

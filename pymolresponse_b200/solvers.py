@@ -380,7 +380,8 @@ class ExactLineqSolver(LineqSolver, _HessianBlocks, ABC):
 
     def _prepare(self, hamiltonian: Hamiltonian, spin: Spin, want_ab: bool = False):
         assemble = self._assemble_uhf if self.is_uhf else self._assemble_rhf
-        M, K, A, B = assemble(hamiltonian, spin, want_ab)
+        with nv.nvtx_range("assemble_hessian"):
+            M, K, A, B = assemble(hamiltonian, spin, want_ab)
         self._system = eng.HalfSizeSystem(M, K, A, B)
         self._prepared_for = (hamiltonian, spin)
         return self._system

@@ -35,7 +35,8 @@ def launches(path, out, note=""):
         a[1] += t
     tot = sum(v[1] for v in agg.values())
     with open(out, "w") as f:
-        f.write(f"# ncu launch list summary ({len(rows)} launches, {tot/1e6:.1f} ms of kernel time)\n\n")
+        nl = sum(v[0] for v in agg.values())
+        f.write(f"# ncu launch list summary ({nl} launches, {tot/1e6:.1f} ms of kernel time)\n\n")
         f.write("`ncu --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised: "
                 "compare shares, not absolutes).\n\n")
         if note:

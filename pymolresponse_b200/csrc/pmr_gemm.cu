@@ -51,6 +51,7 @@ struct GemmArgs {
   double* C2;  // optional second (differently strided) copy of the result
   long long c2_sm, c2_sn, c2_b1, c2_b2;
   int tri_rows;  // tensor-map kernel, LOWER: tile rows that are narrower than the matrix
+  int c_late;    // tensor-map kernel: add the old C tile in the epilogue (L2-prefetched) 
 };
 
 template <int BM, int BN, int WM, int WN, bool AKC, bool BKC, int NSTAGE>
@@ -618,7 +619,11 @@ int launch_bulk_cfg(GemmArgs a, int batch1, int batch2, cudaStream_t st) {
 // Shared memory is dense (128-byte rows, no padding) with the hardware 128-byte swizzle: the 16-byte
 // chunk c of row r lives at chunk c ^ (r & 7), which makes the per-lane 64-bit fragment loads of the
 // m8n8k4 shapes bank-conflict free (8 rows x 32 bytes of a warp's request fall on 4 distinct chunk
-// pairs, two rows each: the two-wavefront minimum of a 256-byte request).  The math warps never
+// pairs, two rows each: the two-wavefront minimum of a 256-byte request; LDS.64 is served per half
+// warp, so ncu still counts 3.1 wavefronts per load.  A row permutation {0,2,4,6,1,3,5,7} of the
+// fragment slots removes them (757 M -> 27 M conflicts) and gains 1.8 % on full beta = 0 products, but
+// nothing on the lower-triangular beta = 1 updates this kernel exists for, whose epilogue it
+// complicates (-2.5 %): measured and not kept).  The math warps never
 // touch global memory or a CTA-wide barrier in the main loop, exactly as in dgemm_bulk_kernel.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
@@ -713,20 +718,16 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
   // ===== math warps =====
   const int g = lane >> 2, t = lane & 3;
-  // Fragment slot g reads tile row 8 q + pg, pg = {0,2,4,6,1,3,5,7}[g]: LDS.64 is served per HALF
-  // warp, and with the 128-byte swizzle the two 16-byte chunks a lane pair needs sit at chunk pair
-  // (kk ^ (row >> 1)) -- rows 0..3 (slots of one half warp) would share two chunk pairs (2-way
-  // conflict, measured 3.1 wavefronts per load); rows {0,2,4,6} / {1,3,5,7} hit four distinct pairs.
-  const int pg = ((g & 3) << 1) | (g >> 2);
   const int wm0 = (warp % WARPS_M) * WM;
   const int wn0 = (warp / WARPS_M) * WN;
   const bool warp_active = !(lower && bn0 + wn0 > bm0 + wm0 + WM - 1);
   const double alpha = p.alpha;
   const bool use_beta = (p.beta != 0.0);
-  const bool vec = p.c_vec2 != 0;      // unit column stride, 16-byte aligned rows
-  // beta != 0: the old C tile is only PREFETCHED into L2 here and added in the epilogue, so the first
-  // DMMA never waits for a DRAM round trip
-  if (use_beta && vec && warp_active) {
+  // c_late: the old C tile is only PREFETCHED into L2 here and added in the epilogue, so the first
+  // DMMA does not wait for a DRAM round trip; otherwise it is loaded into the accumulators now
+  const bool c_late = use_beta && p.c_late && p.c_vec2;
+  const double ratio = (use_beta && !c_late) ? p.beta / alpha : 0.0;
+  if (c_late && warp_active) {
 #pragma unroll
     for (int h = 0; h < WM / 16; ++h) {
       const int m = bm0 + wm0 + (lane >> 1) + 16 * h;
@@ -737,14 +738,35 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   }
   double acc[MI][NI][2];
 #pragma unroll
-  for (int mi = 0; mi < MI; ++mi)
+  for (int mi = 0; mi < MI; ++mi) {
+    const int m = bm0 + wm0 + mi * 8 + g;
 #pragma unroll
-    for (int ni = 0; ni < NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    for (int ni = 0; ni < NI; ++ni) {
+      acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+      if (use_beta && !c_late && warp_active) {
+        const int n = bn0 + wn0 + ni * 8 + 2 * t;
+        if (m < p.M && n < p.N) {
+          const bool ok1 = (n + 1 < p.N) && (!lower || n + 1 <= m);
+          const bool ok0 = (!lower || n <= m);
+          const double* c = Cb + (long long)m * p.c_sm + (long long)n * p.c_sn;
+          if (p.c_vec2 && ok0 && ok1) {
+            const double2 o = *reinterpret_cast<const double2*>(c);
+            acc[mi][ni][0] = ratio * o.x;
+            acc[mi][ni][1] = ratio * o.y;
+          } else {
+            if (ok0) acc[mi][ni][0] = ratio * c[0];
+            if (ok1) acc[mi][ni][1] = ratio * c[p.c_sn];
+          }
+        }
+      }
+    }
+  }
 
-  // byte offset of element (row = 8 q + pg, k = 4 kk + t) inside a tile: rows are 128 bytes, the
-  // 16-byte chunk (2 kk + t/2) is XOR-ed with row & 7 = pg (wm0, wn0 and 8 q are multiples of 8)
-  // (the k-step only flips address bits 5-6: offset(kk) = offset(0) ^ (kk << 5), one register)
-  const int koff0 = pg * ROWB + ((((t >> 1)) ^ pg) << 4) + ((t & 1) << 3);
+  // byte offset of element (row = 8 q + g, k = 4 kk + t) inside a tile: rows are 128 bytes, the
+  // 16-byte chunk (2 kk + t/2) is XOR-ed with g (= row & 7: wm0, wn0 and 8 q are multiples of 8)
+  int koff[BK / 4];
+#pragma unroll
+  for (int kk = 0; kk < BK / 4; ++kk) koff[kk] = g * ROWB + (((2 * kk + (t >> 1)) ^ g) << 4) + ((t & 1) << 3);
 
   for (int kt = 0; kt < KT; ++kt) {
     const int slot = kt % NSTAGE;
@@ -757,10 +779,10 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         double a[MI], b[NI];
 #pragma unroll
         for (int mi = 0; mi < MI; ++mi)
-          a[mi] = *reinterpret_cast<const double*>(As + mi * 8 * ROWB + (koff0 ^ (kk << 5)));
+          a[mi] = *reinterpret_cast<const double*>(As + mi * 8 * ROWB + koff[kk]);
 #pragma unroll
         for (int ni = 0; ni < NI; ++ni)
-          b[ni] = *reinterpret_cast<const double*>(Bs + ni * 8 * ROWB + (koff0 ^ (kk << 5)));
+          b[ni] = *reinterpret_cast<const double*>(Bs + ni * 8 * ROWB + koff[kk]);
 #pragma unroll
         for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
@@ -772,65 +794,43 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   }
   if (!warp_active) return;
 
-  // epilogue.  Accumulator slot (g; 2t, 2t+1) is matrix element (row pg; columns pc, pc + 2) with
-  // pc = {0,4,1,5}[t] (the B-side permutation).  For the vector path lanes t and t^2 swap one value
-  // each so that every lane owns two ADJACENT columns cs, cs+1 (cs = 4 (t&1) + 2 (t>>1)).
-  const double beta = p.beta;
-  const int cs = ((t & 1) << 2) | ((t >> 1) << 1);
-  const int pc = ((2 * t) & 3) << 1 | (t >> 1);
+  const double beta_late = c_late ? p.beta : 0.0;
 #pragma unroll
   for (int mi = 0; mi < MI; ++mi) {
-    const int m = bm0 + wm0 + mi * 8 + pg;
-    if (vec) {
-      double2 v[NI];
-#pragma unroll
-      for (int ni = 0; ni < NI; ++ni) {   // shuffles first: executed by the whole warp
-        const double give = (t < 2) ? acc[mi][ni][1] : acc[mi][ni][0];
-        const double got = __shfl_xor_sync(0xffffffffu, give, 2);
-        v[ni].x = (t < 2) ? acc[mi][ni][0] : got;
-        v[ni].y = (t < 2) ? got : acc[mi][ni][1];
-      }
-      if (m >= p.M) continue;
-      double2 old[NI];
-      if (use_beta) {
-#pragma unroll
-        for (int ni = 0; ni < NI; ++ni) {
-          const int n = bn0 + wn0 + ni * 8 + cs;
-          old[ni] = make_double2(0.0, 0.0);
-          if (n < p.N && (!lower || n <= m)) {
-            const double* c = Cb + (long long)m * p.c_sm + n;
-            if (n + 1 < p.N && (!lower || n + 1 <= m)) old[ni] = *reinterpret_cast<const double2*>(c);
-            else old[ni].x = c[0];
-          }
-        }
-      }
+    const int m = bm0 + wm0 + mi * 8 + g;
+    if (m >= p.M) continue;
+    double2 old[NI];
+    if (c_late) {
 #pragma unroll
       for (int ni = 0; ni < NI; ++ni) {
-        const int n = bn0 + wn0 + ni * 8 + cs;
-        if (n >= p.N) continue;
-        const bool ok1 = (n + 1 < p.N) && (!lower || n + 1 <= m);
-        const bool ok0 = (!lower || n <= m);
-        double2 o;
-        o.x = alpha * v[ni].x;
-        o.y = alpha * v[ni].y;
-        if (use_beta) { o.x = fma(beta, old[ni].x, o.x); o.y = fma(beta, old[ni].y, o.y); }
-        double* c = Cb + (long long)m * p.c_sm + n;
-        if (ok0 && ok1) *reinterpret_cast<double2*>(c) = o;
-        else if (ok0) c[0] = o.x;
-      }
-    } else {
-      if (m >= p.M) continue;
-#pragma unroll
-      for (int ni = 0; ni < NI; ++ni) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int n = bn0 + wn0 + ni * 8 + pc + 2 * e;
-          if (n >= p.N || (lower && n > m)) continue;
-          double* c = Cb + (long long)m * p.c_sm + (long long)n * p.c_sn;
-          double o = alpha * acc[mi][ni][e];
-          if (use_beta) o = fma(beta, c[0], o);
-          c[0] = o;
+        const int n = bn0 + wn0 + ni * 8 + 2 * t;
+        old[ni] = make_double2(0.0, 0.0);
+        if (n < p.N && (!lower || n <= m)) {
+          const double* c = Cb + (long long)m * p.c_sm + n;
+          if (n + 1 < p.N && (!lower || n + 1 <= m)) old[ni] = *reinterpret_cast<const double2*>(c);
+          else old[ni].x = c[0];
         }
+      }
+    }
+#pragma unroll
+    for (int ni = 0; ni < NI; ++ni) {
+      const int n = bn0 + wn0 + ni * 8 + 2 * t;
+      if (n >= p.N) continue;
+      const bool ok1 = (n + 1 < p.N) && (!lower || n + 1 <= m);
+      const bool ok0 = (!lower || n <= m);
+      double* c = Cb + (long long)m * p.c_sm + (long long)n * p.c_sn;
+      if (c_late) {
+        acc[mi][ni][0] = fma(beta_late / alpha, old[ni].x, acc[mi][ni][0]);
+        acc[mi][ni][1] = fma(beta_late / alpha, old[ni].y, acc[mi][ni][1]);
+      }
+      if (p.c_vec2 && ok0 && ok1) {
+        double2 v;
+        v.x = alpha * acc[mi][ni][0];
+        v.y = alpha * acc[mi][ni][1];
+        *reinterpret_cast<double2*>(c) = v;
+      } else {
+        if (ok0) c[0] = alpha * acc[mi][ni][0];
+        if (ok1) c[p.c_sn] = alpha * acc[mi][ni][1];
       }
     }
   }
@@ -895,12 +895,14 @@ int launch_tma_lower(GemmArgs a, int batch1, int batch2, cudaStream_t st) {
   PMR_REQUIRE(batch1 <= 65535 && batch2 <= 65535, "dgemm: batch count above 65535");
   long long ntiles = (long long)a.tiles_m * a.tiles_n;
   if (a.flags & PMR_GEMM_LOWER) {
-    static_assert(true, "");
     constexpr int R = (BM >= BN) ? BM / BN : 1;
-    PMR_REQUIRE(BM >= BN, "dgemm: lower-triangular store needs BM >= BN");
     a.tri_rows = std::min(a.tiles_m, a.tiles_n / R);     // rows with R (tm + 1) <= tiles_n
     ntiles = (long long)R * a.tri_rows * (a.tri_rows + 1) / 2 + (long long)(a.tiles_m - a.tri_rows) * a.tiles_n;
   }
+  // measured (config 5 step, same box): adding the old C tile in the epilogue from L2 instead of
+  // preloading it into the accumulators: 321.3 -> 311.3 ms; PMR_GEMM_C_LATE=0 restores the preload
+  static const int c_late = [] { const char* e = getenv("PMR_GEMM_C_LATE"); return e ? atoi(e) : 1; }();
+  a.c_late = c_late;
   dim3 grid((unsigned)ntiles, (unsigned)batch2, (unsigned)batch1);
   ProfRecord rec{};
   if (g_prof_on) {
@@ -1040,14 +1042,10 @@ int gemm(const pmr_gemm_t& g0, cudaStream_t st) {
   // k-contiguous operands on both sides (C -= P P^T trailing updates, S = L_M^T L ...): tensor-map TMA
   // feed, PMR_GEMM_NO_TMA=1 keeps them on the cp.async ring (comparison runs)
   static const bool allow_tma = [] { const char* e = getenv("PMR_GEMM_NO_TMA"); return !(e && atoi(e)); }();
-  static const bool tma_inplace = [] { const char* e = getenv("PMR_GEMM_TMA_INPLACE"); return !e || atoi(e); }();
-  if (allow_tma && akc && bkc && a.a_vec2 && a.b_vec2 && g.K > 0 && g.C2 == nullptr &&
-      (!(g.flags & PMR_GEMM_C_ALIASES_A) || tma_inplace)) {
+  if (allow_tma && akc && bkc && a.a_vec2 && a.b_vec2 && g.K > 0 && !(g.flags & PMR_GEMM_C_ALIASES_A) &&
+      g.C2 == nullptr) {
     int r;
-    // in-place A <- A B (C aliases A, single column tile): a CTA stores its rows only after its math
-    // warps have consumed the last k-tile, i.e. after every TMA load of those rows has landed
-    if (g.flags & PMR_GEMM_C_ALIASES_A) r = launch_tma_cfg<64, 128, 32, 32, 4, 2>(a, g.batch1, g.batch2, st);
-    else if (bn == 128) r = launch_tma_cfg<128, 128, 32, 32, 4, 1>(a, g.batch1, g.batch2, st);
+    if (bn == 128) r = launch_tma_cfg<128, 128, 32, 32, 4, 1>(a, g.batch1, g.batch2, st);
     else if (bn == 64) r = launch_tma_cfg<128, 64, 32, 32, TMA_STAGES_64, 2>(a, g.batch1, g.batch2, st);
     else r = launch_tma_cfg<128, 32, 32, 32, 4, 2>(a, g.batch1, g.batch2, st);
     if (r <= 0) return r;   // > 0: not expressible as a tensor map, fall through

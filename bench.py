@@ -573,8 +573,10 @@ def bench_workload(w, args, rank, world, local, torch, peak64, do_e2e=True, do_c
 
     lib = nv.lib()
     F = algorithmic_flops(w)
+    note(f"{w['key']}: building inputs")
     inp = build_inputs(w, rank, world, torch)
     I_dev = inp["I"]
+    note(f"{w['key']}: inputs resident, warm-up + timed steps")
 
     def sync_all():
         torch.cuda.synchronize()
@@ -620,6 +622,7 @@ def bench_workload(w, args, rank, world, local, torch, peak64, do_e2e=True, do_c
                              and int(system.M.shape[0]) == int(system.N)) else None
 
     # ---------------- stage clocks + roofline pass (untimed extra steps) ---------------------
+    note(f"{w['key']}: resident {ms:.1f} ms/step; stage clocks + roofline pass")
     stages = {}
     eng.STAGE_TIMES = True
     ao2mo_mod.LAST_STAGE.clear()
@@ -670,6 +673,7 @@ def bench_workload(w, args, rank, world, local, torch, peak64, do_e2e=True, do_c
 
     # ---------------- end-to-end: host buffers, H2D + D2H inside the timed region ------------
     e2e = None
+    note(f"{w['key']}: end-to-end variants")
     if do_e2e and not args.no_e2e and w["input"] == "dense":
         e2e = bench_e2e(w, args, inp, res, rank, world, torch, F, sync_all, max_over_ranks,
                         e2e_steps_cap)
@@ -705,6 +709,41 @@ def bench_workload(w, args, rank, world, local, torch, peak64, do_e2e=True, do_c
     return record, gpu
 
 
+def note(msg):
+    """Progress line on stderr (rank 0): which phase a killed run died in, with the host memory left."""
+    if int(os.environ.get("RANK", "0")) == 0:
+        a = host_memory_available()
+        sys.stderr.write(f"[bench {time.time() - _T0:7.1f}s] {msg} (host memory left: "
+                         f"{'?' if a is None else f'{a / 2**30:.0f} GiB'})\n")
+        sys.stderr.flush()
+
+
+def host_memory_available():
+    """Bytes of host memory this process may still take: the smaller of what the machine reports and
+    what the container's cgroup (v2 memory.max / v1 memory.limit_in_bytes) leaves -- a pinned
+    allocation beyond the cgroup limit gets the whole job killed, not an exception."""
+    avail = None
+    try:
+        import psutil
+
+        avail = int(psutil.virtual_memory().available)
+    except Exception:
+        pass
+    for lim_p, use_p in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                         ("/sys/fs/cgroup/memory/memory.limit_in_bytes",
+                          "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            lim = open(lim_p).read().strip()
+            if lim == "max":
+                continue
+            left = int(lim) - int(open(use_p).read().strip())
+            if 0 < int(lim) < (1 << 60):
+                avail = left if avail is None else min(avail, left)
+        except Exception:
+            continue
+    return avail
+
+
 def bench_e2e(w, args, inp, res, rank, world, torch, F, sync_all, max_over_ranks, steps_cap=0):
     """The same step through the public API with the AO tensor in HOST memory (H2D inside the timed
     region, response vectors + property tensors read back as NumPy).  Variants:
@@ -719,21 +758,19 @@ def bench_e2e(w, args, inp, res, rank, world, torch, F, sync_all, max_over_ranks
     I_dev = inp["I"]
     n = w["n"]
     need = I_dev.numel() * 8
-    try:
-        import psutil
-
-        avail = psutil.virtual_memory().available
-    except Exception:
-        avail = None
+    avail = host_memory_available()
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-    level = 0 if avail is None else (2 if avail > 2.3 * need * local_world + (8 << 30) else
-                                     1 if avail > 1.15 * need * local_world + (8 << 30) else -1)
+    # pinned copy of every rank's slab (level 1) plus a pageable copy (level 2), with head room: the
+    # staging buffers, the CPU check and the interpreter itself live in the same cgroup
+    level = 0 if avail is None else (2 if avail > 2.5 * need * local_world + (16 << 30) else
+                                     1 if avail > 1.3 * need * local_world + (16 << 30) else -1)
     if avail is None:
-        level = 2
+        level = 1
     flag = torch.tensor([level], dtype=torch.int64, device="cuda")
     if world > 1:
         pd.dist().all_reduce(flag, op=pd.dist().ReduceOp.MIN)
     level = int(flag.item())
+    note(f"e2e: need {need / 2**30:.0f} GiB per rank x {local_world} ranks, level {level}")
     if level < 0:
         return {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "note": f"skipped: host RAM available {avail / 2**30:.0f} GiB < {local_world} ranks x "
@@ -885,16 +922,18 @@ def run_ours(args):
         headline, gpu3 = bench_workload(w3, args, rank, world, local, torch, peak64,
                                         do_e2e=not args.no_config3_e2e, do_clocks=True, e2e_steps_cap=2)
 
-    sample = cpu = None
-    if rank == 0 and not args.no_cpu:
-        sample, cpu = same_config_sample(args, torch, world)
     if world > 1:
         pd.barrier()
         pd.dist().destroy_process_group()
     if rank != 0:
         return
+    # rank 0 alone from here on (the other ranks have exited: the host cores are free for the CPU legs)
+    sample = cpu = None
+    if not args.no_cpu:
+        sample, cpu = same_config_sample(args, torch, world)
     # the CPU restatement runs after the process group is gone (minutes at config 3: no collective
     # may be waiting on rank 0 meanwhile)
+    note("CPU restatement check")
     check = None if args.no_check else run_check(w, gpu)
     if headline is not None:
         headline["check"] = None if args.no_check else run_check(w3, gpu3)

@@ -211,6 +211,16 @@ int pmr_potrs_phase(const double* L, int N, long long lda, const double* dinv, d
 /* Lower triangle of A^-1 from the Cholesky factor (out may not alias L); work: N*N doubles. */
 int pmr_potri_lower(const double* L, int N, long long lda, const double* dinv, double* out,
                     long long ldo, double* work, void* stream);
+/* Z = inv(L) for the lower Cholesky factor (diagonal-block inverses in `dinv`) by recursive
+ * doubling: log2(N/128) levels of two batched GEMMs (Z21 = -Z22 L21 Z11 for every pair of
+ * neighbouring blocks) instead of one substitution step per 128 columns.  Entries of Z above its
+ * 128-wide block diagonal are scratch on exit.  pmr_gram_lower_cols: columns [c0, c0+ncols) of the
+ * lower triangle of Z^T Z (= (L L^T)^-1; c0 % 128 == 0) -- together the scipy.linalg.inv(chol)
+ * + product of ExactInvCholesky (solvers.py:527-530), and the column blocks ranks share out. */
+int pmr_trtri_tree(const double* L, int N, long long lda, const double* dinv, double* Z,
+                   long long ldz, void* stream);
+int pmr_gram_lower_cols(const double* Z, int N, long long ldz, int c0, int ncols, double* out,
+                        long long ldo, void* stream);
 /* S_f = M + shift_a[f] * I + shift_b[f] * W on the lower triangle, f < nf (frequency batch). */
 int pmr_shifted_combine(const double* M, const double* W, int N, long long ldm, long long ldw,
                         const double* shift_a_host, const double* shift_b_host, int nf,

@@ -241,6 +241,29 @@ def potri_lower(Lfac, dinv):
     return out
 
 
+def trtri_tree(Lfac, dinv):
+    """Z = inv(L) (lower; entries above the 128-wide block diagonal are scratch)."""
+    N = int(Lfac.shape[-1])
+    Z = nv.empty(N, N)
+    nv.check(nv.lib().pmr_trtri_tree(nv.ptr(Lfac), N, int(Lfac.stride(0)), nv.ptr(dinv), nv.ptr(Z), N,
+                                     nv.stream_ptr()))
+    return Z
+
+
+def gram_lower_cols(Z, out, c0, ncols):
+    """out[c0:, c0:c0+ncols] (lower part) = columns of Z^T Z for lower-triangular Z."""
+    N = int(Z.shape[0])
+    nv.check(nv.lib().pmr_gram_lower_cols(nv.ptr(Z), N, int(Z.stride(0)), int(c0), int(ncols),
+                                          nv.ptr(out), int(out.stride(0)), nv.stream_ptr()))
+    return out
+
+
+#: below this size the shared K^-1 is built from a LOCAL inv(L) (recursive doubling: a handful of
+#: launches, N^3/3 flops on every rank) + this rank's columns of Z^T Z; above it the flops of the
+#: replicated inv(L) cost more than the latency-bound substitutions they replace
+KINV_TREE_MAX_N = 12288
+
+
 def shifted_combine(M, W, shift_a, shift_b, extra_rows=0):
     """S_f(lower) = M + shift_a[f] I + shift_b[f] W for all f -> (nf, N + extra_rows, N); the extra
     rows (right-hand sides for pmr_potrf_rows) are left for the caller to fill."""
@@ -453,6 +476,38 @@ class HalfSizeSystem:
                 Kinv[:, lo:hi].copy_(gathered[:, src0:src0 + (hi - lo)])
         return Kinv
 
+    def _kinv_distributed_tree(self, Kfac, dinvK):
+        """Small-N variant of :meth:`_kinv_distributed`: every rank inverts the factor itself
+        (pmr_trtri_tree) and forms only its column blocks of Z^T Z; the blocks -- 2 * world of them,
+        cut at multiples of 128, rank r taking blocks r and 2*world-1-r so that the triangular work
+        is balanced -- are all-gathered.  Lower triangle only, the rest zero."""
+        from pymolresponse_b200 import distributed as pd
+
+        rank, world = pd.rank_world()
+        N = self.N
+        nblocks = 2 * world
+        nb128 = (N + 127) // 128
+        cuts = [min(N, 128 * ((nb128 * b) // nblocks)) for b in range(nblocks)] + [N]
+        bounds = [(cuts[b], cuts[b + 1]) for b in range(nblocks)]
+        wmax = max(hi - lo for lo, hi in bounds)
+        Z = trtri_tree(Kfac, dinvK)
+        local = nv.zeros(N, 2 * wmax)
+        full = nv.empty(N, N)                      # column blocks land here at their own offsets
+        for k, b in enumerate((rank, nblocks - 1 - rank)):
+            lo, hi = bounds[b]
+            if hi > lo:
+                full[:, lo:hi].zero_()
+                gram_lower_cols(Z, full, lo, hi - lo)
+                local[:, k * wmax:k * wmax + (hi - lo)].copy_(full[:, lo:hi])
+        del Z
+        gathered = pd.allgather_columns(local, 2 * wmax * world)
+        for r in range(world):
+            for k, b in enumerate((r, nblocks - 1 - r)):
+                lo, hi = bounds[b]
+                src0 = r * 2 * wmax + k * wmax
+                full[:, lo:hi].copy_(gathered[:, src0:src0 + (hi - lo)])
+        return full
+
     def _kinv_distributed(self, Kfac, dinvK):
         """K^-1 with the work split over the ranks: every rank solves K X = E_J for its own identity
         columns against the shared factor and the column blocks are all-gathered (N^2 * 8 bytes in
@@ -465,6 +520,8 @@ class HalfSizeSystem:
 
         rank, world = pd.rank_world()
         N = self.N
+        if N <= KINV_TREE_MAX_N and N >= 128 * 2 * world:
+            return self._kinv_distributed_tree(Kfac, dinvK)
         nblocks = 2 * world
         bounds = [pd.shard_range(N, b, nblocks) for b in range(nblocks)]
         mine = [bounds[rank], bounds[nblocks - 1 - rank]]

@@ -110,6 +110,8 @@ SYMBOLS = {
     "pmr_potrs_phase": (C.c_int, [c_dp, C.c_int, c_ll, c_dp, c_dp, C.c_int, c_ll, C.c_int, C.c_int,
                                   c_dp, C.c_int, C.c_int, C.c_int, c_dp]),
     "pmr_potri_lower": (C.c_int, [c_dp, C.c_int, c_ll, c_dp, c_dp, c_ll, c_dp, c_dp]),
+    "pmr_trtri_tree": (C.c_int, [c_dp, C.c_int, c_ll, c_dp, c_dp, c_ll, c_dp]),
+    "pmr_gram_lower_cols": (C.c_int, [c_dp, C.c_int, c_ll, C.c_int, C.c_int, c_dp, c_ll, c_dp]),
     "pmr_shifted_combine": (C.c_int, [c_dp, c_dp, C.c_int, c_ll, c_ll, C.POINTER(C.c_double),
                                       C.POINTER(C.c_double), C.c_int, c_dp, c_ll, c_ll, c_dp]),
     "pmr_shift_diagonal": (C.c_int, [c_dp, C.c_int, c_ll, C.c_double, c_dp]),

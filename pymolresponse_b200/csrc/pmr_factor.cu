@@ -215,6 +215,17 @@ __global__ void symmetrize_lower_kernel(double* __restrict__ A, int N, long long
   }
 }
 
+// Z[kb*NB + r][kb*NB + c] = dinv[kb][r][c] for every diagonal block kb (grid: nblk x NB rows)
+__global__ void place_diag_blocks_kernel(const double* __restrict__ dinv, double* __restrict__ Z,
+                                         long long ldz, int N) {
+  const int kb = blockIdx.x, r = blockIdx.y;
+  const int k0 = kb * NB;
+  if (k0 + r >= N) return;
+  const double* src = dinv + (long long)kb * NB * NB + (long long)r * NB;
+  double* dst = Z + (long long)(k0 + r) * ldz + k0;
+  for (int c = threadIdx.x; c < NB && k0 + c < N; c += blockDim.x) dst[c] = src[c];
+}
+
 __global__ void copy_block_kernel(const double* __restrict__ src, long long lds,
                                   double* __restrict__ dst, long long ldd, int rows, int cols) {
   const int r = blockIdx.y;
@@ -902,43 +913,89 @@ extern "C" int pmr_potrs_phase(const double* L, int N, long long lda, const doub
                     backward ? 2 : 1, chunk_lo, chunk_hi, as_stream(stream));
 }
 
+// Z = inv(L), L lower triangular with the inverses of its 128 x 128 diagonal blocks in `dinv`:
+// recursive doubling.  Level 0 places the diagonal-block inverses; at block size b = 128 * 2^l every
+// pair of neighbouring blocks [[L11, 0], [L21, L22]] gets  Z21 = -Z22 L21 Z11  from two GEMMs that are
+// BATCHED over all pairs of the level (log2(N/128) levels, about 2 launches each, against one
+// latency-bound substitution step per 128 columns: 56 steps at N = 7168).  Triangular operands skip
+// their zero halves through the k-range flags (T^T = Z11^T L21^T with k >= row tile; Z21 = -Z22 T with
+// k <= row tile), so the work is the N^3/3 of a triangular inversion.  T^T lives in the (dead) Z12
+// block; entries of Z above its 128-wide block diagonal are scratch on exit (the Gram product below
+// starts its k loop at the row tile and never reads them), the block diagonal itself is exact.
+extern "C" int pmr_trtri_tree(const double* L, int N, long long lda, const double* dinv, double* Z,
+                              long long ldz, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  PMR_REQUIRE(N >= 0, "trtri_tree: bad N");
+  if (N == 0) return 0;
+  PMR_REQUIRE(L && dinv && Z, "trtri_tree: null pointer");
+  PMR_REQUIRE(lda >= N && ldz >= N, "trtri_tree: leading dimension too small");
+  const int nblk = (N + NB - 1) / NB;
+  {
+    dim3 grid(nblk, NB);
+    place_diag_blocks_kernel<<<grid, 128, 0, st>>>(dinv, Z, ldz, N);
+    PMR_CHECK_LAUNCH("place_diag_blocks_kernel");
+  }
+  for (long long b = NB; b < N; b *= 2) {
+    const long long span = 2 * b;                  // rows covered by one pair
+    const int npairs = (int)((N + span - 1) / span);
+    // pairs [0, nfull) have a complete second block; at most one ragged pair follows
+    int nfull = 0;
+    while (nfull < npairs && (long long)nfull * span + span <= N) ++nfull;
+    for (int part = 0; part < 2; ++part) {
+      const int first = part == 0 ? 0 : nfull;
+      const int count = part == 0 ? nfull : npairs - nfull;
+      if (count <= 0) continue;
+      const long long r0 = (long long)first * span;
+      const long long n1 = b;
+      const long long n2 = part == 0 ? b : (long long)N - (r0 + b);
+      if (n2 <= 0) continue;                       // a lone block at the end: nothing to couple
+      const double* L21 = L + (r0 + b) * lda + r0;
+      double* Z11 = Z + r0 * ldz + r0;
+      double* Z12 = Z + r0 * ldz + (r0 + b);       // scratch: T^T (n1 x n2)
+      double* Z21 = Z + (r0 + b) * ldz + r0;
+      double* Z22 = Z + (r0 + b) * ldz + (r0 + b);
+      const long long ps_l = span * (lda + 1), ps_z = span * (ldz + 1);
+      // T^T(c, r) = sum_{k >= c} Z11(k, c) L21(r, k)
+      pmr_gemm_t g1 = make_gemm((int)n1, (int)n2, (int)n1, 1.0, Z11, 1, ldz, L21, 1, lda, 0.0, Z12, ldz, 1);
+      g1.flags = PMR_GEMM_KSTART_M;
+      g1.batch1 = count; g1.a_b1 = ps_z; g1.b_b1 = ps_l; g1.c_b1 = ps_z;
+      PMR_TRY(gemm(g1, st));
+      // Z21(r, c) = -sum_{k <= r} Z22(r, k) T(k, c),  T(k, c) = T^T(c, k)
+      pmr_gemm_t g2 = make_gemm((int)n2, (int)n1, (int)n2, -1.0, Z22, ldz, 1, Z12, 1, ldz, 0.0, Z21, ldz, 1);
+      g2.flags = PMR_GEMM_KEND_M;
+      g2.batch1 = count; g2.a_b1 = ps_z; g2.b_b1 = ps_z; g2.c_b1 = ps_z;
+      PMR_TRY(gemm(g2, st));
+    }
+  }
+  return 0;
+}
+
+// out[c0 + r', c0 + c'] (r' >= c', c' < ncols) = sum_k Z(k, c0 + r') Z(k, c0 + c'): the columns
+// [c0, c0 + ncols) of the lower triangle of Z^T Z for lower-triangular Z (rows >= c0 only: the
+// sub-block Z[c0:, c0:] is itself lower triangular, so nothing above it contributes).
+extern "C" int pmr_gram_lower_cols(const double* Z, int N, long long ldz, int c0, int ncols,
+                                   double* out, long long ldo, void* stream) {
+  PMR_REQUIRE(N >= 0 && c0 >= 0 && ncols >= 0 && c0 + ncols <= N, "gram_lower_cols: bad range");
+  if (N == 0 || ncols == 0) return 0;
+  PMR_REQUIRE(Z && out, "gram_lower_cols: null pointer");
+  PMR_REQUIRE(c0 % NB == 0, "gram_lower_cols: c0 must be a multiple of 128 (the k loop starts at the row tile)");
+  const int m = N - c0;
+  const double* Zs = Z + (long long)c0 * ldz + c0;
+  pmr_gemm_t s = make_gemm(m, ncols, m, 1.0, Zs, 1, ldz, Zs, ldz, 1, 0.0,
+                           out + (long long)c0 * ldo + c0, ldo, 1);
+  s.flags = PMR_GEMM_LOWER | PMR_GEMM_KSTART_M;
+  return gemm(s, as_stream(stream));
+}
+
 extern "C" int pmr_potri_lower(const double* L, int N, long long lda, const double* dinv,
                                double* out, long long ldo, double* work, void* stream) {
-  cudaStream_t st = as_stream(stream);
   PMR_REQUIRE(N >= 0, "potri: bad N");
   if (N == 0) return 0;
   PMR_REQUIRE(L && dinv && out && work, "potri: null pointer");
   PMR_REQUIRE(ldo >= N, "potri: ldo < N");
-  const int nblk = (N + NB - 1) / NB;
-  const long long ldw = N;
-  // Z = inv(L) (lower) -> work ; right-looking forward substitution on the identity, the running
-  // right-hand side lives in `out` (only its nonzero block columns are touched).
-  PMR_CHECK_CUDA(cudaMemset2DAsync(out, sizeof(double) * ldo, 0, sizeof(double) * N, N, st));
-  for (int kb = 0; kb < nblk; ++kb) {
-    const int k0 = kb * NB, jb = std::min(NB, N - k0), rest = N - k0 - jb;
-    const double* dk = dinv + (long long)kb * NB * NB;
-    double* Zk = work + (long long)k0 * ldw;
-    if (k0 > 0) {
-      pmr_gemm_t g = make_gemm(jb, k0, jb, 1.0, dk, NB, 1, out + (long long)k0 * ldo, ldo, 1, 0.0,
-                               Zk, ldw, 1);
-      PMR_TRY(gemm(g, st));
-    }
-    {
-      dim3 grid((jb + 127) / 128, jb);
-      copy_block_kernel<<<grid, 128, 0, st>>>(dk, NB, Zk + k0, ldw, jb, jb);
-      PMR_CHECK_LAUNCH("copy_block_kernel");
-    }
-    if (rest > 0) {
-      pmr_gemm_t u = make_gemm(rest, k0 + jb, jb, -1.0, L + (long long)(k0 + jb) * lda + k0, lda, 1,
-                               Zk, ldw, 1, 1.0, out + (long long)(k0 + jb) * ldo, ldo, 1);
-      PMR_TRY(gemm(u, st));
-    }
-  }
-  // out(lower) = Z^T Z ; Z(r, a) = 0 for r < a lets the k loop start at the row-tile origin
-  pmr_gemm_t s = make_gemm(N, N, N, 1.0, work, 1, ldw, work, ldw, 1, 0.0, out, ldo, 1);
-  s.flags = PMR_GEMM_LOWER | PMR_GEMM_KSTART_M;
-  PMR_TRY(gemm(s, st));
-  return 0;
+  // Z = inv(L) -> work (recursive doubling), then out(lower) = Z^T Z
+  PMR_TRY(pmr_trtri_tree(L, N, lda, dinv, work, N, stream));
+  return pmr_gram_lower_cols(work, N, N, 0, N, out, ldo, stream);
 }
 
 extern "C" int pmr_symmetrize_lower(double* A, int N, long long lda, void* stream) {

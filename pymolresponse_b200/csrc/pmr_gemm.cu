@@ -51,7 +51,6 @@ struct GemmArgs {
   double* C2;  // optional second (differently strided) copy of the result
   long long c2_sm, c2_sn, c2_b1, c2_b2;
   int tri_rows;  // tensor-map kernel, LOWER: tile rows that are narrower than the matrix
-  int c_late;    // tensor-map kernel: add the old C tile in the epilogue (L2-prefetched) 
 };
 
 template <int BM, int BN, int WM, int WN, bool AKC, bool BKC, int NSTAGE>
@@ -636,10 +635,9 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
-template <int BM, int BN, int WM, int WN, int NSTAGE, int MINB, bool LOWER>
-__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32 + 32, MINB)
-dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                 const GemmArgs p) {
+template <int BM, int BN, int WM, int WN, int NSTAGE, bool LOWER>
+__device__ __forceinline__ void dgemm_tma_body(const CUtensorMap& mapA, const CUtensorMap& mapB,
+                                               const GemmArgs& p) {
   constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
   constexpr int NWC = WARPS_M * WARPS_N;
   constexpr int MI = WM / 8, NI = WN / 8;
@@ -723,11 +721,10 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const bool warp_active = !(lower && bn0 + wn0 > bm0 + wm0 + WM - 1);
   const double alpha = p.alpha;
   const bool use_beta = (p.beta != 0.0);
-  // c_late: the old C tile is only PREFETCHED into L2 here and added in the epilogue, so the first
-  // DMMA does not wait for a DRAM round trip; otherwise it is loaded into the accumulators now
-  const bool c_late = use_beta && p.c_late && p.c_vec2;
-  const double ratio = (use_beta && !c_late) ? p.beta / alpha : 0.0;
-  if (c_late && warp_active) {
+  // beta != 0: the old C tile is only PREFETCHED into L2 here and added in the epilogue, so the first
+  // DMMA never waits for a DRAM round trip (measured on the config-5 step: 321.3 -> 311.3 ms against
+  // loading it into the accumulators up front)
+  if (use_beta && p.c_vec2 && warp_active) {
 #pragma unroll
     for (int h = 0; h < WM / 16; ++h) {
       const int m = bm0 + wm0 + (lane >> 1) + 16 * h;
@@ -738,35 +735,14 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   }
   double acc[MI][NI][2];
 #pragma unroll
-  for (int mi = 0; mi < MI; ++mi) {
-    const int m = bm0 + wm0 + mi * 8 + g;
+  for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
-    for (int ni = 0; ni < NI; ++ni) {
-      acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-      if (use_beta && !c_late && warp_active) {
-        const int n = bn0 + wn0 + ni * 8 + 2 * t;
-        if (m < p.M && n < p.N) {
-          const bool ok1 = (n + 1 < p.N) && (!lower || n + 1 <= m);
-          const bool ok0 = (!lower || n <= m);
-          const double* c = Cb + (long long)m * p.c_sm + (long long)n * p.c_sn;
-          if (p.c_vec2 && ok0 && ok1) {
-            const double2 o = *reinterpret_cast<const double2*>(c);
-            acc[mi][ni][0] = ratio * o.x;
-            acc[mi][ni][1] = ratio * o.y;
-          } else {
-            if (ok0) acc[mi][ni][0] = ratio * c[0];
-            if (ok1) acc[mi][ni][1] = ratio * c[p.c_sn];
-          }
-        }
-      }
-    }
-  }
+    for (int ni = 0; ni < NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
   // byte offset of element (row = 8 q + g, k = 4 kk + t) inside a tile: rows are 128 bytes, the
   // 16-byte chunk (2 kk + t/2) is XOR-ed with g (= row & 7: wm0, wn0 and 8 q are multiples of 8)
-  int koff[BK / 4];
-#pragma unroll
-  for (int kk = 0; kk < BK / 4; ++kk) koff[kk] = g * ROWB + (((2 * kk + (t >> 1)) ^ g) << 4) + ((t & 1) << 3);
+  // (the k-step only flips address bits 5-6: offset(kk) = offset(0) ^ (kk << 5), one register)
+  const int koff0 = g * ROWB + (((t >> 1) ^ g) << 4) + ((t & 1) << 3);
 
   for (int kt = 0; kt < KT; ++kt) {
     const int slot = kt % NSTAGE;
@@ -779,10 +755,10 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         double a[MI], b[NI];
 #pragma unroll
         for (int mi = 0; mi < MI; ++mi)
-          a[mi] = *reinterpret_cast<const double*>(As + mi * 8 * ROWB + koff[kk]);
+          a[mi] = *reinterpret_cast<const double*>(As + mi * 8 * ROWB + (koff0 ^ (kk << 5)));
 #pragma unroll
         for (int ni = 0; ni < NI; ++ni)
-          b[ni] = *reinterpret_cast<const double*>(Bs + ni * 8 * ROWB + koff[kk]);
+          b[ni] = *reinterpret_cast<const double*>(Bs + ni * 8 * ROWB + (koff0 ^ (kk << 5)));
 #pragma unroll
         for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
@@ -794,21 +770,25 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   }
   if (!warp_active) return;
 
-  const double beta_late = c_late ? p.beta : 0.0;
+  const double ratio = use_beta ? p.beta / alpha : 0.0;
 #pragma unroll
   for (int mi = 0; mi < MI; ++mi) {
     const int m = bm0 + wm0 + mi * 8 + g;
     if (m >= p.M) continue;
     double2 old[NI];
-    if (c_late) {
+    if (use_beta) {
 #pragma unroll
       for (int ni = 0; ni < NI; ++ni) {
         const int n = bn0 + wn0 + ni * 8 + 2 * t;
         old[ni] = make_double2(0.0, 0.0);
         if (n < p.N && (!lower || n <= m)) {
-          const double* c = Cb + (long long)m * p.c_sm + n;
-          if (n + 1 < p.N && (!lower || n + 1 <= m)) old[ni] = *reinterpret_cast<const double2*>(c);
-          else old[ni].x = c[0];
+          const double* c = Cb + (long long)m * p.c_sm + (long long)n * p.c_sn;
+          const bool two = n + 1 < p.N && (!lower || n + 1 <= m);
+          if (p.c_vec2 && two) old[ni] = *reinterpret_cast<const double2*>(c);
+          else {
+            old[ni].x = c[0];
+            if (two) old[ni].y = c[p.c_sn];
+          }
         }
       }
     }
@@ -819,21 +799,37 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const bool ok1 = (n + 1 < p.N) && (!lower || n + 1 <= m);
       const bool ok0 = (!lower || n <= m);
       double* c = Cb + (long long)m * p.c_sm + (long long)n * p.c_sn;
-      if (c_late) {
-        acc[mi][ni][0] = fma(beta_late / alpha, old[ni].x, acc[mi][ni][0]);
-        acc[mi][ni][1] = fma(beta_late / alpha, old[ni].y, acc[mi][ni][1]);
-      }
+      double2 v;
+      v.x = acc[mi][ni][0];
+      v.y = acc[mi][ni][1];
+      if (use_beta) { v.x = fma(ratio, old[ni].x, v.x); v.y = fma(ratio, old[ni].y, v.y); }
+      v.x *= alpha;
+      v.y *= alpha;
       if (p.c_vec2 && ok0 && ok1) {
-        double2 v;
-        v.x = alpha * acc[mi][ni][0];
-        v.y = alpha * acc[mi][ni][1];
         *reinterpret_cast<double2*>(c) = v;
       } else {
-        if (ok0) c[0] = alpha * acc[mi][ni][0];
-        if (ok1) c[p.c_sn] = alpha * acc[mi][ni][1];
+        if (ok0) c[0] = v.x;
+        if (ok1) c[p.c_sn] = v.y;
       }
     }
   }
+}
+
+// Two entry points around the same body: ptxas caps the 288-thread kernel at 96 registers for two
+// CTAs per SM (a few spills in the k loop); 18 warps x 112 registers = 64 512 also fit the register
+// file, which __maxnreg__ states directly (PMR_GEMM_TMA_REGS=112 selects it for A/B runs).
+template <int BM, int BN, int WM, int WN, int NSTAGE, int MINB, bool LOWER>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32 + 32, MINB)
+dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                 const GemmArgs p) {
+  dgemm_tma_body<BM, BN, WM, WN, NSTAGE, LOWER>(mapA, mapB, p);
+}
+
+template <int BM, int BN, int WM, int WN, int NSTAGE, int MINB, bool LOWER>
+__global__ void __maxnreg__(112)
+dgemm_tma_kernel_r112(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                      const GemmArgs p) {
+  dgemm_tma_body<BM, BN, WM, WN, NSTAGE, LOWER>(mapA, mapB, p);
 }
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -883,7 +879,9 @@ int launch_tma_lower(GemmArgs a, int batch1, int batch2, cudaStream_t st) {
   if (!make_operand_map(&mapA, a.A, a.M, a.K, a.a_ld, batch2, a.a_b2, batch1, a.a_b1, BM) ||
       !make_operand_map(&mapB, a.B, a.N, a.K, a.b_ld, batch2, a.b_b2, batch1, a.b_b1, BN))
     return 1;
-  auto kern = dgemm_tma_kernel<BM, BN, WM, WN, NSTAGE, MINB, LOWER>;
+  static const bool r112 = [] { const char* e = getenv("PMR_GEMM_TMA_REGS"); return e && atoi(e) == 112; }();
+  auto kern = (r112 && MINB == 2) ? dgemm_tma_kernel_r112<BM, BN, WM, WN, NSTAGE, MINB, LOWER>
+                                  : dgemm_tma_kernel<BM, BN, WM, WN, NSTAGE, MINB, LOWER>;
   static thread_local bool configured = false;
   if (!configured) {
     PMR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -899,10 +897,6 @@ int launch_tma_lower(GemmArgs a, int batch1, int batch2, cudaStream_t st) {
     a.tri_rows = std::min(a.tiles_m, a.tiles_n / R);     // rows with R (tm + 1) <= tiles_n
     ntiles = (long long)R * a.tri_rows * (a.tri_rows + 1) / 2 + (long long)(a.tiles_m - a.tri_rows) * a.tiles_n;
   }
-  // measured (config 5 step, same box): adding the old C tile in the epilogue from L2 instead of
-  // preloading it into the accumulators: 321.3 -> 311.3 ms; PMR_GEMM_C_LATE=0 restores the preload
-  static const int c_late = [] { const char* e = getenv("PMR_GEMM_C_LATE"); return e ? atoi(e) : 1; }();
-  a.c_late = c_late;
   dim3 grid((unsigned)ntiles, (unsigned)batch2, (unsigned)batch1);
   ProfRecord rec{};
   if (g_prof_on) {

@@ -272,7 +272,7 @@ def test_potrf_reports_first_bad_pivot():
     assert list(nv.to_host(info)) == [0, 1]
 
 
-@pytest.mark.parametrize("n", [3, 128, 200, 385])
+@pytest.mark.parametrize("n", [3, 128, 200, 385, 640, 1537, 2560, 3000])
 def test_potri_lower(n):
     from pymolresponse_b200 import _engine as eng
 
@@ -284,6 +284,24 @@ def test_potri_lower(n):
     want = np.linalg.inv(A)
     il = np.tril_indices(n)
     assert np.abs(W[il] - want[il]).max() <= 1e-11 * max(1, n)
+    # the recursive-doubling triangular inverse on its own (ragged pair sizes at several levels)
+    Z = nv.to_host(eng.trtri_tree(Ad, dinv))
+    Lref = np.linalg.cholesky(A)
+    Zref = np.linalg.inv(Lref)
+    assert np.abs(np.tril(Z) - Zref).max() <= 1e-11 * max(1, n)
+    for k0 in range(0, n, 128):          # the block diagonal is exact, zeros above the diagonal included
+        blk = Z[k0:k0 + 128, k0:k0 + 128]
+        assert np.array_equal(np.triu(blk, 1), np.zeros_like(blk))
+    # column blocks of Z^T Z (what the ranks share out)
+    if n >= 385:
+        c0 = 128 * ((n // 128) // 2)
+        out = nv.zeros(n, n)
+        eng.gram_lower_cols(nv.to_dev(Z), out, c0, min(200, n - c0))
+        got = nv.to_host(out)
+        w = min(200, n - c0)
+        ref = np.tril(want)[:, c0:c0 + w]
+        assert np.abs(got[c0:, c0:c0 + w] - ref[c0:]).max() <= 1e-11 * n
+        assert np.abs(got[:c0]).max() == 0.0
 
 
 def test_shifted_combine_lower_triangle():

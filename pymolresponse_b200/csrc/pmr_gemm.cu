@@ -815,20 +815,12 @@ __device__ __forceinline__ void dgemm_tma_body(const CUtensorMap& mapA, const CU
   }
 }
 
-// Two entry points around the same body: ptxas caps the 288-thread kernel at 96 registers for two
-// CTAs per SM (a few spills in the k loop); 18 warps x 112 registers = 64 512 also fit the register
-// file, which __maxnreg__ states directly (PMR_GEMM_TMA_REGS=112 selects it for A/B runs).
+// (ptxas caps the 288-thread kernel at 96 registers for two CTAs per SM, with a few spills in the k
+// loop; a __maxnreg__(112) build fits the register file on paper but ran 9 % slower: not kept.)
 template <int BM, int BN, int WM, int WN, int NSTAGE, int MINB, bool LOWER>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32 + 32, MINB)
 dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const GemmArgs p) {
-  dgemm_tma_body<BM, BN, WM, WN, NSTAGE, LOWER>(mapA, mapB, p);
-}
-
-template <int BM, int BN, int WM, int WN, int NSTAGE, int MINB, bool LOWER>
-__global__ void __maxnreg__(112)
-dgemm_tma_kernel_r112(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                      const GemmArgs p) {
   dgemm_tma_body<BM, BN, WM, WN, NSTAGE, LOWER>(mapA, mapB, p);
 }
 
@@ -879,9 +871,7 @@ int launch_tma_lower(GemmArgs a, int batch1, int batch2, cudaStream_t st) {
   if (!make_operand_map(&mapA, a.A, a.M, a.K, a.a_ld, batch2, a.a_b2, batch1, a.a_b1, BM) ||
       !make_operand_map(&mapB, a.B, a.N, a.K, a.b_ld, batch2, a.b_b2, batch1, a.b_b1, BN))
     return 1;
-  static const bool r112 = [] { const char* e = getenv("PMR_GEMM_TMA_REGS"); return e && atoi(e) == 112; }();
-  auto kern = (r112 && MINB == 2) ? dgemm_tma_kernel_r112<BM, BN, WM, WN, NSTAGE, MINB, LOWER>
-                                  : dgemm_tma_kernel<BM, BN, WM, WN, NSTAGE, MINB, LOWER>;
+  auto kern = dgemm_tma_kernel<BM, BN, WM, WN, NSTAGE, MINB, LOWER>;
   static thread_local bool configured = false;
   if (!configured) {
     PMR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));

@@ -1086,3 +1086,34 @@ def test_row_block_assembly_matches_full_matrices():
         A_os, B_os = bl.run(o, v, 3, v + 1, terms, None, "PQ", i_lo=lo, i_hi=hi)
         assert np.array_equal(nv.to_host(A_os), full_os[lo * v:hi * v])
         assert np.array_equal(nv.to_host(B_os), -full_os[lo * v:hi * v])
+
+
+def test_form_tei_mo_through_pyscf_and_psi4_program_objects(monkeypatch):
+    """Solver.form_tei_mo (reference solvers.py:86-127) with Program.PySCF / Program.Psi4 objects:
+    duck-typed stand-ins hand out the AO ERI tensor exactly as pyscf's ``mol.intor('int2e',
+    aosym='s1')`` / psi4's ``MintsHelper.ao_eri()`` would; results equal the Program.Arrays route."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    from _fake_qc import FakeMole, install_fake_psi4
+
+    from pymolresponse_b200 import cphf, operators, solvers, synthetic
+    from pymolresponse_b200.core import Hamiltonian, Program, Spin
+
+    n, o = 20, 3
+    case = synthetic.rhf_case(n, o)
+    Or = synthetic.operator_integrals(n, 3, False)
+    install_fake_psi4(monkeypatch, n, eri=case["I"])
+    results = {}
+    for tag, program, obj in (("arrays", Program.Arrays, case["I"]),
+                              ("pyscf", Program.PySCF, FakeMole(n, (o, o), eri=case["I"])),
+                              ("psi4", Program.Psi4, "fake psi4 molecule")):
+        s = solvers.ExactInv(case["C"], case["E"], case["occupations"])
+        d = cphf.CPHF(s)
+        d.add_operator(operators.Operator(label="dipole", is_imaginary=False, ao_integrals=Or))
+        d.set_frequencies([0.0, 0.1])
+        d.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet, program=program, program_obj=obj)
+        results[tag] = np.stack(d.results)
+    assert np.array_equal(results["pyscf"], results["arrays"])
+    assert np.array_equal(results["psi4"], results["arrays"])

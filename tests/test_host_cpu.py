@@ -327,3 +327,46 @@ def test_eigensolver_error_behaviour_matches_reference():
     assert issubclass(solvers.EigSolverTDA, solvers.EigSolver)
     x, y = solvers.EigSolver.norm_xy(np.array([3.0, 0.0, 0.0, 1.0]), 1, 2)
     assert abs(2 * (x @ x - y @ y) - 1.0) < 1e-15
+
+
+def test_pyscf_and_psi4_adapters_with_duck_typed_packages(monkeypatch):
+    """the integral adapters against stand-ins for pyscf.gto.Mole / psi4.core
+    (neither package exists in this image): label -> intor name / component count, the spin-orbit
+    sum over nuclei, occupations and the four gauge-origin keywords, psi4's MintsHelper hand-off."""
+    from _fake_qc import FakeMole, install_fake_psi4
+
+    from pymolresponse_b200 import integrals
+    from pymolresponse_b200.interfaces import pyscf_adapter as pa
+
+    n = 6
+    mol = FakeMole(n, (3, 2))
+    gen = pa.IntegralsPyscf(mol)
+    assert np.array_equal(gen.integrals(integrals.DIPOLE), mol._ints["cint1e_r_sph"])
+    assert mol.calls[-1] == ("cint1e_r_sph", 3, None)
+    assert np.array_equal(gen.integrals(integrals.ANGMOM_COMMON_GAUGE), mol._ints["cint1e_cg_irxp_sph"])
+    assert np.array_equal(gen.integrals(integrals.ANGMOM_GIAO), mol._ints["cint1e_giao_irjxp_sph"])
+    assert np.array_equal(gen.integrals(integrals.DIPVEL), mol._ints["cint1e_ipovlp_sph"])
+    so = gen.integrals(integrals.SO_SPHER_1e)
+    want = sum(mol._charges[a] * mol._prinvxp[a] for a in range(3))
+    np.testing.assert_allclose(so, want, rtol=0, atol=1e-14)
+    assert np.abs(np.asarray(gen.integrals(integrals.SO_SPHER_1e_EFF))).max() == 0.0
+    C = np.linalg.qr(np.random.default_rng(0).standard_normal((n, n)))[0][None]
+    occ = pa.occupations_from_pyscf_mol(mol, C)
+    assert occ == (3, 3, 2, 4)
+    assert np.array_equal(pa.calculate_origin_pyscf("zero", mol, C, occ), np.zeros(3))
+    com = pa.calculate_origin_pyscf("com", mol, C, occ)
+    np.testing.assert_allclose(com, (mol._masses[:, None] * mol._coords).sum(0) / mol._masses.sum())
+    ncc = pa.calculate_origin_pyscf("ncc", mol, C, occ)
+    np.testing.assert_allclose(ncc, (mol._charges[:, None] * mol._coords).sum(0) / mol._charges.sum())
+    ecc = pa.calculate_origin_pyscf("ecc", mol, C, (3, 3, 3, 3))
+    D = 2 * C[0][:, :3] @ C[0][:, :3].T
+    np.testing.assert_allclose(ecc, np.einsum("xpq,pq->x", mol._ints["cint1e_r_sph"], D) / np.trace(D))
+    with pytest.raises(ValueError):
+        pa.calculate_origin_pyscf("nonsense", mol, C, occ)
+    # psi4
+    dip, ang = install_fake_psi4(monkeypatch, n, eri=None)
+    from pymolresponse_b200.interfaces.psi4_adapter import IntegralsPsi4
+
+    g4 = IntegralsPsi4(molecule="h2o")
+    assert np.array_equal(g4.integrals(integrals.DIPOLE), dip)
+    assert np.array_equal(g4.integrals(integrals.ANGMOM_COMMON_GAUGE), ang)

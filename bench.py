@@ -296,7 +296,7 @@ HESSIAN_ROWS = True   # N > 1: row-block-sharded MO blocks / Hessian assembly (-
 
 
 def one_step(w, inp, I, device_resident: bool, world: int, stage_ms: dict | None = None,
-             ao_symmetry: str = "s1"):
+             ao_symmetry: str = "s1", keep_solver: bool = False):
     """One full property calculation through the public API.  ``I`` is a CUDA tensor (kernel
     timing, inputs resident) or a host NumPy array (end-to-end timing, H2D inside)."""
     from pymolresponse_b200 import cphf, integrals, solvers
@@ -360,7 +360,7 @@ def one_step(w, inp, I, device_resident: bool, world: int, stage_ms: dict | None
     pol.form_results()
     out["polarizabilities"] = pol.polarizabilities
     out["stats"] = getattr(s, "solve_stats", {})
-    out["solver"] = s
+    out["solver"] = s if keep_solver else None
     mark("polarizability_sweep")
     if stage_ms is not None:
         torch.cuda.synchronize()
@@ -499,7 +499,8 @@ def check_worker(spec_path: str):
         ops.append({"ao_integrals": inp["O_imag"], "is_imaginary": True})
     t0 = time.perf_counter()
     out = fac.run_cphf_factorised(inp["B"], inp["C"], inp["E"], inp["occ"], ops, freqs,
-                                  return_mk_samples=spec.get("mk_samples", 64), seed=7)
+                                  return_mk_samples=spec.get("mk_samples", CHECK_MK_SAMPLES),
+                                  seed=spec.get("mk_seed", CHECK_MK_SEED))
     seconds = time.perf_counter() - t0
     smp = out["mk_samples"]
     np.savez(spec["out"], results=np.stack(out["results"]), seconds=seconds,
@@ -510,6 +511,7 @@ def check_worker(spec_path: str):
 
 
 _T0 = time.time()
+CHECK_MK_SAMPLES, CHECK_MK_SEED = 64, 7
 WALL_BUDGET_S = 780.0     # the driver gives every bench invocation 870 s
 
 
@@ -517,7 +519,8 @@ def run_check(w, gpu, timeout_s=None):
     """gpu: dict(polarizabilities: {freq index: (3,3)}, magnetizability or None, mk: callable
     (rows, cols) -> (M values, K values) or None).  Returns the ``check`` record."""
     tmp = tempfile.mkdtemp(prefix="pmr_check_")
-    spec = {"workload": w, "out": os.path.join(tmp, "cpu.npz"), "mk_samples": 64}
+    spec = {"workload": w, "out": os.path.join(tmp, "cpu.npz"), "mk_samples": CHECK_MK_SAMPLES,
+            "mk_seed": CHECK_MK_SEED}
     sp = os.path.join(tmp, "spec.json")
     Path(sp).write_text(json.dumps(spec))
     env = dict(os.environ)
@@ -553,7 +556,8 @@ def run_check(w, gpu, timeout_s=None):
     rec["max_abs_err_vs_cpu_restatement"] = worst
     rec["alpha_static_diag"] = [float(x) for x in np.diag(np.asarray(gpu["polarizabilities"][0]))]
     if gpu.get("mk") is not None:
-        Mg, Kg = gpu["mk"](cpu["rows"], cpu["cols"])
+        rows_i, cols_i, Mg, Kg = gpu["mk"]
+        assert np.array_equal(rows_i, cpu["rows"]) and np.array_equal(cols_i, cpu["cols"])
         rec["max_rel_err_M_samples"] = float(np.abs(Mg - cpu["M"]).max() / float(cpu["M_max"]))
         rec["max_rel_err_K_samples"] = float(np.abs(Kg - cpu["K"]).max() / float(cpu["K_max"]))
         rec["mk_samples"] = int(len(cpu["rows"]))
@@ -601,25 +605,32 @@ def bench_workload(w, args, rank, world, local, torch, peak64, do_e2e=True, do_c
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        res = one_step(w, inp, I_dev, True, world)
+        res = None       # the previous step's matrices are released first, as a caller's loop would
+        res = one_step(w, inp, I_dev, True, world, keep_solver=True)
     e1.record()
     sync_all()
     launches = nv.launch_count()
     clocks = sampler.stop() if (rank == 0 and do_clocks) else None
     ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
 
-    # results of the timed run, for the check (small D2H, outside the timed region)
+    # results of the timed run, for the check (small D2H, outside the timed region); the M / K probes
+    # are read now so that the solver's matrices can be released before the end-to-end variants
     gpu = {"polarizabilities": {i: nv.to_host(res["polarizabilities"][i]) for i in w["check_freqs"]},
-           "magnetizability": nv.to_host(res["magnetizability"]) if w["magnetizability"] else None}
+           "magnetizability": nv.to_host(res["magnetizability"]) if w["magnetizability"] else None,
+           "mk": None}
     system = getattr(res["solver"], "_system", None)
+    if (system is not None and getattr(system, "M", None) is not None
+            and int(system.M.shape[0]) == int(system.N) and not args.no_check):
+        from oracle import pmr_factorised as fac   # check leg only: the probe positions
 
-    def mk_probe(rows, cols):
-        r = torch.from_numpy(np.asarray(rows)).cuda()
-        c = torch.from_numpy(np.asarray(cols)).cuda()
-        return system.M[r, c].cpu().numpy(), system.K[r, c].cpu().numpy()
-
-    gpu["mk"] = mk_probe if (system is not None and getattr(system, "M", None) is not None
-                             and int(system.M.shape[0]) == int(system.N)) else None
+        rows_i, cols_i = fac.sample_indices(int(system.N), CHECK_MK_SAMPLES, CHECK_MK_SEED)
+        rt, ct = torch.from_numpy(rows_i).cuda(), torch.from_numpy(cols_i).cuda()
+        gpu["mk"] = (rows_i, cols_i, system.M[rt, ct].cpu().numpy(), system.K[rt, ct].cpu().numpy())
+        del rt, ct
+    del system
+    res = {"polarizabilities": [nv.to_host(p_) for p_ in res["polarizabilities"]],
+           "stats": res.get("stats")}
+    torch.cuda.empty_cache()
 
     # ---------------- stage clocks + roofline pass (untimed extra steps) ---------------------
     note(f"{w['key']}: resident {ms:.1f} ms/step; stage clocks + roofline pass")

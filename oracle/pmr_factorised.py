@@ -308,6 +308,17 @@ def property_gradients(ao_integrals, C, nocc):
     return np.asarray(out)
 
 
+def sample_indices(N, count, seed=0):
+    """Seeded (row, col) probes of the lower triangle (what the device factorisations read) plus a
+    sweep of the diagonal: the M / K elements compared between the CPU restatement and the GPU."""
+    rng = np.random.default_rng(seed)
+    rr = rng.integers(0, N, count)
+    cc = rng.integers(0, N, count)
+    lo, hi = np.maximum(rr, cc), np.minimum(rr, cc)
+    diag = np.arange(0, N, max(1, N // 64))
+    return np.concatenate((lo, diag)).astype(np.int64), np.concatenate((hi, diag)).astype(np.int64)
+
+
 def run_cphf_factorised(B, C, E, occupations, operators, frequencies, hamiltonian="rpa",
                         spin="singlet", return_mk_samples=0, seed=0):
     """CPHF.run with an exact solver (cphf.py:56-66) from the AO factor B.
@@ -334,14 +345,7 @@ def run_cphf_factorised(B, C, E, occupations, operators, frequencies, hamiltonia
     N = M.shape[0]
     samples = []
     if return_mk_samples:
-        rng = np.random.default_rng(seed)
-        rr = rng.integers(0, N, return_mk_samples)
-        cc = rng.integers(0, N, return_mk_samples)
-        # lower triangle (what the device factorisations read), plus the diagonal
-        lo = np.maximum(rr, cc)
-        hi = np.minimum(rr, cc)
-        rr, cc = np.concatenate((lo, np.arange(0, N, max(1, N // 64)))), np.concatenate(
-            (hi, np.arange(0, N, max(1, N // 64))))
+        rr, cc = sample_indices(N, return_mk_samples, seed)
         samples = [(int(r), int(c), float(M[r, c]), float(K[r, c])) for r, c in zip(rr, cc)]
         samples.append(("max_abs", "max_abs", float(np.abs(M).max()), float(np.abs(K).max())))
     cols, signs, spans = [], [], []

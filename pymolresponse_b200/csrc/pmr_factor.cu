@@ -32,25 +32,32 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Diagonal-block kernel: Cholesky of a (<=128)^2 block and the inverse of its factor, one CTA per
 // matrix of the batch, everything in shared memory.  The block is padded with the identity to
 // 128x128 so every loop is uniform.  Work is organised in 32-wide block columns:
-//   factor : warp 0 factors the 32x32 diagonal block in REGISTERS (row per lane, shuffles for the
-//            column broadcasts), then all threads do the TRSM of the rows below (row per thread,
-//            right-looking, accumulators in registers) and the SYRK of the trailing block;
-//   inverse: in place, right to left: inv(D_j) per warp in registers, then
-//            L[below, j] <- -inv(L[below, below]) L[below, j] inv(D_j).
-// 12 + 8 block-level barriers instead of 2 per column.
+//   factor : warp 0 factors the 32x32 diagonal block D in REGISTERS (row per lane, shuffles for the
+//            column broadcasts, rsqrt instead of sqrt + divide) and inverts it right away (column per
+//            lane); the rows below are then X = P inv(D)^T -- a small GEMM over ALL threads with a
+//            1x4 register tile, not a 32-step dependent substitution on one thread per row -- and the
+//            trailing block gets its rank-32 update from 2x2 register tiles;
+//   inverse: in place, right to left, from the stored inv(D) blocks:
+//            L[below, j] <- -inv(L[below, below]) L[below, j] inv(D_j), 1x4 register tiles.
+// This kernel is the latency floor of every panel chain (single-matrix potrf, distributed factor of
+// K): 99 us before this layout (ncu: 7.3 barrier-stall cycles per issue, three warps doing the
+// substitution while thirteen waited).
 constexpr int SB = 32;
 constexpr int TLD = SB + 1;
 constexpr int POTF2_THREADS = 512;
-constexpr size_t POTF2_SMEM = sizeof(double) * (NB * NBLD + (NB - SB) * TLD + NB);
+// L [NB][NBLD] + T [NB-SB][TLD] + Dinv [NB/SB][SB][TLD] + rdiag [NB]
+constexpr size_t POTF2_SMEM =
+    sizeof(double) * (NB * NBLD + (NB - SB) * TLD + (NB / SB) * SB * TLD + NB);
 
 __global__ void __launch_bounds__(POTF2_THREADS, 1)
 potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, int jb,
                    double* __restrict__ dinv, long long stride_dinv, int* __restrict__ info,
                    int k0) {
   extern __shared__ double sm[];
-  double* L = sm;                      // [NB][NBLD]
-  double* T = sm + NB * NBLD;          // [NB-SB][TLD]
-  double* rdiag = T + (NB - SB) * TLD; // [NB] reciprocals of the diagonal of L
+  double* L = sm;                          // [NB][NBLD]
+  double* T = sm + NB * NBLD;              // [NB-SB][TLD]
+  double* Dinv = T + (NB - SB) * TLD;      // [NB/SB][SB][TLD]: inverses of the diagonal 32x32 factors
+  double* rdiag = Dinv + (NB / SB) * SB * TLD;  // [NB] reciprocals of the diagonal of L
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   constexpr unsigned FULL = 0xffffffffu;
@@ -69,6 +76,7 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, in
   // ------------------------------------------------------------------ factorisation
   for (int kb = 0; kb < NB / SB; ++kb) {
     const int c0 = kb * SB;
+    double* Dk = Dinv + kb * SB * TLD;
     if (warp == 0) {
       double a[SB];
 #pragma unroll
@@ -78,8 +86,8 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, in
       for (int j = 0; j < SB; ++j) {
         const double d = __shfl_sync(FULL, a[j], j);
         if (!(d > 0.0) && bad == 0) bad = c0 + j + 1;
-        const double ljj = sqrt(d);
-        const double rl = 1.0 / ljj;
+        const double rl = rsqrt(d);
+        const double ljj = d * rl;
         a[j] = (lane == j) ? ljj : a[j] * rl;
         if (lane == j) rdiag[c0 + j] = rl;
 #pragma unroll
@@ -91,39 +99,64 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, in
 #pragma unroll
       for (int k = 0; k < SB; ++k) L[(c0 + lane) * NBLD + c0 + k] = (k <= lane) ? a[k] : 0.0;
       if (lane == 0 && bad != 0 && *info == 0) *info = k0 + bad;
+      __syncwarp();
+      // inv(D): lane owns column `lane` (forward substitution on the unit vector)
+      double s[SB];
+#pragma unroll
+      for (int r = 0; r < SB; ++r) s[r] = (r == lane) ? 1.0 : 0.0;
+#pragma unroll
+      for (int q = 0; q < SB; ++q) {
+        const double x = s[q] * rdiag[c0 + q];
+        s[q] = x;
+#pragma unroll
+        for (int r = q + 1; r < SB; ++r) s[r] -= L[(c0 + r) * NBLD + c0 + q] * x;
+      }
+#pragma unroll
+      for (int r = 0; r < SB; ++r) Dk[r * TLD + lane] = s[r];   // Dk[r][c] = inv(D)(r, c), 0 above
     }
     __syncthreads();
     const int r0 = c0 + SB;
     const int nrows = NB - r0;
-    if (tid < nrows) {
-      // X D^T = P for one row of the panel below the diagonal block (right-looking substitution)
-      const int r = r0 + tid;
-      double s[SB];
-#pragma unroll
-      for (int c = 0; c < SB; ++c) s[c] = L[r * NBLD + c0 + c];
-#pragma unroll
-      for (int c = 0; c < SB; ++c) {
-        const double x = s[c] * rdiag[c0 + c];
-        s[c] = x;
-#pragma unroll
-        for (int c2 = c + 1; c2 < SB; ++c2) s[c2] -= x * L[(c0 + c2) * NBLD + c0 + c];
+    // X = P inv(D)^T: X[r][c] = sum_{q <= c} P[r][q] Dk[c][q]; thread = one row x four columns
+    for (int idx = tid; idx < nrows * (SB / 4); idx += POTF2_THREADS) {
+      const int rr = idx >> 3, cg = (idx & 7) << 2;
+      const double* pr = L + (r0 + rr) * NBLD + c0;
+      double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+#pragma unroll 8
+      for (int q = 0; q < SB; ++q) {
+        if (q > cg + 3) break;
+        const double pv = pr[q];
+        x0 += pv * Dk[(cg + 0) * TLD + q];
+        x1 += pv * Dk[(cg + 1) * TLD + q];
+        x2 += pv * Dk[(cg + 2) * TLD + q];
+        x3 += pv * Dk[(cg + 3) * TLD + q];
       }
-#pragma unroll
-      for (int c = 0; c < SB; ++c) L[r * NBLD + c0 + c] = s[c];
+      double* tr = T + rr * TLD + cg;
+      tr[0] = x0; tr[1] = x1; tr[2] = x2; tr[3] = x3;
     }
     __syncthreads();
-    for (int idx = tid; idx < nrows * nrows; idx += POTF2_THREADS) {
-      const int rr = idx / nrows, cc = idx - rr * nrows;
-      if (cc > rr) continue;
-      const double* xr = L + (r0 + rr) * NBLD + c0;
-      const double* xc = L + (r0 + cc) * NBLD + c0;
-      double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-      for (int q = 0; q < SB; q += 2) {
-        s0 += xr[q] * xc[q];
-        s1 += xr[q + 1] * xc[q + 1];
+    // copy X into the factor and update the trailing block: L[r][c] -= X[r] . X[c], 2 x 2 tiles
+    for (int idx = tid; idx < nrows * SB; idx += POTF2_THREADS) {
+      const int rr = idx >> 5, c = idx & 31;
+      L[(r0 + rr) * NBLD + c0 + c] = T[rr * TLD + c];
+    }
+    const int nt = nrows >> 1;   // nrows is a multiple of 32
+    for (int idx = tid; idx < nt * nt; idx += POTF2_THREADS) {
+      const int tr = idx / nt, tc = idx - tr * nt;
+      if (tc > tr) continue;
+      const double* xa = T + (2 * tr) * TLD;
+      const double* xb = T + (2 * tc) * TLD;
+      double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
+#pragma unroll 8
+      for (int q = 0; q < SB; ++q) {
+        const double a0 = xa[q], a1 = xa[TLD + q], b0 = xb[q], b1 = xb[TLD + q];
+        s00 += a0 * b0; s01 += a0 * b1; s10 += a1 * b0; s11 += a1 * b1;
       }
-      L[(r0 + rr) * NBLD + r0 + cc] -= (s0 + s1);
+      double* l0 = L + (r0 + 2 * tr) * NBLD + r0 + 2 * tc;
+      l0[0] -= s00;
+      if (tc < tr) l0[1] -= s01;          // (2tr, 2tc+1) lies above the diagonal when tc == tr
+      l0[NBLD] -= s10;
+      l0[NBLD + 1] -= s11;
     }
     __syncthreads();
   }
@@ -135,38 +168,42 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, in
   __syncthreads();
 
   // ------------------------------------------------------------------ inverse of L, in place
-  if (warp < NB / SB) {
-    const int c0 = warp * SB;
-    double s[SB];  // column `lane` of inv(D)
-#pragma unroll
-    for (int r = 0; r < SB; ++r) s[r] = (r == lane) ? 1.0 : 0.0;
-#pragma unroll
-    for (int q = 0; q < SB; ++q) {
-      const double x = s[q] * rdiag[c0 + q];
-      s[q] = x;
-#pragma unroll
-      for (int r = q + 1; r < SB; ++r) s[r] -= L[(c0 + r) * NBLD + c0 + q] * x;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < SB; ++r) L[(c0 + r) * NBLD + c0 + lane] = s[r];
+  for (int idx = tid; idx < (NB / SB) * SB * SB; idx += POTF2_THREADS) {
+    const int kb = idx >> 10, r = (idx >> 5) & 31, c = idx & 31;
+    L[(kb * SB + r) * NBLD + kb * SB + c] = Dinv[kb * SB * TLD + r * TLD + c];
   }
   __syncthreads();
   for (int j = NB / SB - 2; j >= 0; --j) {
     const int c0 = j * SB, r0 = c0 + SB, nb = NB - r0;
-    for (int idx = tid; idx < nb * SB; idx += POTF2_THREADS) {
-      const int rr = idx >> 5, c = idx & 31;
+    // T = W[below, below] L[below, j]   (W = the part of inv(L) already in place, lower triangular)
+    for (int idx = tid; idx < nb * (SB / 4); idx += POTF2_THREADS) {
+      const int rr = idx >> 3, cg = (idx & 7) << 2;
       const int r = r0 + rr;
-      double acc = 0.0;
-      for (int q = r0; q <= r; ++q) acc += L[r * NBLD + q] * L[q * NBLD + c0 + c];
-      T[rr * TLD + c] = acc;
+      const double* wr = L + r * NBLD;
+      double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+      for (int q = r0; q <= r; ++q) {
+        const double wv = wr[q];
+        const double* lq = L + q * NBLD + c0 + cg;
+        t0 += wv * lq[0]; t1 += wv * lq[1]; t2 += wv * lq[2]; t3 += wv * lq[3];
+      }
+      double* tr = T + rr * TLD + cg;
+      tr[0] = t0; tr[1] = t1; tr[2] = t2; tr[3] = t3;
     }
     __syncthreads();
-    for (int idx = tid; idx < nb * SB; idx += POTF2_THREADS) {
-      const int rr = idx >> 5, c = idx & 31;
-      double acc = 0.0;
-      for (int q = c; q < SB; ++q) acc += T[rr * TLD + q] * L[(c0 + q) * NBLD + c0 + c];
-      L[(r0 + rr) * NBLD + c0 + c] = -acc;
+    // W[below, j] = -T inv(D_j)
+    const double* Dj = Dinv + j * SB * TLD;
+    for (int idx = tid; idx < nb * (SB / 4); idx += POTF2_THREADS) {
+      const int rr = idx >> 3, cg = (idx & 7) << 2;
+      const double* trow = T + rr * TLD;
+      double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
+#pragma unroll 8
+      for (int q = cg; q < SB; ++q) {       // Dj[q][c] = 0 for q < c
+        const double tv = trow[q];
+        const double* dq = Dj + q * TLD + cg;
+        w0 += tv * dq[0]; w1 += tv * dq[1]; w2 += tv * dq[2]; w3 += tv * dq[3];
+      }
+      double* lw = L + (r0 + rr) * NBLD + c0 + cg;
+      lw[0] = -w0; lw[1] = -w1; lw[2] = -w2; lw[3] = -w3;
     }
     __syncthreads();
   }

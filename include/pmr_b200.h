@@ -168,6 +168,9 @@ long long pmr_potrf_dinv_doubles(int N);
  * (look-ahead).  Switch it off to get serialised, individually timeable kernels (bench.py's
  * roofline pass does); results are identical either way.  Per calling thread; default on. */
 void pmr_set_lookahead(int on);
+/* Development aid: while a device buffer (>= 19 long long) is set, the diagonal-block kernel of the
+ * Cholesky stores clock64() at its phase boundaries (tools/potf2_phases.py); NULL switches it off. */
+int pmr_debug_potf2_timing(long long* device_buffer);
 /* pmr_potrf keeps a transposed copy of the current 512-column panel so its rank-k updates run on the
  * TMA-bulk GEMM; switch off to use the in-place row-major panel with the cp.async GEMM (A/B test). */
 void pmr_set_transposed_panels(int on);

@@ -45,6 +45,13 @@ __device__ __forceinline__ double warp_sum(double v) {
 constexpr int SB = 32;
 constexpr int TLD = SB + 1;
 constexpr int POTF2_THREADS = 512;
+// development aid: when set (pmr_debug_potf2_timing), thread 0 of CTA 0 stores clock64() at the phase
+// boundaries of the diagonal-block kernel (tools/potf2_phases.py prints the differences)
+__device__ long long* g_potf2_clock = nullptr;
+#define POTF2_TICK(slot)                                                          \
+  do {                                                                            \
+    if (tid == 0 && blockIdx.x == 0 && g_potf2_clock) g_potf2_clock[slot] = clock64(); \
+  } while (0)
 // L [NB][NBLD] + T [NB-SB][TLD] + Dinv [NB/SB][SB][TLD] + rdiag [NB]
 constexpr size_t POTF2_SMEM =
     sizeof(double) * (NB * NBLD + (NB - SB) * TLD + (NB / SB) * SB * TLD + NB);
@@ -64,14 +71,28 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, in
   A += (long long)blockIdx.x * stride_a;
   dinv += (long long)blockIdx.x * stride_dinv;
   info += blockIdx.x;
+  POTF2_TICK(0);
 
-  for (int idx = tid; idx < NB * NB; idx += POTF2_THREADS) {
-    const int r = idx >> 7, c = idx & (NB - 1);
-    double v = (r == c) ? 1.0 : 0.0;
-    if (r < jb && c <= r) v = A[(long long)r * lda + c];
-    L[r * NBLD + c] = v;
+  // load the lower triangle: eight independent global loads in flight per thread (a dependent
+  // load -> shared-store loop pays one DRAM round trip per iteration: 32 of them)
+#pragma unroll 1
+  for (int it = 0; it < NB * NB / (POTF2_THREADS * 8); ++it) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = tid + (it * 8 + u) * POTF2_THREADS;
+      const int r = idx >> 7, c = idx & (NB - 1);
+      v[u] = (r == c) ? 1.0 : 0.0;
+      if (r < jb && c <= r) v[u] = A[(long long)r * lda + c];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = tid + (it * 8 + u) * POTF2_THREADS;
+      L[(idx >> 7) * NBLD + (idx & (NB - 1))] = v[u];
+    }
   }
   __syncthreads();
+  POTF2_TICK(1);
 
   // ------------------------------------------------------------------ factorisation
   for (int kb = 0; kb < NB / SB; ++kb) {
@@ -115,6 +136,7 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, in
       for (int r = 0; r < SB; ++r) Dk[r * TLD + lane] = s[r];   // Dk[r][c] = inv(D)(r, c), 0 above
     }
     __syncthreads();
+    POTF2_TICK(2 + 3 * kb);
     const int r0 = c0 + SB;
     const int nrows = NB - r0;
     // X = P inv(D)^T: X[r][c] = sum_{q <= c} P[r][q] Dk[c][q]; thread = one row x four columns
@@ -135,6 +157,7 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, in
       tr[0] = x0; tr[1] = x1; tr[2] = x2; tr[3] = x3;
     }
     __syncthreads();
+    POTF2_TICK(3 + 3 * kb);
     // copy X into the factor and update the trailing block: L[r][c] -= X[r] . X[c], 2 x 2 tiles
     for (int idx = tid; idx < nrows * SB; idx += POTF2_THREADS) {
       const int rr = idx >> 5, c = idx & 31;
@@ -159,6 +182,7 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, in
       l0[NBLD + 1] -= s11;
     }
     __syncthreads();
+    POTF2_TICK(4 + 3 * kb);
   }
 
   for (int idx = tid; idx < NB * NB; idx += POTF2_THREADS) {
@@ -166,6 +190,7 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, in
     if (r < jb && c <= r) A[(long long)r * lda + c] = L[r * NBLD + c];
   }
   __syncthreads();
+  POTF2_TICK(14);
 
   // ------------------------------------------------------------------ inverse of L, in place
   for (int idx = tid; idx < (NB / SB) * SB * SB; idx += POTF2_THREADS) {
@@ -206,11 +231,14 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, in
       lw[0] = -w0; lw[1] = -w1; lw[2] = -w2; lw[3] = -w3;
     }
     __syncthreads();
+    POTF2_TICK(15 + (NB / SB - 2 - j));
   }
   for (int idx = tid; idx < NB * NB; idx += POTF2_THREADS) {
     const int r = idx >> 7, c = idx & (NB - 1);
     if (r < jb && c <= r) dinv[(long long)r * NB + c] = L[r * NBLD + c];
   }
+  __syncthreads();
+  POTF2_TICK(18);
 }
 
 constexpr int SHIFT_MAX = 64;  // frequencies per launch (shifts travel as kernel parameters)
@@ -411,6 +439,11 @@ __global__ void lu_diag_solve_kernel(const double* __restrict__ LU, long long ld
 }  // namespace pmr
 
 using namespace pmr;
+
+extern "C" int pmr_debug_potf2_timing(long long* device_buffer /* >= 19 slots, or NULL to stop */) {
+  PMR_CHECK_CUDA(cudaMemcpyToSymbol(g_potf2_clock, &device_buffer, sizeof(device_buffer)));
+  return 0;
+}
 
 extern "C" void pmr_set_lookahead(int on) { g_lookahead = on != 0; }
 extern "C" void pmr_set_transposed_panels(int on) { g_transposed_panels = on != 0; }

@@ -56,6 +56,54 @@ __device__ long long* g_potf2_clock = nullptr;
 constexpr size_t POTF2_SMEM =
     sizeof(double) * (NB * NBLD + (NB - SB) * TLD + (NB / SB) * SB * TLD + NB);
 
+// Shared-memory micro GEMM of the diagonal-block kernel: C(m x n) (op)= sign * A(m x K) B(K x n),
+// every thread owns 4 x 4 register tiles (8 shared loads per 16 DFMA; the earlier 1 x 4 / scalar
+// loops were bound by shared-memory wavefronts: 41 k cycles for one 96 x 96 x 32 product pair).
+//   BT     : B is read transposed, B(q, c) = Bp[c * ldb + q]
+//   MODE 0 : C = sign * sum        MODE 1 : C -= sum, lower triangle of a square C only (SYRK)
+//   k range of a tile: [kbeg, min(K, kcap0 + kcap_row * (tile's last row + 1)))  -- triangular A
+// m, n multiples of 4.  All operands live in shared memory.
+template <bool BT, int MODE>
+__device__ __forceinline__ void smem_mm4(const double* __restrict__ Ap, int lda,
+                                         const double* __restrict__ Bp, int ldb, double* __restrict__ Cp,
+                                         int ldc, int m, int n, int K, int kbeg_col, int kcap0,
+                                         int kcap_row, double sign, int tid) {
+  const int tn = n >> 2, tm = m >> 2;
+  for (int idx = tid; idx < tm * tn; idx += POTF2_THREADS) {
+    const int tr = idx / tn, tc = idx - tr * tn;
+    if (MODE == 1 && tc > tr) continue;
+    const int r0 = tr << 2, c0 = tc << 2;
+    // triangular operands: B(q, c) = 0 for q < c (kbeg_col = 1) / A(r, q) = 0 for q > r (kcap_row = 1)
+    const int kb = kbeg_col ? c0 : 0;
+    const int ke = min(K, kcap0 + kcap_row * (r0 + 4));
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+#pragma unroll 4
+    for (int q = kb; q < ke; ++q) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = Ap[(r0 + i) * lda + q];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = BT ? Bp[(c0 + j) * ldb + q] : Bp[q * ldb + c0 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double* c = Cp + (r0 + i) * ldc + c0 + j;
+        if (MODE == 0) *c = sign * acc[i][j];
+        else if (c0 + j <= r0 + i) *c -= acc[i][j];
+      }
+  }
+}
+
 __global__ void __launch_bounds__(POTF2_THREADS, 1)
 potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, int jb,
                    double* __restrict__ dinv, long long stride_dinv, int* __restrict__ info,
@@ -139,48 +187,16 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, in
     POTF2_TICK(2 + 3 * kb);
     const int r0 = c0 + SB;
     const int nrows = NB - r0;
-    // X = P inv(D)^T: X[r][c] = sum_{q <= c} P[r][q] Dk[c][q]; thread = one row x four columns
-    for (int idx = tid; idx < nrows * (SB / 4); idx += POTF2_THREADS) {
-      const int rr = idx >> 3, cg = (idx & 7) << 2;
-      const double* pr = L + (r0 + rr) * NBLD + c0;
-      double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
-#pragma unroll 8
-      for (int q = 0; q < SB; ++q) {
-        if (q > cg + 3) break;
-        const double pv = pr[q];
-        x0 += pv * Dk[(cg + 0) * TLD + q];
-        x1 += pv * Dk[(cg + 1) * TLD + q];
-        x2 += pv * Dk[(cg + 2) * TLD + q];
-        x3 += pv * Dk[(cg + 3) * TLD + q];
-      }
-      double* tr = T + rr * TLD + cg;
-      tr[0] = x0; tr[1] = x1; tr[2] = x2; tr[3] = x3;
-    }
+    // X = P inv(D)^T: X[r][c] = sum_{q <= c} P[r][q] Dk[c][q]  (Dk[c][q] = 0 for q > c: full k range)
+    smem_mm4<true, 0>(L + r0 * NBLD + c0, NBLD, Dk, TLD, T, TLD, nrows, SB, SB, 0, SB, 0, 1.0, tid);
     __syncthreads();
     POTF2_TICK(3 + 3 * kb);
-    // copy X into the factor and update the trailing block: L[r][c] -= X[r] . X[c], 2 x 2 tiles
+    // copy X into the factor and update the trailing block: L[r][c] -= X[r] . X[c] (lower part)
     for (int idx = tid; idx < nrows * SB; idx += POTF2_THREADS) {
       const int rr = idx >> 5, c = idx & 31;
       L[(r0 + rr) * NBLD + c0 + c] = T[rr * TLD + c];
     }
-    const int nt = nrows >> 1;   // nrows is a multiple of 32
-    for (int idx = tid; idx < nt * nt; idx += POTF2_THREADS) {
-      const int tr = idx / nt, tc = idx - tr * nt;
-      if (tc > tr) continue;
-      const double* xa = T + (2 * tr) * TLD;
-      const double* xb = T + (2 * tc) * TLD;
-      double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
-#pragma unroll 8
-      for (int q = 0; q < SB; ++q) {
-        const double a0 = xa[q], a1 = xa[TLD + q], b0 = xb[q], b1 = xb[TLD + q];
-        s00 += a0 * b0; s01 += a0 * b1; s10 += a1 * b0; s11 += a1 * b1;
-      }
-      double* l0 = L + (r0 + 2 * tr) * NBLD + r0 + 2 * tc;
-      l0[0] -= s00;
-      if (tc < tr) l0[1] -= s01;          // (2tr, 2tc+1) lies above the diagonal when tc == tr
-      l0[NBLD] -= s10;
-      l0[NBLD + 1] -= s11;
-    }
+    smem_mm4<true, 1>(T, TLD, T, TLD, L + r0 * NBLD + r0, NBLD, nrows, nrows, SB, 0, SB, 0, 1.0, tid);
     __syncthreads();
     POTF2_TICK(4 + 3 * kb);
   }
@@ -200,36 +216,13 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, in
   __syncthreads();
   for (int j = NB / SB - 2; j >= 0; --j) {
     const int c0 = j * SB, r0 = c0 + SB, nb = NB - r0;
-    // T = W[below, below] L[below, j]   (W = the part of inv(L) already in place, lower triangular)
-    for (int idx = tid; idx < nb * (SB / 4); idx += POTF2_THREADS) {
-      const int rr = idx >> 3, cg = (idx & 7) << 2;
-      const int r = r0 + rr;
-      const double* wr = L + r * NBLD;
-      double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
-      for (int q = r0; q <= r; ++q) {
-        const double wv = wr[q];
-        const double* lq = L + q * NBLD + c0 + cg;
-        t0 += wv * lq[0]; t1 += wv * lq[1]; t2 += wv * lq[2]; t3 += wv * lq[3];
-      }
-      double* tr = T + rr * TLD + cg;
-      tr[0] = t0; tr[1] = t1; tr[2] = t2; tr[3] = t3;
-    }
+    // T = W[below, below] L[below, j]  (W = the part of inv(L) already in place: lower triangular,
+    // so row block r needs k <= r only), then W[below, j] = -T inv(D_j)  (Dj(q, c) = 0 for q < c)
+    smem_mm4<false, 0>(L + r0 * NBLD + r0, NBLD, L + r0 * NBLD + c0, NBLD, T, TLD, nb, SB, nb, 0, 0, 1,
+                       1.0, tid);
     __syncthreads();
-    // W[below, j] = -T inv(D_j)
-    const double* Dj = Dinv + j * SB * TLD;
-    for (int idx = tid; idx < nb * (SB / 4); idx += POTF2_THREADS) {
-      const int rr = idx >> 3, cg = (idx & 7) << 2;
-      const double* trow = T + rr * TLD;
-      double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
-#pragma unroll 8
-      for (int q = cg; q < SB; ++q) {       // Dj[q][c] = 0 for q < c
-        const double tv = trow[q];
-        const double* dq = Dj + q * TLD + cg;
-        w0 += tv * dq[0]; w1 += tv * dq[1]; w2 += tv * dq[2]; w3 += tv * dq[3];
-      }
-      double* lw = L + (r0 + rr) * NBLD + c0 + cg;
-      lw[0] = -w0; lw[1] = -w1; lw[2] = -w2; lw[3] = -w3;
-    }
+    smem_mm4<false, 0>(T, TLD, Dinv + j * SB * TLD, TLD, L + r0 * NBLD + c0, NBLD, nb, SB, SB, 1, SB, 0,
+                       -1.0, tid);
     __syncthreads();
     POTF2_TICK(15 + (NB / SB - 2 - j));
   }

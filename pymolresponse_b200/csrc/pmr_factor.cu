@@ -52,29 +52,33 @@ __device__ long long* g_potf2_clock = nullptr;
   do {                                                                            \
     if (tid == 0 && blockIdx.x == 0 && g_potf2_clock) g_potf2_clock[slot] = clock64(); \
   } while (0)
-// L [NB][NBLD] + T [NB-SB][TLD] + Dinv [NB/SB][SB][TLD] + rdiag [NB]
+constexpr int XLD = NB - SB + 1;   // row of the transposed panel XT[32][96]
+// L [NB][NBLD] + T [NB-SB][TLD] + Dinv [NB/SB][SB][TLD] + rdiag [NB] + XT [SB][XLD]
 constexpr size_t POTF2_SMEM =
-    sizeof(double) * (NB * NBLD + (NB - SB) * TLD + (NB / SB) * SB * TLD + NB);
+    sizeof(double) * (NB * NBLD + (NB - SB) * TLD + (NB / SB) * SB * TLD + NB + SB * XLD);
 
 // Shared-memory micro GEMM of the diagonal-block kernel: C(m x n) (op)= sign * A(m x K) B(K x n),
-// every thread owns 4 x 4 register tiles (8 shared loads per 16 DFMA; the earlier 1 x 4 / scalar
+// every thread owns a 4 x 4 register tile (8 shared loads per 16 DFMA; the earlier 1 x 4 / scalar
 // loops were bound by shared-memory wavefronts: 41 k cycles for one 96 x 96 x 32 product pair).
+// Tile = four CONSECUTIVE rows x four columns STRIDED by n/4 (tc, tc + n/4, ...), column tile fastest
+// over the threads: a warp then reads consecutive words of B (or consecutive rows of a transposed B,
+// odd leading dimension) and at most four distinct rows of A -- conflict free; 4 x 4 blocks of
+// consecutive columns put 24 threads on 4 banks (measured: no gain over the scalar loop).
 //   BT     : B is read transposed, B(q, c) = Bp[c * ldb + q]
-//   MODE 0 : C = sign * sum        MODE 1 : C -= sum, lower triangle of a square C only (SYRK)
-//   k range of a tile: [kbeg, min(K, kcap0 + kcap_row * (tile's last row + 1)))  -- triangular A
-// m, n multiples of 4.  All operands live in shared memory.
+//   MODE 0 : C = sign * sum (optionally also C2^T)   MODE 1 : C -= sum on the lower triangle (SYRK)
+//   k range of a tile: [kbeg_col ? tc : 0, min(K, kcap0 + kcap_row * (last row + 1)))  -- triangular
+//   operands (B(q, c) = 0 for q < c; A(r, q) = 0 for q > r).  m, n multiples of 4.
 template <bool BT, int MODE>
 __device__ __forceinline__ void smem_mm4(const double* __restrict__ Ap, int lda,
                                          const double* __restrict__ Bp, int ldb, double* __restrict__ Cp,
-                                         int ldc, int m, int n, int K, int kbeg_col, int kcap0,
-                                         int kcap_row, double sign, int tid) {
+                                         int ldc, double* __restrict__ C2, int ld2, int m, int n, int K,
+                                         int kbeg_col, int kcap0, int kcap_row, double sign, int tid) {
   const int tn = n >> 2, tm = m >> 2;
   for (int idx = tid; idx < tm * tn; idx += POTF2_THREADS) {
     const int tr = idx / tn, tc = idx - tr * tn;
-    if (MODE == 1 && tc > tr) continue;
-    const int r0 = tr << 2, c0 = tc << 2;
-    // triangular operands: B(q, c) = 0 for q < c (kbeg_col = 1) / A(r, q) = 0 for q > r (kcap_row = 1)
-    const int kb = kbeg_col ? c0 : 0;
+    const int r0 = tr << 2;
+    if (MODE == 1 && tc > r0 + 3) continue;
+    const int kb = kbeg_col ? tc : 0;
     const int ke = min(K, kcap0 + kcap_row * (r0 + 4));
     double acc[4][4];
 #pragma unroll
@@ -87,7 +91,7 @@ __device__ __forceinline__ void smem_mm4(const double* __restrict__ Ap, int lda,
 #pragma unroll
       for (int i = 0; i < 4; ++i) a[i] = Ap[(r0 + i) * lda + q];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = BT ? Bp[(c0 + j) * ldb + q] : Bp[q * ldb + c0 + j];
+      for (int j = 0; j < 4; ++j) b[j] = BT ? Bp[(tc + j * tn) * ldb + q] : Bp[q * ldb + tc + j * tn];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -97,9 +101,14 @@ __device__ __forceinline__ void smem_mm4(const double* __restrict__ Ap, int lda,
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        double* c = Cp + (r0 + i) * ldc + c0 + j;
-        if (MODE == 0) *c = sign * acc[i][j];
-        else if (c0 + j <= r0 + i) *c -= acc[i][j];
+        const int col = tc + j * tn;
+        double* c = Cp + (r0 + i) * ldc + col;
+        if (MODE == 0) {
+          *c = sign * acc[i][j];
+          if (C2) C2[col * ld2 + r0 + i] = sign * acc[i][j];
+        } else if (col <= r0 + i) {
+          *c -= acc[i][j];
+        }
       }
   }
 }
@@ -113,6 +122,7 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, in
   double* T = sm + NB * NBLD;              // [NB-SB][TLD]
   double* Dinv = T + (NB - SB) * TLD;      // [NB/SB][SB][TLD]: inverses of the diagonal 32x32 factors
   double* rdiag = Dinv + (NB / SB) * SB * TLD;  // [NB] reciprocals of the diagonal of L
+  double* XT = rdiag + NB;                 // [SB][XLD]: the current panel X, transposed
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   constexpr unsigned FULL = 0xffffffffu;
@@ -188,7 +198,8 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, in
     const int r0 = c0 + SB;
     const int nrows = NB - r0;
     // X = P inv(D)^T: X[r][c] = sum_{q <= c} P[r][q] Dk[c][q]  (Dk[c][q] = 0 for q > c: full k range)
-    smem_mm4<true, 0>(L + r0 * NBLD + c0, NBLD, Dk, TLD, T, TLD, nrows, SB, SB, 0, SB, 0, 1.0, tid);
+    smem_mm4<true, 0>(L + r0 * NBLD + c0, NBLD, Dk, TLD, T, TLD, XT, XLD, nrows, SB, SB, 0, SB, 0, 1.0,
+                      tid);
     __syncthreads();
     POTF2_TICK(3 + 3 * kb);
     // copy X into the factor and update the trailing block: L[r][c] -= X[r] . X[c] (lower part)
@@ -196,7 +207,8 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, in
       const int rr = idx >> 5, c = idx & 31;
       L[(r0 + rr) * NBLD + c0 + c] = T[rr * TLD + c];
     }
-    smem_mm4<true, 1>(T, TLD, T, TLD, L + r0 * NBLD + r0, NBLD, nrows, nrows, SB, 0, SB, 0, 1.0, tid);
+    smem_mm4<false, 1>(T, TLD, XT, XLD, L + r0 * NBLD + r0, NBLD, nullptr, 0, nrows, nrows, SB, 0, SB, 0,
+                       1.0, tid);
     __syncthreads();
     POTF2_TICK(4 + 3 * kb);
   }
@@ -218,11 +230,11 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, in
     const int c0 = j * SB, r0 = c0 + SB, nb = NB - r0;
     // T = W[below, below] L[below, j]  (W = the part of inv(L) already in place: lower triangular,
     // so row block r needs k <= r only), then W[below, j] = -T inv(D_j)  (Dj(q, c) = 0 for q < c)
-    smem_mm4<false, 0>(L + r0 * NBLD + r0, NBLD, L + r0 * NBLD + c0, NBLD, T, TLD, nb, SB, nb, 0, 0, 1,
-                       1.0, tid);
+    smem_mm4<false, 0>(L + r0 * NBLD + r0, NBLD, L + r0 * NBLD + c0, NBLD, T, TLD, nullptr, 0, nb, SB, nb,
+                       0, 0, 1, 1.0, tid);
     __syncthreads();
-    smem_mm4<false, 0>(T, TLD, Dinv + j * SB * TLD, TLD, L + r0 * NBLD + c0, NBLD, nb, SB, SB, 1, SB, 0,
-                       -1.0, tid);
+    smem_mm4<false, 0>(T, TLD, Dinv + j * SB * TLD, TLD, L + r0 * NBLD + c0, NBLD, nullptr, 0, nb, SB, SB,
+                       1, SB, 0, -1.0, tid);
     __syncthreads();
     POTF2_TICK(15 + (NB / SB - 2 - j));
   }

@@ -19,7 +19,8 @@ namespace pmr {
 namespace {
 
 constexpr int NB = 128;
-constexpr int NBLD = NB + 1;
+constexpr int NBLD = NB + 4;   // +4 doubles: the m8n8k4 fragment loads of the in-kernel DMMA products
+                               // (lane (g, t) -> row g, k t) fall on 16 distinct 8-byte banks per half warp
 static thread_local bool g_lookahead = true;
 static thread_local bool g_transposed_panels = false;
 
@@ -43,7 +44,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // K): 99 us before this layout (ncu: 7.3 barrier-stall cycles per issue, three warps doing the
 // substitution while thirteen waited).
 constexpr int SB = 32;
-constexpr int TLD = SB + 1;
+constexpr int TLD = SB + 4;
 constexpr int POTF2_THREADS = 512;
 // development aid: when set (pmr_debug_potf2_timing), thread 0 of CTA 0 stores clock64() at the phase
 // boundaries of the diagonal-block kernel (tools/potf2_phases.py prints the differences)
@@ -52,64 +53,56 @@ __device__ long long* g_potf2_clock = nullptr;
   do {                                                                            \
     if (tid == 0 && blockIdx.x == 0 && g_potf2_clock) g_potf2_clock[slot] = clock64(); \
   } while (0)
-constexpr int XLD = NB - SB + 1;   // row of the transposed panel XT[32][96]
-// L [NB][NBLD] + T [NB-SB][TLD] + Dinv [NB/SB][SB][TLD] + rdiag [NB] + XT [SB][XLD]
+// L [NB][NBLD] + T [NB-SB][TLD] + Dinv [NB/SB][SB][TLD] + rdiag [NB]
 constexpr size_t POTF2_SMEM =
-    sizeof(double) * (NB * NBLD + (NB - SB) * TLD + (NB / SB) * SB * TLD + NB + SB * XLD);
+    sizeof(double) * (NB * NBLD + (NB - SB) * TLD + (NB / SB) * SB * TLD + NB);
 
-// Shared-memory micro GEMM of the diagonal-block kernel: C(m x n) (op)= sign * A(m x K) B(K x n),
-// every thread owns a 4 x 4 register tile (8 shared loads per 16 DFMA; the earlier 1 x 4 / scalar
-// loops were bound by shared-memory wavefronts: 41 k cycles for one 96 x 96 x 32 product pair).
-// Tile = four CONSECUTIVE rows x four columns STRIDED by n/4 (tc, tc + n/4, ...), column tile fastest
-// over the threads: a warp then reads consecutive words of B (or consecutive rows of a transposed B,
-// odd leading dimension) and at most four distinct rows of A -- conflict free; 4 x 4 blocks of
-// consecutive columns put 24 threads on 4 banks (measured: no gain over the scalar loop).
+__device__ __forceinline__ void potf2_dmma(double (&c)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c[0]), "+d"(c[1])
+      : "d"(a), "d"(b));
+}
+
+// Shared-memory micro GEMM of the diagonal-block kernel on the FP64 TENSOR pipe:
+// C(m x n) (op)= sign * A(m x K) B(K x n), one 8 x 8 output tile per warp and pass, DMMA.8x8x4 with
+// the fragments read straight from shared memory (one LDS.64 per operand and DMMA; leading
+// dimensions = 4 mod 16 doubles make them conflict free).  On B200 the vector FP64 pipe issues a
+// warp DFMA every 4 cycles per sub-partition, the tensor pipe does 256 FMA in 16: scalar and
+// register-tiled DFMA versions of these products measured 41 k / 13 k cycles for the largest pair.
 //   BT     : B is read transposed, B(q, c) = Bp[c * ldb + q]
-//   MODE 0 : C = sign * sum (optionally also C2^T)   MODE 1 : C -= sum on the lower triangle (SYRK)
-//   k range of a tile: [kbeg_col ? tc : 0, min(K, kcap0 + kcap_row * (last row + 1)))  -- triangular
-//   operands (B(q, c) = 0 for q < c; A(r, q) = 0 for q > r).  m, n multiples of 4.
+//   MODE 0 : C = sign * sum          MODE 1 : C -= sum on the lower triangle of a square C (SYRK)
+//   kbeg_col: B(q, c) = 0 for q < c (k loop starts at the column tile); kcap_row: A(r, q) = 0 for q > r
+//   (k loop ends with the row tile).  m, n multiples of 8, K of 4.
 template <bool BT, int MODE>
-__device__ __forceinline__ void smem_mm4(const double* __restrict__ Ap, int lda,
+__device__ __forceinline__ void smem_mm8(const double* __restrict__ Ap, int lda,
                                          const double* __restrict__ Bp, int ldb, double* __restrict__ Cp,
-                                         int ldc, double* __restrict__ C2, int ld2, int m, int n, int K,
-                                         int kbeg_col, int kcap0, int kcap_row, double sign, int tid) {
-  const int tn = n >> 2, tm = m >> 2;
-  for (int idx = tid; idx < tm * tn; idx += POTF2_THREADS) {
-    const int tr = idx / tn, tc = idx - tr * tn;
-    const int r0 = tr << 2;
-    if (MODE == 1 && tc > r0 + 3) continue;
-    const int kb = kbeg_col ? tc : 0;
-    const int ke = min(K, kcap0 + kcap_row * (r0 + 4));
-    double acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+                                         int ldc, int m, int n, int K, int kbeg_col, int kcap_row,
+                                         double sign, int warp, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const int tn = n >> 3, tm = m >> 3;
+  for (int tile = warp; tile < tm * tn; tile += POTF2_THREADS / 32) {
+    const int tr = tile / tn, tc = tile - tr * tn;
+    if (MODE == 1 && tc > tr) continue;
+    const int r0 = tr << 3, c0 = tc << 3;
+    const int kb = kbeg_col ? c0 : 0;
+    const int ke = kcap_row ? min(K, r0 + 8) : K;
+    double acc[2] = {0.0, 0.0};
+    const double* ap = Ap + (r0 + g) * lda + t;
+    const double* bp = BT ? Bp + (c0 + g) * ldb + t : Bp + t * ldb + c0 + g;
 #pragma unroll 4
-    for (int q = kb; q < ke; ++q) {
-      double a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = Ap[(r0 + i) * lda + q];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = BT ? Bp[(tc + j * tn) * ldb + q] : Bp[q * ldb + tc + j * tn];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    for (int q0 = kb; q0 < ke; q0 += 4) {
+      const double a = ap[q0];
+      const double b = BT ? bp[q0] : bp[q0 * ldb];
+      potf2_dmma(acc, a, b);
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int col = tc + j * tn;
-        double* c = Cp + (r0 + i) * ldc + col;
-        if (MODE == 0) {
-          *c = sign * acc[i][j];
-          if (C2) C2[col * ld2 + r0 + i] = sign * acc[i][j];
-        } else if (col <= r0 + i) {
-          *c -= acc[i][j];
-        }
-      }
+    double* c = Cp + (r0 + g) * ldc + c0 + 2 * t;
+    if (MODE == 0) {
+      c[0] = sign * acc[0];
+      c[1] = sign * acc[1];
+    } else {
+      if (c0 + 2 * t <= r0 + g) c[0] -= acc[0];
+      if (c0 + 2 * t + 1 <= r0 + g) c[1] -= acc[1];
+    }
   }
 }
 
@@ -122,7 +115,6 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, in
   double* T = sm + NB * NBLD;              // [NB-SB][TLD]
   double* Dinv = T + (NB - SB) * TLD;      // [NB/SB][SB][TLD]: inverses of the diagonal 32x32 factors
   double* rdiag = Dinv + (NB / SB) * SB * TLD;  // [NB] reciprocals of the diagonal of L
-  double* XT = rdiag + NB;                 // [SB][XLD]: the current panel X, transposed
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   constexpr unsigned FULL = 0xffffffffu;
@@ -198,8 +190,7 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, in
     const int r0 = c0 + SB;
     const int nrows = NB - r0;
     // X = P inv(D)^T: X[r][c] = sum_{q <= c} P[r][q] Dk[c][q]  (Dk[c][q] = 0 for q > c: full k range)
-    smem_mm4<true, 0>(L + r0 * NBLD + c0, NBLD, Dk, TLD, T, TLD, XT, XLD, nrows, SB, SB, 0, SB, 0, 1.0,
-                      tid);
+    smem_mm8<true, 0>(L + r0 * NBLD + c0, NBLD, Dk, TLD, T, TLD, nrows, SB, SB, 0, 0, 1.0, warp, lane);
     __syncthreads();
     POTF2_TICK(3 + 3 * kb);
     // copy X into the factor and update the trailing block: L[r][c] -= X[r] . X[c] (lower part)
@@ -207,8 +198,7 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, in
       const int rr = idx >> 5, c = idx & 31;
       L[(r0 + rr) * NBLD + c0 + c] = T[rr * TLD + c];
     }
-    smem_mm4<false, 1>(T, TLD, XT, XLD, L + r0 * NBLD + r0, NBLD, nullptr, 0, nrows, nrows, SB, 0, SB, 0,
-                       1.0, tid);
+    smem_mm8<true, 1>(T, TLD, T, TLD, L + r0 * NBLD + r0, NBLD, nrows, nrows, SB, 0, 0, 1.0, warp, lane);
     __syncthreads();
     POTF2_TICK(4 + 3 * kb);
   }
@@ -230,11 +220,11 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, long long stride_a, in
     const int c0 = j * SB, r0 = c0 + SB, nb = NB - r0;
     // T = W[below, below] L[below, j]  (W = the part of inv(L) already in place: lower triangular,
     // so row block r needs k <= r only), then W[below, j] = -T inv(D_j)  (Dj(q, c) = 0 for q < c)
-    smem_mm4<false, 0>(L + r0 * NBLD + r0, NBLD, L + r0 * NBLD + c0, NBLD, T, TLD, nullptr, 0, nb, SB, nb,
-                       0, 0, 1, 1.0, tid);
+    smem_mm8<false, 0>(L + r0 * NBLD + r0, NBLD, L + r0 * NBLD + c0, NBLD, T, TLD, nb, SB, nb, 0, 1, 1.0,
+                       warp, lane);
     __syncthreads();
-    smem_mm4<false, 0>(T, TLD, Dinv + j * SB * TLD, TLD, L + r0 * NBLD + c0, NBLD, nullptr, 0, nb, SB, SB,
-                       1, SB, 0, -1.0, tid);
+    smem_mm8<false, 0>(T, TLD, Dinv + j * SB * TLD, TLD, L + r0 * NBLD + c0, NBLD, nb, SB, SB, 1, 0, -1.0,
+                       warp, lane);
     __syncthreads();
     POTF2_TICK(15 + (NB / SB - 2 - j));
   }

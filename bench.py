@@ -668,7 +668,7 @@ def bench_workload(w, args, rank, world, local, torch, peak64, do_e2e=True, do_c
         if prof:
             top = max(prof, key=lambda k: prof[k]["ms"])
             a = prof[top]
-            tr = ncu_traffic(f"{w['key']}:{top}")
+            tr = ncu_traffic(f"{w['key']}:n{world}:{top}")
             roofline = {"bound": "tensor", "kernel": f"dgemm kernel class [{top}]",
                         "achieved": a["tflops"], "peak": peak64, "unit": "TFLOP/s",
                         "frac": a["tflops"] / peak64 if peak64 else None,

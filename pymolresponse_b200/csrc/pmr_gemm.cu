@@ -1030,7 +1030,13 @@ int gemm(const pmr_gemm_t& g0, cudaStream_t st) {
       g.C2 == nullptr) {
     int r;
     if (bn == 128) r = launch_tma_cfg<128, 128, 32, 32, 4, 1>(a, g.batch1, g.batch2, st);
-    else if (bn == 64) r = launch_tma_cfg<128, 64, 32, 32, TMA_STAGES_64, 2>(a, g.batch1, g.batch2, st);
+    else if (bn == 64) {
+      // ring depth: 4 x 24 KiB per CTA by default; PMR_GEMM_TMA_STAGES = 3 / 6 for A/B runs
+      static const int stages = [] { const char* e = getenv("PMR_GEMM_TMA_STAGES"); return e ? atoi(e) : TMA_STAGES_64; }();
+      if (stages == 3) r = launch_tma_cfg<128, 64, 32, 32, 3, 2>(a, g.batch1, g.batch2, st);
+      else if (stages == 6) r = launch_tma_cfg<128, 64, 32, 32, 6, 1>(a, g.batch1, g.batch2, st);
+      else r = launch_tma_cfg<128, 64, 32, 32, TMA_STAGES_64, 2>(a, g.batch1, g.batch2, st);
+    }
     else r = launch_tma_cfg<128, 32, 32, 32, 4, 2>(a, g.batch1, g.batch2, st);
     if (r <= 0) return r;   // > 0: not expressible as a tensor map, fall through
   }

@@ -33,7 +33,7 @@ namespace {
 
 constexpr int BK = 16;
 constexpr int PAD = 4;
-constexpr int TMA_STAGES_64 = 4;  // 4 x 24 KiB per CTA, two CTAs per SM
+constexpr int TMA_STAGES_64 = 3;  // 3 x 24 KiB per CTA, two CTAs per SM (A/B on the config-5 step: 4 stages 306.4 ms, 3 stages 304.4)
 
 struct GemmArgs {
   int M, N, K;

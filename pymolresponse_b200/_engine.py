@@ -476,7 +476,7 @@ class HalfSizeSystem:
                 Kinv[:, lo:hi].copy_(gathered[:, src0:src0 + (hi - lo)])
         return Kinv
 
-    def _kinv_distributed_tree(self, Kfac, dinvK):
+    def _kinv_distributed_tree(self, Kfac, dinvK, clock=None):
         """Small-N variant of :meth:`_kinv_distributed`: every rank inverts the factor itself
         (pmr_trtri_tree) and forms only its column blocks of Z^T Z; the blocks -- 2 * world of them,
         cut at multiples of 128, rank r taking blocks r and 2*world-1-r so that the triangular work
@@ -490,7 +490,9 @@ class HalfSizeSystem:
         cuts = [min(N, 128 * ((nb128 * b) // nblocks)) for b in range(nblocks)] + [N]
         bounds = [(cuts[b], cuts[b + 1]) for b in range(nblocks)]
         wmax = max(hi - lo for lo, hi in bounds)
+        mark = clock.mark if clock is not None else (lambda name: None)
         Z = trtri_tree(Kfac, dinvK)
+        mark("K_inverse.trtri")
         local = nv.zeros(N, 2 * wmax)
         full = nv.empty(N, N)                      # column blocks land here at their own offsets
         for k, b in enumerate((rank, nblocks - 1 - rank)):
@@ -500,7 +502,9 @@ class HalfSizeSystem:
                 gram_lower_cols(Z, full, lo, hi - lo)
                 local[:, k * wmax:k * wmax + (hi - lo)].copy_(full[:, lo:hi])
         del Z
+        mark("K_inverse.gram_columns")
         gathered = pd.allgather_columns(local, 2 * wmax * world)
+        mark("K_inverse.allgather")
         for r in range(world):
             for k, b in enumerate((r, nblocks - 1 - r)):
                 lo, hi = bounds[b]
@@ -508,7 +512,7 @@ class HalfSizeSystem:
                 full[:, lo:hi].copy_(gathered[:, src0:src0 + (hi - lo)])
         return full
 
-    def _kinv_distributed(self, Kfac, dinvK):
+    def _kinv_distributed(self, Kfac, dinvK, clock=None):
         """K^-1 with the work split over the ranks: every rank solves K X = E_J for its own identity
         columns against the shared factor and the column blocks are all-gathered (N^2 * 8 bytes in
         total over NVLink).  Only the lower triangle of the result is filled (its one consumer, the
@@ -521,7 +525,7 @@ class HalfSizeSystem:
         rank, world = pd.rank_world()
         N = self.N
         if N <= KINV_TREE_MAX_N and N >= 128 * 2 * world:
-            return self._kinv_distributed_tree(Kfac, dinvK)
+            return self._kinv_distributed_tree(Kfac, dinvK, clock)
         nblocks = 2 * world
         bounds = [pd.shard_range(N, b, nblocks) for b in range(nblocks)]
         mine = [bounds[rank], bounds[nblocks - 1 - rank]]
@@ -589,7 +593,7 @@ class HalfSizeSystem:
             clock.stage("K_inverse")
             if (share_kinv or any_dyn) and Kinv is None:
                 if share_kinv:
-                    Kinv = self._kinv_distributed(Kfac, dinvK)
+                    Kinv = self._kinv_distributed(Kfac, dinvK, clock)
                     self.stats["potri_shared"] = self.stats.get("potri_shared", 0) + 1
                 else:
                     Kinv = potri_lower(Kfac, dinvK)

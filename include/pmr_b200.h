@@ -171,9 +171,6 @@ void pmr_set_lookahead(int on);
 /* Development aid: while a device buffer (>= 19 long long) is set, the diagonal-block kernel of the
  * Cholesky stores clock64() at its phase boundaries (tools/potf2_phases.py); NULL switches it off. */
 int pmr_debug_potf2_timing(long long* device_buffer);
-/* pmr_potrf keeps a transposed copy of the current 512-column panel so its rank-k updates run on the
- * TMA-bulk GEMM; switch off to use the in-place row-major panel with the cp.async GEMM (A/B test). */
-void pmr_set_transposed_panels(int on);
 int pmr_potrf(double* A, int N, long long lda, int batch, long long stride_a, double* dinv,
               int* info /* device, batch ints */, void* stream);
 /* Same factorisation of the leading N x N block of a (rows x N) matrix, rows >= N: the rows below
@@ -256,6 +253,21 @@ int pmr_contract_results(const double* P, int nP, long long ldp, const double* R
  *   xy[c,0:nov] = (p+m)/2, xy[c,nov:2nov] = (p-m)/2   (supervector [X;Y], solvers.py:418-425) */
 int pmr_pm_to_xy(const double* p, const double* m, int ncomp, long long nov, long long ldp,
                  long long ldm, double* xy, long long ldxy, void* stream);
+/* Packing kernels of the half-size solver (right-hand sides [g; s g] of solvers.py:401-425 for all
+ * frequencies and operator components at once; host arrays: imag_col[c] = -1 for a real operator,
+ * else the column of T = K^-1 g; w = the frequencies of this call, <= 64 each):
+ *   pmr_solve_pack_rhs  out[q][c][k] = 2 g[c][k] | 2 w_q T[k][imag_col[c]] | 0 (padding), written as
+ *                       the extra ROWS of the matrices pmr_potrf_rows factorises (stride_q apart)
+ *   pmr_solve_pack_p    prhs[k][q*ncols + c] = w_q m[q][k][c] + (imaginary ? 2 g[c][k] : 0)
+ *   pmr_solve_xy        xy[(q,c)] = [(p + m)/2 ; (p - m)/2], p[k][q*ncols + c] (or NULL), m[q][k][c] */
+int pmr_solve_pack_rhs(const double* g, long long ldg, const double* T, int nimag,
+                       const int* imag_col_host, int ncols, int ncp, const double* w_host, int nfc,
+                       long long N, double* out, long long stride_q, void* stream);
+int pmr_solve_pack_p(const double* m, int ncp, const double* g, long long ldg,
+                     const int* imag_col_host, int ncols, const double* w_host, int nfc, long long N,
+                     double* prhs, void* stream);
+int pmr_solve_xy(const double* p, const double* m, int ncp, int ncols, int nfc, long long N,
+                 double* xy, void* stream);
 /* y = a*x + b*y on ncols x nrows strided blocks */
 int pmr_axpby(long long rows, long long cols, double a, const double* x, long long ldx, double b,
               double* y, long long ldy, void* stream);
@@ -328,7 +340,6 @@ int pmr_iter_update_d(double* d, const double* y, const double* rho_new, const d
  *                        host: full C-order (n,n,n,n) array (pinned for an asynchronous copy)
  *   pmr_eri_complete_s8  fills the rest of the tensor in place from the uploaded part
  * ------------------------------------------------------------------------------------------ */
-void pmr_set_upload_streams(int count); /* side streams the layout-1 DMAs are spread over (1..8) */
 long long pmr_eri_s8_bytes(int n, int layout);
 int pmr_eri_upload_s8(const double* host, double* dev, int n, int layout, void* stream);
 int pmr_eri_complete_s8(double* dev, int n, int layout, void* stream);

@@ -552,6 +552,17 @@ class HalfSizeSystem:
         on the device and are read ONCE, after everything has been queued."""
         N = self.N
         nf, ncols = len(frequencies), int(g_rows.shape[0])
+        if ncols > 64:
+            # the packing kernels take <= 64 right-hand-side columns a call: solve them in groups
+            # (the factor of K and K^-1 are computed once and reused)
+            torch = nv.torch_mod()
+            parts, bad = [], set()
+            for c0 in range(0, ncols, 64):
+                xy_g, bad_g = self.solve(g_rows[c0:c0 + 64].contiguous(), signs[c0:c0 + 64], frequencies,
+                                         distributed=distributed, global_frequencies=global_frequencies)
+                parts.append(xy_g)
+                bad |= bad_g
+            return torch.cat(parts, dim=1), bad
         xy = nv.zeros(nf, ncols, 2 * N)
         if N == 0 or ncols == 0:
             return xy, set()
@@ -606,8 +617,12 @@ class HalfSizeSystem:
         if nf > 0 and not self._K_bad and any_dyn and imag_cols:
             T = nv.matmul(Kinv, G[:, imag_cols].contiguous())  # T = K^-1 g for the imaginary columns
 
+        lib = nv.lib()
+        null = C.c_void_p(0)
+        imag_col_arr = (C.c_int * max(1, ncols))(*[imag_cols.index(c) if c in imag_cols else -1
+                                                   for c in range(ncols)])
         if nf > 0 and not self._K_bad:
-            step = self._chunk(nf)
+            step = min(self._chunk(nf), 64)     # the packing kernels take <= 64 frequencies a call
             for f0 in range(0, nf, step):
                 fs = list(range(f0, min(nf, f0 + step)))
                 ws = [freqs[f] for f in fs]
@@ -619,19 +634,17 @@ class HalfSizeSystem:
                 # under 10); the padding column stays zero
                 ncp = ncols + (ncols & 1)
                 clock.stage("shifted_combine")
-                # right-hand sides of the m equations, one per ROW: (nfc, ncp, N)
-                rhs_rows = nv.zeros(nfc, ncp, N)
-                if real_cols:
-                    rhs_rows[:, real_cols, :] = 2.0 * g_rows[real_cols]
-                if imag_cols and T is not None:
-                    wv = torch.tensor([2.0 * w for w in ws], dtype=torch.float64, device=G.device)
-                    rhs_rows[:, imag_cols, :] = wv[:, None, None] * T.t()[None, :, :]
+                wsub = ws
                 if need_m:
-                    # S(w) with the right-hand sides appended as extra rows: the factorisation
-                    # forward-substitutes them on the way (pmr_potrf_rows), only L^T m = y remains
+                    # S(w) with the right-hand sides appended as extra rows (one kernel packs them):
+                    # the factorisation forward-substitutes them on the way (pmr_potrf_rows), only
+                    # L^T m = y remains
                     S = shifted_combine(self.M, Kinv if any_dyn else None, [0.0] * nfc,
                                         [-(w * w) for w in ws], extra_rows=ncp)
-                    S[:, N:, :] = rhs_rows
+                    nv.check(lib.pmr_solve_pack_rhs(
+                        nv.ptr(g_rows), int(g_rows.stride(0)), nv.ptr(T) if T is not None else null,
+                        len(imag_cols), imag_col_arr, ncols, ncp, _darr(wsub), nfc, N,
+                        nv.ptr(S, N * N), (N + ncp) * N, nv.stream_ptr()))
                     clock.mark("shifted_combine")
                     clock.stage("potrf_S")
                     dinvS, infoS = potrf_rows(S, N, batch=nfc)
@@ -640,33 +653,26 @@ class HalfSizeSystem:
                     self.stats["potrf_batch"] += nfc
                     infos.append((infoS, fs))
                     Y = S[:, N:, :].transpose(1, 2).contiguous()            # (nfc, N, ncp)
-                    rhs_pad = potrs_backward(S, N, dinvS, Y, batch=nfc)     # m_f
+                    m_sol = potrs_backward(S, N, dinvS, Y, batch=nfc)       # m_f, (nfc, N, ncp)
                 else:
                     S = dinvS = None
-                    rhs_pad = nv.zeros(nfc, N, ncp)
-                rhs_m = rhs_pad[:, :, :ncols]
+                    m_sol = nv.zeros(nfc, N, ncp)
                 # p_f = K^-1 ((1+s) g + w m_f), every frequency a block of columns
                 need_p = bool(imag_cols) or any(w != 0.0 for w in ws)
                 p_all = None
                 if need_p:
-                    wvec = torch.tensor(ws, dtype=torch.float64, device=rhs_m.device)
-                    p_all = nv.empty(N, nfc * ncols)
-                    p_view = p_all.view(N, nfc, ncols)
-                    p_view.copy_((rhs_m * wvec[:, None, None]).permute(1, 0, 2))
-                    if imag_cols:
-                        p_view[:, :, imag_cols] += 2.0 * G[:, None, imag_cols]
+                    p_rhs = nv.empty(N, nfc * ncols)
+                    nv.check(lib.pmr_solve_pack_p(nv.ptr(m_sol), ncp, nv.ptr(g_rows),
+                                                  int(g_rows.stride(0)), imag_col_arr, ncols,
+                                                  _darr(wsub), nfc, N, nv.ptr(p_rhs), nv.stream_ptr()))
                     if Kinv is not None:
-                        p_all = nv.matmul(Kinv, p_all)
+                        p_all = nv.matmul(Kinv, p_rhs)
                     else:
-                        potrs(Kfac, dinvK, p_all)
-                m_rows = rhs_m.transpose(1, 2).contiguous()                    # (nfc, ncols, N)
-                p_rows = (p_all.view(N, nfc, ncols).permute(1, 2, 0).contiguous()
-                          if p_all is not None else None)
+                        p_all = potrs(Kfac, dinvK, p_rhs)
                 # xy[f0 : f0 + nfc] is one contiguous (nfc * ncols, 2N) block
-                nv.check(nv.lib().pmr_pm_to_xy(
-                    nv.ptr(p_rows) if p_rows is not None else C.c_void_p(0), nv.ptr(m_rows),
-                    nfc * ncols, N, N, N, nv.ptr(xy[f0]), 2 * N, nv.stream_ptr()))
-                del S, dinvS, rhs_m, rhs_pad, p_all
+                nv.check(lib.pmr_solve_xy(nv.ptr(p_all) if p_all is not None else null, nv.ptr(m_sol),
+                                          ncp, ncols, nfc, N, nv.ptr(xy[f0]), nv.stream_ptr()))
+                del S, dinvS, m_sol, p_all
                 clock.mark("solves")
 
         # ---- one host read of every pivot-failure word

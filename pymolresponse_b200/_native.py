@@ -98,7 +98,6 @@ SYMBOLS = {
     "pmr_potrf_dinv_doubles": (c_ll, [C.c_int]),
     "pmr_set_lookahead": (None, [C.c_int]),
     "pmr_debug_potf2_timing": (C.c_int, [c_dp]),
-    "pmr_set_transposed_panels": (None, [C.c_int]),
     "pmr_potrf": (C.c_int, [c_dp, C.c_int, c_ll, C.c_int, c_ll, c_dp, c_dp, c_dp]),
     "pmr_potrf_rows": (C.c_int, [c_dp, C.c_int, C.c_int, c_ll, C.c_int, c_ll, c_dp, c_dp, c_dp]),
     "pmr_potrs_ex": (C.c_int, [c_dp, C.c_int, c_ll, C.c_int, c_ll, c_dp, c_dp, C.c_int, c_ll, c_ll,
@@ -126,7 +125,6 @@ SYMBOLS = {
     "pmr_zero_upper": (C.c_int, [c_dp, C.c_int, c_ll, c_dp]),
     "pmr_scale_columns": (C.c_int, [c_dp, C.c_int, C.c_int, c_ll, c_dp, c_dp]),
     "pmr_normalize_columns": (C.c_int, [c_dp, C.c_int, C.c_int, c_ll, c_dp]),
-    "pmr_set_upload_streams": (None, [C.c_int]),
     "pmr_eri_s8_bytes": (c_ll, [C.c_int, C.c_int]),
     "pmr_eri_upload_s8": (C.c_int, [c_dp, c_dp, C.c_int, C.c_int, c_dp]),
     "pmr_eri_complete_s8": (C.c_int, [c_dp, C.c_int, C.c_int, c_dp]),
@@ -139,6 +137,11 @@ SYMBOLS = {
     "pmr_contract_results": (C.c_int, [c_dp, C.c_int, c_ll, c_dp, C.c_int, c_ll, c_ll, C.c_double,
                                        c_dp, c_dp, c_dp]),
     "pmr_pm_to_xy": (C.c_int, [c_dp, c_dp, C.c_int, c_ll, c_ll, c_ll, c_dp, c_ll, c_dp]),
+    "pmr_solve_pack_rhs": (C.c_int, [c_dp, c_ll, c_dp, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int,
+                                     C.POINTER(C.c_double), C.c_int, c_ll, c_dp, c_ll, c_dp]),
+    "pmr_solve_pack_p": (C.c_int, [c_dp, C.c_int, c_dp, c_ll, C.POINTER(C.c_int), C.c_int,
+                                   C.POINTER(C.c_double), C.c_int, c_ll, c_dp, c_dp]),
+    "pmr_solve_xy": (C.c_int, [c_dp, c_dp, C.c_int, C.c_int, C.c_int, c_ll, c_dp, c_dp]),
     "pmr_axpby": (C.c_int, [c_ll, c_ll, C.c_double, c_dp, c_ll, C.c_double, c_dp, c_ll, c_dp]),
     "pmr_uncoupled_divide": (C.c_int, [c_dp, C.c_int, c_ll, c_dp, C.c_double, c_dp, c_dp]),
     "pmr_jk_contract": (C.c_int, [c_dp, C.c_int, c_dp, C.c_int, c_dp, c_dp, c_dp]),

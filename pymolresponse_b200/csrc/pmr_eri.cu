@@ -203,10 +203,10 @@ extern "C" long long pmr_eri_s8_bytes(int n, int layout) {
 
 // Narrow strided rows cost a fixed time per row on top of the bytes (measured on B200, n = 256:
 // 5.79 GB in 160 ms = 36 GB/s against 55 GB/s for long runs).  The DMAs can be spread over side
-// streams (pmr_set_upload_streams); measured 1..8 streams: no gain, the limit is the PCIe read
+// streams measured 1..8 streams: no gain, the limit is the PCIe read
 // of short host rows, not the copy engine -- so the default is the caller's stream alone.
 constexpr int kMaxUploadStreams = 8;
-static int g_upload_streams = 1;
+static const int g_upload_streams = 1;  // (1..8 side streams measured: no gain, the PCIe read is the limit)
 
 struct UploadStreams {
   cudaStream_t s[kMaxUploadStreams] = {};
@@ -228,9 +228,6 @@ static int upload_streams_ready() {
   return 0;
 }
 
-extern "C" void pmr_set_upload_streams(int count) {
-  g_upload_streams = std::max(1, std::min(kMaxUploadStreams, count));
-}
 
 extern "C" int pmr_eri_upload_s8(const double* host, double* dev, int n, int layout, void* stream) {
   cudaStream_t st = as_stream(stream);

@@ -22,7 +22,6 @@ constexpr int NB = 128;
 constexpr int NBLD = NB + 4;   // +4 doubles: the m8n8k4 fragment loads of the in-kernel DMMA products
                                // (lane (g, t) -> row g, k t) fall on 16 distinct 8-byte banks per half warp
 static thread_local bool g_lookahead = true;
-static thread_local bool g_transposed_panels = false;
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -441,7 +440,6 @@ extern "C" int pmr_debug_potf2_timing(long long* device_buffer /* >= 19 slots, o
 }
 
 extern "C" void pmr_set_lookahead(int on) { g_lookahead = on != 0; }
-extern "C" void pmr_set_transposed_panels(int on) { g_transposed_panels = on != 0; }
 
 extern "C" long long pmr_potrf_dinv_doubles(int N) {
   const long long nblk = (N + NB - 1) / NB;
@@ -495,30 +493,6 @@ extern "C" int pmr_potrf_rows(double* A, int N, int rows, long long lda, int bat
   const bool lookahead = g_lookahead && N > 2 * NBO;
   cudaStream_t sp = lookahead ? sa : st;  // stream of the panel work
 
-  // EXPERIMENT, off by default (pmr_set_transposed_panels): transposed panel store
-  // PT[J%2][k][row] (k < 512) written by the panel solve next to the in-place result, so that the
-  // rank-128 / rank-512 updates read both operands contiguous along m/n and run on the TMA-bulk +
-  // mbarrier GEMM.  Measured on B200 it does not pay: at K = 512 the per-tile costs dominate and the
-  // bulk kernel reaches 29.5 TFLOP/s on these lower-triangular updates against 31 for the
-  // k-contiguous cp.async kernel (the bulk kernel's 35 TFLOP/s needs long k loops).
-  const long long ldp = ((long long)N + 15) & ~15LL;
-  const long long pt_one = (long long)NBO * ldp;   // one buffer of one matrix
-  const long long pt_mat = 2 * pt_one;             // double-buffered (look-ahead)
-  double* PT = nullptr;
-  const bool use_pt = g_transposed_panels && N > NB && rows == N;
-  if (use_pt) {
-    static thread_local bool pool_kept = false;
-    if (!pool_kept) {  // keep freed blocks in the stream-ordered pool instead of returning them to the OS
-      int dev = 0;
-      cudaMemPool_t pool;
-      unsigned long long keep = ~0ULL;
-      PMR_CHECK_CUDA(cudaGetDevice(&dev));
-      PMR_CHECK_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-      PMR_CHECK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-      pool_kept = true;
-    }
-    PMR_CHECK_CUDA(cudaMallocAsync(&PT, sizeof(double) * pt_mat * batch, st));
-  }
   if (lookahead) PMR_CHECK_CUDA(cudaStreamWaitEvent(sa, new_event(st), 0));
   cudaEvent_t u2_done_prev = nullptr;  // U2 of block J-1 finished (on st)
 
@@ -527,17 +501,11 @@ extern "C" int pmr_potrf_rows(double* A, int N, int rows, long long lda, int bat
   auto syrk = [&](int jblk, int j0, int koff, int kw, int r0, int nrows, int c0, int ncols,
                   cudaStream_t s) -> int {
     double* Cp = A + (long long)r0 * lda + c0;
-    pmr_gemm_t t;
-    if (use_pt) {
-      const double* pt = PT + (long long)(jblk & 1) * pt_one + (long long)koff * ldp;
-      t = make_gemm(nrows, ncols, kw, -1.0, pt + r0, 1, ldp, pt + c0, ldp, 1, 1.0, Cp, lda, 1);
-      t.a_b1 = pt_mat; t.b_b1 = pt_mat;
-    } else {
-      const double* Pr = A + (long long)r0 * lda + j0 + koff;
-      const double* Pc = A + (long long)c0 * lda + j0 + koff;
-      t = make_gemm(nrows, ncols, kw, -1.0, Pr, lda, 1, Pc, 1, lda, 1.0, Cp, lda, 1);
-      t.a_b1 = stride_a; t.b_b1 = stride_a;
-    }
+    const double* Pr = A + (long long)r0 * lda + j0 + koff;
+    const double* Pc = A + (long long)c0 * lda + j0 + koff;
+    pmr_gemm_t t = make_gemm(nrows, ncols, kw, -1.0, Pr, lda, 1, Pc, 1, lda, 1.0, Cp, lda, 1);
+    t.a_b1 = stride_a; t.b_b1 = stride_a;
+    (void)jblk;
     t.batch1 = batch; t.c_b1 = stride_a;
     t.flags = PMR_GEMM_LOWER;
     return gemm(t, s);
@@ -553,6 +521,11 @@ extern "C" int pmr_potrf_rows(double* A, int N, int rows, long long lda, int bat
       const int rest = rows - k0 - jb;   // rows below the diagonal block (extra rows included)
       double* Akk = A + (long long)k0 * lda + k0;
       double* dk = dinv + (long long)kb * NB * NB;
+      // inside the outer block the updates are LEFT-looking: this 128-wide block column receives the
+      // contributions of all earlier panels of the block in ONE GEMM with k = k0 - j0 (128, 256,
+      // 384) just before it is factorised, instead of three rank-128 updates spread over the panels
+      // (same flops; the short-k launches were the slow 11 % of the trailing-update class)
+      if (k0 > j0) PMR_TRY(syrk(jblk, j0, 0, k0 - j0, k0, rows - k0, k0, jb, sp));
       potf2_trtri_kernel<<<batch, POTF2_THREADS, smem, sp>>>(Akk, lda, stride_a, jb, dk, dstride,
                                                              info, k0);
       PMR_CHECK_LAUNCH("potf2_trtri_kernel");
@@ -561,14 +534,7 @@ extern "C" int pmr_potrf_rows(double* A, int N, int rows, long long lda, int bat
         pmr_gemm_t g = make_gemm(rest, jb, jb, 1.0, A21, lda, 1, dk, 1, NB, 0.0, A21, lda, 1);
         g.batch1 = batch; g.a_b1 = stride_a; g.b_b1 = dstride; g.c_b1 = stride_a;
         g.flags = PMR_GEMM_C_ALIASES_A;
-        if (use_pt) {
-          g.C2 = PT + (long long)(jblk & 1) * pt_one + (long long)(k0 - j0) * ldp + (k0 + jb);
-          g.c2_sm = 1; g.c2_sn = ldp; g.c2_b1 = pt_mat;
-        }
         PMR_TRY(gemm(g, sp));
-        const int ncols = jend - (k0 + jb);  // columns of the outer block still to be updated
-        if (ncols > 0)
-          PMR_TRY(syrk(jblk, j0, k0 - j0, jb, k0 + jb, rest, k0 + jb, ncols, sp));
       }
     }
     const int rest = N - jend;          // columns still to be updated
@@ -591,7 +557,6 @@ extern "C" int pmr_potrf_rows(double* A, int N, int rows, long long lda, int bat
     u2_done_prev = new_event(st);
   }
   if (lookahead) PMR_CHECK_CUDA(cudaStreamWaitEvent(st, new_event(sa), 0));
-  if (PT) PMR_CHECK_CUDA(cudaFreeAsync(PT, st));
   for (cudaEvent_t e : events) cudaEventDestroy(e);
   return 0;
 }
@@ -625,6 +590,14 @@ extern "C" int pmr_potrf_panel(double* A, int N, long long lda, int j0, double* 
     const int jb = std::min(NB, N - k0);
     const int rest = N - k0 - jb;
     double* dk = dinv + (long long)kb * NB * NB;
+    if (k0 > j0) {
+      // left-looking inside the block column: one update with k = k0 - j0 (see pmr_potrf_rows)
+      const double* Pk = A + (long long)k0 * lda + j0;
+      pmr_gemm_t t = make_gemm(N - k0, jb, k0 - j0, -1.0, Pk, lda, 1, Pk, 1, lda, 1.0,
+                               A + (long long)k0 * lda + k0, lda, 1);
+      t.flags = PMR_GEMM_LOWER;
+      PMR_TRY(gemm(t, st));
+    }
     potf2_trtri_kernel<<<1, POTF2_THREADS, smem, st>>>(A + (long long)k0 * lda + k0, lda, 0, jb, dk,
                                                        dstride, info, k0);
     PMR_CHECK_LAUNCH("potf2_trtri_kernel");
@@ -633,13 +606,6 @@ extern "C" int pmr_potrf_panel(double* A, int N, long long lda, int j0, double* 
       pmr_gemm_t g = make_gemm(rest, jb, jb, 1.0, A21, lda, 1, dk, 1, NB, 0.0, A21, lda, 1);
       g.flags = PMR_GEMM_C_ALIASES_A;
       PMR_TRY(gemm(g, st));
-      const int ncols = jend - (k0 + jb);
-      if (ncols > 0) {
-        double* A22 = A + (long long)(k0 + jb) * lda + (k0 + jb);
-        pmr_gemm_t t = make_gemm(rest, ncols, jb, -1.0, A21, lda, 1, A21, 1, lda, 1.0, A22, lda, 1);
-        t.flags = PMR_GEMM_LOWER;
-        PMR_TRY(gemm(t, st));
-      }
     }
   }
   return 0;

@@ -926,16 +926,6 @@ int launch_bulk(const GemmArgs& a, bool akc, bool bkc, int b1, int b2, cudaStrea
   return launch_bulk_cfg<BM, BN, WM, WN, false, false, NSTAGE, MINB, true, 2>(a, b1, b2, st);
 }
 
-// warp-specialised cp.async producers (any layout; 16-byte copies only: the 8-byte variant stays on
-// the plain kernel)
-template <int BM, int BN, int WM, int WN, int NSTAGE, int MINB>
-int launch_ws(const GemmArgs& a, bool akc, bool bkc, int b1, int b2, cudaStream_t st) {
-  if (akc && bkc) return launch_bulk_cfg<BM, BN, WM, WN, true, true, NSTAGE, MINB, false, 2>(a, b1, b2, st);
-  if (akc && !bkc) return launch_bulk_cfg<BM, BN, WM, WN, true, false, NSTAGE, MINB, false, 2>(a, b1, b2, st);
-  if (!akc && bkc) return launch_bulk_cfg<BM, BN, WM, WN, false, true, NSTAGE, MINB, false, 2>(a, b1, b2, st);
-  return launch_bulk_cfg<BM, BN, WM, WN, false, false, NSTAGE, MINB, false, 2>(a, b1, b2, st);
-}
-
 template <int BM, int BN, int WM, int WN, int NSTAGE, int MINB>
 int launch_layout(const GemmArgs& a, bool akc, bool bkc, int b1, int b2, cudaStream_t st) {
   if (a.a_vec2 && a.b_vec2) {
@@ -1040,13 +1030,6 @@ int gemm(const pmr_gemm_t& g0, cudaStream_t st) {
     else r = launch_tma_cfg<128, 32, 32, 32, 4, 2>(a, g.batch1, g.batch2, st);
     if (r <= 0) return r;   // > 0: not expressible as a tensor map, fall through
   }
-  // EXPERIMENT (PMR_GEMM_WS=1): warp-specialised cp.async producers + mbarriers for the k-contiguous
-  // layouts.  Measured on B200 it is not faster than the plain ring (8192^3: 32.4 vs 33.7 TFLOP/s;
-  // K = 128: 28.2 vs 29.8; batched Cholesky 15.9 vs 15.5 ms), so it is off by default.
-  static const bool allow_ws = [] { const char* e = getenv("PMR_GEMM_WS"); return e && atoi(e); }();
-  if (allow_ws && bn == 64 && a.a_vec2 && a.b_vec2 && g.K > 0 && !(g.flags & PMR_GEMM_C_ALIASES_A) &&
-      g.C2 == nullptr)
-    return launch_ws<128, 64, 32, 32, 3, 2>(a, akc, bkc, g.batch1, g.batch2, st);
   if (bn == 128 && (g.flags & PMR_GEMM_C_ALIASES_A))  // in-place panel solve: full rows per CTA,
     return launch_layout<64, 128, 32, 32, 3, 2>(a, akc, bkc, g.batch1, g.batch2, st);  // 2 CTAs / SM
   if (bn == 128) return launch_layout<128, 128, 32, 32, 4, 1>(a, akc, bkc, g.batch1, g.batch2, st);

@@ -91,6 +91,64 @@ __global__ void pm_to_xy_kernel(const double* __restrict__ p, const double* __re
   xy[c * ldxy + nov + k] = 0.5 * (pv - mv);
 }
 
+// ---- packing kernels of the half-size solver (one launch each instead of a dozen tensor ops) ----
+constexpr int PACK_MAX_COLS = 64;   // right-hand-side columns (all operators' components)
+constexpr int PACK_MAX_FREQ = 64;   // frequencies per launch
+struct PackCols { int imag_col[PACK_MAX_COLS]; };   // -1: real operator, else column of T = K^-1 g
+struct PackFreq { double w[PACK_MAX_FREQ]; };
+
+// right-hand sides of the m equations, one per ROW of the (rows x N) matrix that is factorised:
+//   out[q][c][k] = 2 g[c][k]            (real operator)
+//                  2 w_q T[k][imag(c)]  (imaginary operator; T = K^-1 g, (N, nimag))
+//                  0                    (padding columns c >= ncols)
+__global__ void solve_pack_rhs_kernel(const double* __restrict__ g, long long ldg,
+                                      const double* __restrict__ T, int nimag, int ncols, int ncp,
+                                      long long N, double* __restrict__ out, long long stride_q,
+                                      const PackCols cols, const PackFreq fr) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y, q = blockIdx.z;
+  if (k >= N) return;
+  double v = 0.0;
+  if (c < ncols) {
+    const int ic = cols.imag_col[c];
+    if (ic < 0) v = 2.0 * g[(long long)c * ldg + k];
+    else if (T) v = 2.0 * fr.w[q] * T[k * nimag + ic];
+  }
+  out[(long long)q * stride_q + (long long)c * N + k] = v;
+  (void)ncp;
+}
+
+// right-hand sides of the p equations, all frequencies side by side:
+//   prhs[k][q * ncols + c] = w_q m[q][k][c] + (imaginary ? 2 g[c][k] : 0)
+__global__ void solve_pack_p_kernel(const double* __restrict__ m, int ncp, const double* __restrict__ g,
+                                    long long ldg, int ncols, int nfc, long long N,
+                                    double* __restrict__ prhs, const PackCols cols, const PackFreq fr) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_row = (long long)nfc * ncols;
+  if (e >= N * per_row) return;
+  const long long k = e / per_row;
+  const int qc = (int)(e - k * per_row);
+  const int q = qc / ncols, c = qc - q * ncols;
+  double v = fr.w[q] * m[((long long)q * N + k) * ncp + c];
+  if (cols.imag_col[c] >= 0) v += 2.0 * g[(long long)c * ldg + k];
+  prhs[e] = v;
+}
+
+// xy[(q, c)][0:N] = (p + m) / 2, [N:2N] = (p - m) / 2 with p[k][q * ncols + c] (may be NULL) and
+// m[q][k][c]: the (X; Y) supervectors of solvers.py:418-425 for every frequency and column
+__global__ void solve_xy_kernel(const double* __restrict__ p, const double* __restrict__ m, int ncp,
+                                int ncols, int nfc, long long N, double* __restrict__ xy) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int qc = blockIdx.y;
+  if (k >= N) return;
+  const int q = qc / ncols, c = qc - q * ncols;
+  const double pv = p ? p[k * ((long long)nfc * ncols) + qc] : 0.0;
+  const double mv = m[((long long)q * N + k) * ncp + c];
+  double* row = xy + (long long)qc * 2 * N;
+  row[k] = 0.5 * (pv + mv);
+  row[N + k] = 0.5 * (pv - mv);
+}
+
 __global__ void axpby_kernel(long long rows, long long cols, double a, const double* __restrict__ x,
                              long long ldx, double b, double* __restrict__ y, long long ldy) {
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -293,6 +351,59 @@ extern "C" int pmr_pm_to_xy(const double* p, const double* m, int ncomp, long lo
   dim3 grid((unsigned)((nov + 255) / 256), ncomp);
   pm_to_xy_kernel<<<grid, 256, 0, as_stream(stream)>>>(p, m, nov, ldp, ldm, xy, ldxy);
   PMR_CHECK_LAUNCH("pm_to_xy_kernel");
+  return 0;
+}
+
+static int fill_pack(const int* imag_col_host, int ncols, const double* w_host, int nfc, PackCols& pc,
+                     PackFreq& pf) {
+  PMR_REQUIRE(ncols >= 0 && ncols <= PACK_MAX_COLS, "solve_pack: more than %d right-hand-side columns",
+              PACK_MAX_COLS);
+  PMR_REQUIRE(nfc >= 0 && nfc <= PACK_MAX_FREQ, "solve_pack: more than %d frequencies per call",
+              PACK_MAX_FREQ);
+  for (int c = 0; c < PACK_MAX_COLS; ++c) pc.imag_col[c] = (c < ncols && imag_col_host) ? imag_col_host[c] : -1;
+  for (int q = 0; q < PACK_MAX_FREQ; ++q) pf.w[q] = (q < nfc && w_host) ? w_host[q] : 0.0;
+  return 0;
+}
+
+extern "C" int pmr_solve_pack_rhs(const double* g, long long ldg, const double* T, int nimag,
+                                  const int* imag_col_host, int ncols, int ncp,
+                                  const double* w_host, int nfc, long long N, double* out,
+                                  long long stride_q, void* stream) {
+  PackCols pc; PackFreq pf;
+  PMR_TRY(fill_pack(imag_col_host, ncols, w_host, nfc, pc, pf));
+  PMR_REQUIRE(ncp >= ncols && N >= 0, "solve_pack_rhs: bad dims");
+  if (N == 0 || ncp == 0 || nfc == 0) return 0;
+  PMR_REQUIRE(g && out, "solve_pack_rhs: null pointer");
+  dim3 grid((unsigned)((N + 255) / 256), (unsigned)ncp, (unsigned)nfc);
+  solve_pack_rhs_kernel<<<grid, 256, 0, as_stream(stream)>>>(g, ldg, T, nimag, ncols, ncp, N, out,
+                                                             stride_q, pc, pf);
+  PMR_CHECK_LAUNCH("solve_pack_rhs_kernel");
+  return 0;
+}
+
+extern "C" int pmr_solve_pack_p(const double* m, int ncp, const double* g, long long ldg,
+                                const int* imag_col_host, int ncols, const double* w_host, int nfc,
+                                long long N, double* prhs, void* stream) {
+  PackCols pc; PackFreq pf;
+  PMR_TRY(fill_pack(imag_col_host, ncols, w_host, nfc, pc, pf));
+  const long long total = N * (long long)nfc * ncols;
+  if (total == 0) return 0;
+  PMR_REQUIRE(m && g && prhs, "solve_pack_p: null pointer");
+  solve_pack_p_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(
+      m, ncp, g, ldg, ncols, nfc, N, prhs, pc, pf);
+  PMR_CHECK_LAUNCH("solve_pack_p_kernel");
+  return 0;
+}
+
+extern "C" int pmr_solve_xy(const double* p, const double* m, int ncp, int ncols, int nfc, long long N,
+                            double* xy, void* stream) {
+  PMR_REQUIRE(ncols >= 0 && nfc >= 0 && N >= 0 && ncp >= ncols, "solve_xy: bad dims");
+  if (N == 0 || ncols == 0 || nfc == 0) return 0;
+  PMR_REQUIRE(m && xy, "solve_xy: null pointer");
+  PMR_REQUIRE((long long)nfc * ncols <= 65535, "solve_xy: too many columns");
+  dim3 grid((unsigned)((N + 255) / 256), (unsigned)(nfc * ncols));
+  solve_xy_kernel<<<grid, 256, 0, as_stream(stream)>>>(p, m, ncp, ncols, nfc, N, xy);
+  PMR_CHECK_LAUNCH("solve_xy_kernel");
   return 0;
 }
 

@@ -33,7 +33,6 @@ print(f"whole array: {t:8.1f} ms  {arr.nbytes / t / 1e6:6.1f} GB/s")
 import ctypes as C  # noqa: E402
 
 for layout, ns in ((0, 1), (1, 1), (2, 1)):
-    L.pmr_set_upload_streams(ns)
     nb = int(L.pmr_eri_s8_bytes(n, layout))
     tu = timed(lambda: nv.check(L.pmr_eri_upload_s8(C.c_void_p(arr.ctypes.data), nv.ptr(dev), n, layout, st)))
     tc = timed(lambda: nv.check(L.pmr_eri_complete_s8(nv.ptr(dev), n, layout, st)))

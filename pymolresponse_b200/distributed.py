@@ -206,11 +206,20 @@ def allgather_columns(X, n_cols_total: int):
     rows = int(X.shape[0])
     wmax = (n_cols_total + world - 1) // world
     coll_dev = torch.device("cpu") if (X.is_cuda and _host_staged()) else X.device
-    buf = torch.zeros(rows, wmax, dtype=X.dtype, device=coll_dev)
-    buf[:, : X.shape[1]].copy_(X)
-    parts = [torch.empty_like(buf) for _ in range(world)]
-    d.all_gather(parts, buf)
+    if int(X.shape[1]) == wmax and X.is_contiguous() and coll_dev == X.device:
+        buf = X
+    else:
+        buf = torch.zeros(rows, wmax, dtype=X.dtype, device=coll_dev)
+        buf[:, : X.shape[1]].copy_(X)
     out = torch.empty(rows, n_cols_total, dtype=X.dtype, device=X.device)
+    if coll_dev == X.device:
+        # one flat all-gather (world, rows, wmax), then the column blocks go to their places
+        flat = torch.empty(world, rows, wmax, dtype=X.dtype, device=coll_dev)
+        d.all_gather_into_tensor(flat, buf)
+        parts = [flat[r] for r in range(world)]
+    else:
+        parts = [torch.empty_like(buf) for _ in range(world)]
+        d.all_gather(parts, buf)
     for r in range(world):
         lo, hi = shard_range(n_cols_total, r, world)
         out[:, lo:hi].copy_(parts[r][:, : hi - lo])

@@ -335,33 +335,33 @@ def one_step(w, inp, I, device_resident: bool, world: int, stage_ms: dict | None
     mark("ao2mo")
     gen = integrals.IntegralsArrays({"dipole": inp["O_real"], "angmom_common_gauge": inp["O_imag"]})
     out = {}
-    s_mag = None
-    if w["magnetizability"]:
-        s = s_mag = solvers.ExactInvCholesky(inp["C"], inp["E"], inp["occ"])
-        s.device_results = device_resident
-        s.tei_mo = tei
-        s.tei_mo_rows = rows
-        mag = Magnetizability(Program.Arrays, gen, cphf.CPHF(s))
-        mag.form_operators()
-        mag.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet)
-        mag.form_results()
-        out["magnetizability"] = mag.magnetizability
-        mark("magnetizability")
     s = getattr(solvers, w["solver"])(inp["C"], inp["E"], inp["occ"])
     s.device_results = device_resident
     s.distribute_frequencies = world > 1
     s.tei_mo = tei
     s.tei_mo_rows = rows
-    if s_mag is not None:
-        s_mag.share_hessian_with(s)   # same reference, Hamiltonian and spin: M, K, chol(K) built once
     pol = Polarizability(Program.Arrays, gen, cphf.CPHF(s), frequencies=[float(f) for f in w["pol_freqs"]])
     pol.form_operators()
     pol.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet)
     pol.form_results()
     out["polarizabilities"] = pol.polarizabilities
+    mark("polarizability_sweep")
+    if w["magnetizability"]:
+        # second property on the same reference: M, K, chol(K) and K^-1 of the sweep are adopted
+        # (share_hessian_with), so the static imaginary-operator solve is one product with K^-1
+        sm = solvers.ExactInvCholesky(inp["C"], inp["E"], inp["occ"])
+        sm.device_results = device_resident
+        sm.tei_mo = tei
+        sm.tei_mo_rows = rows
+        s.share_hessian_with(sm)
+        mag = Magnetizability(Program.Arrays, gen, cphf.CPHF(sm))
+        mag.form_operators()
+        mag.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet)
+        mag.form_results()
+        out["magnetizability"] = mag.magnetizability
+        mark("magnetizability")
     out["stats"] = getattr(s, "solve_stats", {})
     out["solver"] = s if keep_solver else None
-    mark("polarizability_sweep")
     if stage_ms is not None:
         torch.cuda.synchronize()
         for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):

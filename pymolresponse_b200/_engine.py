@@ -590,8 +590,11 @@ class HalfSizeSystem:
             if Kfac is None:
                 Kfac = self.K.clone()
                 new_K = True
-                if share_kinv and self.N >= DISTRIBUTED_POTRF_MIN_N:
-                    # collective: every rank is here (share_kinv); K^-1 comes out of the same pass
+                if share_kinv and self.N >= DISTRIBUTED_POTRF_MIN_N and self.N > KINV_TREE_MAX_N:
+                    # large systems -- collective: every rank is here (share_kinv); the factor is
+                    # computed once across the ranks and K^-1 comes out of the same pass.  Smaller
+                    # ones factor K locally (a distributed panel chain would be latency bound) and
+                    # share only the inverse (_kinv_distributed)
                     dinvK, infoK, Kinv = self._factor_and_invert_distributed(Kfac)
                     symmetrize_lower(Kinv)
                     self.stats["potrf_shared"] = self.stats.get("potrf_shared", 0) + 1

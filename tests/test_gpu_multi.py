@@ -47,6 +47,7 @@ A[900, 900] = -3.0
 _, info = eng.potrf_distributed(nv.to_dev(A).clone())
 assert int(info.item()) == 901
 eng.DISTRIBUTED_POTRF_MIN_N = 0      # let the small solver case below take the distributed path too
+eng.KINV_TREE_MAX_N = 0              # (distributed factor of K + substitution-based shared K^-1)
 n, o = 30, 4
 case = synthetic.rhf_case(n, o)
 lo, hi = pd.shard_range(n, rank, world)
@@ -79,6 +80,33 @@ for freqs in ([0.0, 0.1, 0.2], [0.3], [0.0]):
     if any(w != 0.0 for w in freqs):
         assert solver.solve_stats.get("potri_shared", 0) == 1 and solver.solve_stats["potri"] == 0
         assert solver.solve_stats.get("potrf_shared", 0) == 1
+eng.DISTRIBUTED_POTRF_MIN_N, eng.KINV_TREE_MAX_N = 2048, 12288     # defaults again
+# nov = 512: local factor of K, shared K^-1 from the local inv(L) (recursive doubling) + this rank's
+# column blocks of Z^T Z, all-gathered
+nb_, ob_ = 72, 8
+big = synthetic.rhf_case(nb_, ob_)
+blo, bhi = pd.shard_range(nb_, rank, world)
+ab = AO2MO(big["C"], big["occupations"], I=np.ascontiguousarray(big["I"][:, blo:bhi]),
+           nu_range=(blo, bhi), device_results=True, reduce="scatter")
+ab.perform_rhf_partial()
+sb = solvers.ExactInv(big["C"], big["E"], big["occupations"])
+sb.distribute_frequencies = True
+sb.tei_mo = ab.tei_mo
+sb.tei_mo_rows = ab.row_ranges[0]
+db = cphf.CPHF(sb)
+Ob = synthetic.operator_integrals(nb_, 3, False)
+Oib = synthetic.operator_integrals(nb_, 3, True)
+for O_, im_ in ((Ob, False), (Oib, True)):
+    db.add_operator(operators.Operator(label="x", is_imaginary=im_, ao_integrals=O_))
+db.set_frequencies([0.0, 0.2, 0.4])
+db.run(hamiltonian=Hamiltonian.RPA, spin=Spin.singlet, program=None, program_obj=None)
+assert sb.solve_stats.get("potri_shared", 0) == 1 and sb.solve_stats.get("potrf_shared", 0) == 0
+tb = orc.ao2mo_rhf_partial(big["I"], big["C"], ob_)
+rb = orc.run_cphf(big["C"], big["E"], big["occupations"], tb, "partial",
+                  [{"ao_integrals": Ob, "is_imaginary": False}, {"ao_integrals": Oib, "is_imaginary": True}],
+                  [0.0, 0.2, 0.4])
+for f in range(3):
+    assert np.abs(db.results[f] - rb["results"][f]).max() <= 1e-9, f
 # one frequency above the first pole (owned by rank 1): ExactInv falls back to LU there and the
 # gather still completes; ExactInvCholesky raises LinAlgError on EVERY rank (no rank left waiting)
 freqs = [0.1, 1.9, 0.2]

@@ -2,6 +2,7 @@
 logic (shapes, index bookkeeping, DALTON labels, sharding helpers, 2-rank gloo exchange); the
 product path refuses to compute without a GPU (no CPU fallback)."""
 
+import json
 import os
 import re
 import socket
@@ -370,3 +371,37 @@ def test_pyscf_and_psi4_adapters_with_duck_typed_packages(monkeypatch):
     g4 = IntegralsPsi4(molecule="h2o")
     assert np.array_equal(g4.integrals(integrals.DIPOLE), dip)
     assert np.array_equal(g4.integrals(integrals.ANGMOM_COMMON_GAUGE), ang)
+
+
+def test_bench_helpers_without_gpu():
+    """bench.py's host-side bookkeeping: workloads, the algorithmic flop model of SURVEY 8(d), the
+    bounded reference sample, the config both arms print, the host-memory guard."""
+    import bench
+
+    w5 = bench.workload("config5", 1)
+    assert (w5["n"], w5["o"], len(w5["pol_freqs"])) == (256, 32, 64) and w5["magnetizability"]
+    # SURVEY 8(d) table: config 5 F_total = 8.68e12 (+ the static K-solve of the imaginary operator)
+    assert abs(bench.algorithmic_flops(w5) - 8.72e12) < 0.02e12
+    w3 = bench.workload("config3", 8)
+    assert abs(bench.algorithmic_flops(w3) - 1.01e14) < 0.01e14
+    w4 = bench.workload("config4", 2)
+    assert w4["input"] == "dense" and abs(bench.algorithmic_flops(w4) - 1.84e13) < 0.03e13
+    assert bench.workload("config4", 1)["input"] == "df"
+    # both arms print the same static config (the driver compares them)
+    assert bench.static_config(w5, 1) == bench.static_config(bench.workload("config5", 1), 1)
+    assert "fp64" not in json.dumps(bench.static_config(w5, 1))     # no measured values inside
+    # the reference sample grows with the per-step budget
+    assert bench.cpu_sample_spec(20, 5)["n"] == 128
+    assert bench.cpu_sample_spec(3, 3)["n"] == 160
+    assert bench.cpu_sample_spec(1000, 1000)["n"] == 64
+    a = bench.host_memory_available()
+    assert a is None or a > 0
+
+
+def test_factorised_sample_indices_are_shared_between_bench_and_oracle():
+    from oracle import pmr_factorised as fac
+
+    r1, c1 = fac.sample_indices(7168, 64, 7)
+    r2, c2 = fac.sample_indices(7168, 64, 7)
+    assert np.array_equal(r1, r2) and np.array_equal(c1, c2)
+    assert (r1 >= c1).all() and r1.max() < 7168 and len(r1) == 64 + 64

@@ -551,6 +551,7 @@ class HalfSizeSystem:
         The factorisations run optimistically: the pivot-failure words of K and of every S(w) stay
         on the device and are read ONCE, after everything has been queued."""
         N = self.N
+        g_rows = g_rows.contiguous()
         nf, ncols = len(frequencies), int(g_rows.shape[0])
         if ncols > 64:
             # the packing kernels take <= 64 right-hand-side columns a call: solve them in groups

@@ -257,12 +257,13 @@ int pmr_pm_to_xy(const double* p, const double* m, int ncomp, long long nov, lon
  * frequencies and operator components at once; host arrays: imag_col[c] = -1 for a real operator,
  * else the column of T = K^-1 g; w = the frequencies of this call, <= 64 each):
  *   pmr_solve_pack_rhs  out[q][c][k] = 2 g[c][k] | 2 w_q T[k][imag_col[c]] | 0 (padding), written as
- *                       the extra ROWS of the matrices pmr_potrf_rows factorises (stride_q apart)
+ *                       the extra ROWS (row stride ldo) of the matrices pmr_potrf_rows factorises
+ *                       (stride_q apart)
  *   pmr_solve_pack_p    prhs[k][q*ncols + c] = w_q m[q][k][c] + (imaginary ? 2 g[c][k] : 0)
  *   pmr_solve_xy        xy[(q,c)] = [(p + m)/2 ; (p - m)/2], p[k][q*ncols + c] (or NULL), m[q][k][c] */
 int pmr_solve_pack_rhs(const double* g, long long ldg, const double* T, int nimag,
                        const int* imag_col_host, int ncols, int ncp, const double* w_host, int nfc,
-                       long long N, double* out, long long stride_q, void* stream);
+                       long long N, double* out, long long ldo, long long stride_q, void* stream);
 int pmr_solve_pack_p(const double* m, int ncp, const double* g, long long ldg,
                      const int* imag_col_host, int ncols, const double* w_host, int nfc, long long N,
                      double* prhs, void* stream);

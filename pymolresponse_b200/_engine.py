@@ -266,16 +266,19 @@ KINV_TREE_MAX_N = 12288
 
 def shifted_combine(M, W, shift_a, shift_b, extra_rows=0):
     """S_f(lower) = M + shift_a[f] I + shift_b[f] W for all f -> (nf, N + extra_rows, N); the extra
-    rows (right-hand sides for pmr_potrf_rows) are left for the caller to fill."""
+    rows (right-hand sides for pmr_potrf_rows) are left for the caller to fill.  The rows are stored
+    with an EVEN leading dimension (a view of an (.., N + 1) buffer for odd N, e.g. the UHF joint
+    system): the GEMM kernels need 16-byte aligned rows for their TMA / vector paths."""
     L = nv.lib()
     N = int(M.shape[0])
     nf = len(shift_a)
-    S = nv.empty(nf, N + extra_rows, N)
+    ld = N + (N & 1)
+    S = nv.empty(nf, N + extra_rows, ld)
     nv.check(L.pmr_shifted_combine(nv.ptr(M), nv.ptr(W) if W is not None else C.c_void_p(0), N,
                                    int(M.stride(0)), int(W.stride(0)) if W is not None else N,
-                                   _darr(shift_a), _darr(shift_b), nf, nv.ptr(S), N,
-                                   (N + extra_rows) * N, nv.stream_ptr()))
-    return S
+                                   _darr(shift_a), _darr(shift_b), nf, nv.ptr(S), ld,
+                                   (N + extra_rows) * ld, nv.stream_ptr()))
+    return S[:, :, :N] if ld != N else S
 
 
 def axpby(a, x, b, y):
@@ -648,7 +651,8 @@ class HalfSizeSystem:
                     nv.check(lib.pmr_solve_pack_rhs(
                         nv.ptr(g_rows), int(g_rows.stride(0)), nv.ptr(T) if T is not None else null,
                         len(imag_cols), imag_col_arr, ncols, ncp, _darr(wsub), nfc, N,
-                        nv.ptr(S, N * N), (N + ncp) * N, nv.stream_ptr()))
+                        nv.ptr(S, N * int(S.stride(1))), int(S.stride(1)), int(S.stride(0)),
+                        nv.stream_ptr()))
                     clock.mark("shifted_combine")
                     clock.stage("potrf_S")
                     dinvS, infoS = potrf_rows(S, N, batch=nfc)

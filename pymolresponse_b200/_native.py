@@ -138,7 +138,7 @@ SYMBOLS = {
                                        c_dp, c_dp, c_dp]),
     "pmr_pm_to_xy": (C.c_int, [c_dp, c_dp, C.c_int, c_ll, c_ll, c_ll, c_dp, c_ll, c_dp]),
     "pmr_solve_pack_rhs": (C.c_int, [c_dp, c_ll, c_dp, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int,
-                                     C.POINTER(C.c_double), C.c_int, c_ll, c_dp, c_ll, c_dp]),
+                                     C.POINTER(C.c_double), C.c_int, c_ll, c_dp, c_ll, c_ll, c_dp]),
     "pmr_solve_pack_p": (C.c_int, [c_dp, C.c_int, c_dp, c_ll, C.POINTER(C.c_int), C.c_int,
                                    C.POINTER(C.c_double), C.c_int, c_ll, c_dp, c_dp]),
     "pmr_solve_xy": (C.c_int, [c_dp, c_dp, C.c_int, C.c_int, C.c_int, c_ll, c_dp, c_dp]),

@@ -103,8 +103,8 @@ struct PackFreq { double w[PACK_MAX_FREQ]; };
 //                  0                    (padding columns c >= ncols)
 __global__ void solve_pack_rhs_kernel(const double* __restrict__ g, long long ldg,
                                       const double* __restrict__ T, int nimag, int ncols, int ncp,
-                                      long long N, double* __restrict__ out, long long stride_q,
-                                      const PackCols cols, const PackFreq fr) {
+                                      long long N, double* __restrict__ out, long long ldo,
+                                      long long stride_q, const PackCols cols, const PackFreq fr) {
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c = blockIdx.y, q = blockIdx.z;
   if (k >= N) return;
@@ -114,7 +114,7 @@ __global__ void solve_pack_rhs_kernel(const double* __restrict__ g, long long ld
     if (ic < 0) v = 2.0 * g[(long long)c * ldg + k];
     else if (T) v = 2.0 * fr.w[q] * T[k * nimag + ic];
   }
-  out[(long long)q * stride_q + (long long)c * N + k] = v;
+  out[(long long)q * stride_q + (long long)c * ldo + k] = v;
   (void)ncp;
 }
 
@@ -368,15 +368,15 @@ static int fill_pack(const int* imag_col_host, int ncols, const double* w_host, 
 extern "C" int pmr_solve_pack_rhs(const double* g, long long ldg, const double* T, int nimag,
                                   const int* imag_col_host, int ncols, int ncp,
                                   const double* w_host, int nfc, long long N, double* out,
-                                  long long stride_q, void* stream) {
+                                  long long ldo, long long stride_q, void* stream) {
   PackCols pc; PackFreq pf;
   PMR_TRY(fill_pack(imag_col_host, ncols, w_host, nfc, pc, pf));
-  PMR_REQUIRE(ncp >= ncols && N >= 0, "solve_pack_rhs: bad dims");
+  PMR_REQUIRE(ncp >= ncols && N >= 0 && ldo >= N, "solve_pack_rhs: bad dims");
   if (N == 0 || ncp == 0 || nfc == 0) return 0;
   PMR_REQUIRE(g && out, "solve_pack_rhs: null pointer");
   dim3 grid((unsigned)((N + 255) / 256), (unsigned)ncp, (unsigned)nfc);
   solve_pack_rhs_kernel<<<grid, 256, 0, as_stream(stream)>>>(g, ldg, T, nimag, ncols, ncp, N, out,
-                                                             stride_q, pc, pf);
+                                                             ldo, stride_q, pc, pf);
   PMR_CHECK_LAUNCH("solve_pack_rhs_kernel");
   return 0;
 }

@@ -777,7 +777,7 @@ def bench_e2e(w, args, inp, res, rank, world, torch, F, sync_all, max_over_ranks
     # (measured: 512 GiB pinned of 954 GiB available ran, 162 GiB pinned of 248 GiB got the job
     # OOM-killed -- pinned pages, CUDA host contexts and the staging buffers add up)
     level = 0 if avail is None else (2 if avail > 2.9 * need * local_world + (8 << 30) else
-                                     1 if avail > 1.8 * need * local_world + (8 << 30) else -1)
+                                     1 if avail > 1.75 * need * local_world + (8 << 30) else -1)
     if avail is None:
         level = 1
     flag = torch.tensor([level], dtype=torch.int64, device="cuda")

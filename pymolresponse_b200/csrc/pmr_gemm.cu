@@ -2,17 +2,20 @@
 //
 //   C(m,n) = alpha * sum_k A(m,k) B(k,n) + beta * C(m,n)      (two-level strided batch)
 //
-// Design (DESIGN.md section "K1 dgemm"):
-//   * CTA tile BM x BN (128x128 / 128x64 / 128x32), BK = 16, 4-stage cp.async (LDGSTS) ring with
-//     hardware zero-fill for ragged M/N/K edges, so every shape and 8-byte-aligned stride is legal;
-//   * operands stay in their global layout in shared memory (k-contiguous [x][BK+4] or
-//     mn-contiguous [BK][BX+4]); the +4-double row padding makes the per-lane 64-bit fragment
-//     loads of the m8n8k4 shapes bank-conflict free for both layouts;
-//   * each warp owns a 64x32 (or 32x32) accumulator block = 8x4 DMMA.8x8x4 tiles in registers; on
-//     sm_100a all f64 mma shapes lower to DMMA.8x8x4 (checked with cuobjdump), 16 cycles per SMSP,
-//     so the kernel is DMMA-issue bound by construction: 12 LDS.64 per 32 DMMA;
-//   * C is written with arbitrary (row, column) element strides: transposed / packed-index
-//     epilogues (ov packing of operators.py:94, quarter-transform output orders) are free.
+// Three kernels share the CTA tile (128x64, 8 math warps of 32x32, BK = 16), the m8n8k4 fragment
+// mapping and the epilogue conventions (DESIGN.md section "K-gemm"):
+//   * dgemm_tma_kernel  -- both operands k-contiguous (every Cholesky trailing update, C -= P P^T):
+//     cp.async.bulk.tensor (tensor-map TMA, 128-byte swizzle, zero-filled edges) issued by one
+//     producer lane, full/empty mbarrier ring, no CTA-wide barrier and no global-memory instruction in
+//     the math warps' main loop; lower-triangular stores launch only the tiles of the triangle;
+//   * dgemm_bulk_kernel -- both operands contiguous along m / n: one 1-D bulk copy per k row;
+//   * dgemm_dmma_kernel -- every other layout / alignment: cp.async (LDGSTS) ring with hardware
+//     zero-fill, operands in their global layout with +4-double row padding (conflict-free 64-bit
+//     fragment loads for both layouts).
+// On sm_100a all f64 mma shapes lower to DMMA.8x8x4 (checked with cuobjdump), 16 cycles per SMSP: the
+// kernels are DMMA-issue bound by construction (8 LDS.64 per 16 DMMA).  C is written with arbitrary
+// (row, column) element strides: transposed / packed-index epilogues (ov packing of
+// operators.py:94, quarter-transform output orders) are free.
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
@@ -33,7 +36,9 @@ namespace {
 
 constexpr int BK = 16;
 constexpr int PAD = 4;
-constexpr int TMA_STAGES_64 = 3;  // 3 x 24 KiB per CTA, two CTAs per SM (A/B on the config-5 step: 4 stages 306.4 ms, 3 stages 304.4)
+// ring depth of the tensor-map kernel: 3 x 24 KiB per CTA, two CTAs per SM (A/B on the config-5
+// step: 4 stages 306.4 ms, 3 stages 304.4 ms)
+constexpr int TMA_STAGES_64 = 3;
 
 struct GemmArgs {
   int M, N, K;

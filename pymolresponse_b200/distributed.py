@@ -214,9 +214,9 @@ def allgather_columns(X, n_cols_total: int):
     out = torch.empty(rows, n_cols_total, dtype=X.dtype, device=X.device)
     if coll_dev == X.device:
         # one flat all-gather (world, rows, wmax), then the column blocks go to their places
-        flat = torch.empty(world, rows, wmax, dtype=X.dtype, device=coll_dev)
-        d.all_gather_into_tensor(flat, buf)
-        parts = [flat[r] for r in range(world)]
+        flat = torch.empty(world * rows, wmax, dtype=X.dtype, device=coll_dev)
+        d.all_gather_into_tensor(flat, buf)           # rank blocks concatenated along dim 0
+        parts = [flat[r * rows:(r + 1) * rows] for r in range(world)]
     else:
         parts = [torch.empty_like(buf) for _ in range(world)]
         d.all_gather(parts, buf)

@@ -194,6 +194,21 @@ full = pd.gather_round_robin([torch.ones(2, 2, dtype=torch.float64)] if rank == 
 assert len(full) == 1 and torch.equal(full[0], torch.ones(2, 2, dtype=torch.float64))
 lo, hi = pd.shard_range(9, rank, world)
 assert (lo, hi) == ((0, 5) if rank == 0 else (5, 9))
+# a failure on one rank is seen by every rank before the next data-path collective
+assert pd.any_rank(rank == 1) is True and pd.any_rank(False) is False
+# row blocks of the MO integrals / Hessian: reduce-scatter of partial sums, all-gather of the blocks
+# (even and ragged splits), column blocks of the shared K^-1
+for rows in (6, 7):
+    T = torch.arange(rows * 3, dtype=torch.float64).reshape(rows, 3) * (rank + 1)
+    mine = pd.reduce_scatter_rows(T.clone(), rows)
+    rlo, rhi = pd.shard_range(rows, rank, world)
+    want = torch.arange(rows * 3, dtype=torch.float64).reshape(rows, 3) * 3.0
+    assert torch.equal(mine, want[rlo:rhi])
+    assert torch.equal(pd.allgather_rows(mine, rows), want)
+cols = 8
+clo, chi = pd.shard_range(cols, rank, world)
+full = torch.arange(5 * cols, dtype=torch.float64).reshape(5, cols)
+assert torch.equal(pd.allgather_columns(full[:, clo:chi].contiguous(), cols), full)
 pd.barrier()
 dist.destroy_process_group()
 print("ok", rank)

@@ -227,12 +227,20 @@ int pmr_shifted_combine(const double* M, const double* W, int N, long long ldm, 
                         double* S, long long lds, long long stride_s, void* stream);
 /* A[i][i] += value, i < N (frequency shift of the explicit super-Hessian, solvers.py:230-231) */
 int pmr_shift_diagonal(double* A, int N, long long lda, double value, void* stream);
-/* LU with partial pivoting (general / above-pole case): row-major A = P L U in place. */
+/* LU with partial pivoting (general / above-pole case): row-major A = P L U in place, LAPACK's pivots.
+ * Two levels of blocking: 64-column panels are applied inside a 256-column block, the trailing matrix
+ * gets one interchange pass (as a single row permutation), one U12 solve and one rank-256 update per
+ * block. */
 int pmr_getrf(double* A, int N, long long lda, int* ipiv /* device, N */, int* info,
               double* work /* pmr_getrf_work_doubles(N) */, void* stream);
 long long pmr_getrf_work_doubles(int N);
+/* Panels of the pivoted LU are factorised eight columns per launch by one thread-block cluster (rows in
+ * shared memory, one cluster barrier per column) while N - k0 <= 24576 rows remain, and one launch per
+ * column otherwise.  Switching the cluster panel off forces the per-column path (the tests run both;
+ * the pivots and the factors are the same).  Default on. */
+void pmr_set_lu_cluster_panel(int on);
 int pmr_getrs(const double* LU, int N, long long lda, const int* ipiv, double* B, int nrhs,
-              long long ldb, double* work /* N*nrhs */, void* stream);
+              long long ldb, double* work /* N*nrhs + N doubles */, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Operator right-hand sides and property contraction

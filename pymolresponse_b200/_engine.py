@@ -312,7 +312,7 @@ def getrf(A):
 def getrs(LU, ipiv, B):
     L = nv.lib()
     N, nrhs = int(B.shape[0]), int(B.shape[1])
-    work = nv.empty(max(1, N * nrhs))
+    work = nv.empty(max(1, N * nrhs + N))   # row buffer + the pivot sequence as one permutation
     nv.check(L.pmr_getrs(nv.ptr(LU), N, int(LU.stride(0)), nv.ptr(ipiv), nv.ptr(B), nrhs,
                          int(B.stride(0)), nv.ptr(work), nv.stream_ptr()))
     return B

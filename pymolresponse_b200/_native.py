@@ -97,6 +97,7 @@ SYMBOLS = {
     "pmr_energy_differences": (C.c_int, [c_dp, C.c_int, c_dp, C.c_int, c_dp, c_dp]),
     "pmr_potrf_dinv_doubles": (c_ll, [C.c_int]),
     "pmr_set_lookahead": (None, [C.c_int]),
+    "pmr_set_lu_cluster_panel": (None, [C.c_int]),
     "pmr_debug_potf2_timing": (C.c_int, [c_dp]),
     "pmr_potrf": (C.c_int, [c_dp, C.c_int, c_ll, C.c_int, c_ll, c_dp, c_dp, c_dp]),
     "pmr_potrf_rows": (C.c_int, [c_dp, C.c_int, C.c_int, c_ll, C.c_int, c_ll, c_dp, c_dp, c_dp]),

@@ -10,6 +10,8 @@
 //   2. panel:     A21 <- A21 * inv(L_kk)^T            (DMMA GEMM, in place, N = 128 = one tile)
 //   3. trailing:  A22 <- A22 - A21 A21^T  (lower)     (DMMA GEMM, PMR_GEMM_LOWER)
 // Triangular solves use the stored diagonal-block inverses, so every step is a GEMM.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -295,22 +297,88 @@ __global__ void copy_block_kernel(const double* __restrict__ src, long long lds,
 // ------------------------------------------------------------------------------------ LU
 constexpr int PB = 64;  // LU panel width
 
-// stage 1 of the pivot search in column j over rows [j, N)
-__global__ void lu_pivot_partial_kernel(const double* __restrict__ A, long long lda, int N, int j,
-                                        double* __restrict__ pval, int* __restrict__ pidx) {
-  __shared__ double sv[256];
-  __shared__ int si[256];
+// One launch per panel column j (rows [j, N), a warp per row):
+//   1. unless j is the panel's first column, finish column j-1: l = A[i][j-1] / pivot, stored in place, and
+//      A[i][j..pend) -= l * A[j-1][j..pend)  -- the rank-1 step restricted to the panel;
+//   2. unless j == pend (the call that only finishes the panel's last column), search column j for its pivot:
+//      per-block candidates, then the last block to arrive (ticket counter) picks the pivot, records it
+//      and swaps rows j <-> p inside the panel columns [k0, pend).  The interchange of the columns outside
+//      the panel is applied once per panel by lu_laswp_kernel (LAPACK's order of operations).
+// Ties go to the smallest row index, as in LAPACK's idamax.
+constexpr int LU_WARPS = 8;
+constexpr int LU_MAX_PARTS = 512;
+
+__global__ void __launch_bounds__(LU_WARPS * 32)
+lu_column_kernel(double* A, long long lda, int N, int k0, int pend, int j, double* pval, int* pidx,
+                 int* counter, int* ipiv, int* info) {
+  __shared__ double prow[PB];
+  __shared__ double sv[LU_WARPS * 32];
+  __shared__ int si[LU_WARPS * 32];
+  __shared__ int s_last, s_piv;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool finish_prev = j > k0;
+  const bool search = j < pend;
+  double piv = 1.0;
+  if (finish_prev) {
+    for (int c = threadIdx.x; c < pend - j; c += blockDim.x) prow[c] = A[(long long)(j - 1) * lda + j + c];
+    piv = A[(long long)(j - 1) * lda + (j - 1)];
+  }
+  __syncthreads();
   double best = -1.0;
   int bi = j;
-  for (int i = j + blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-    const double v = fabs(A[(long long)i * lda + j]);
-    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  for (int i = j + blockIdx.x * LU_WARPS + warp; i < N; i += gridDim.x * LU_WARPS) {
+    double* row = A + (long long)i * lda;
+    double cand = 0.0;
+    if (finish_prev) {
+      const double l = row[j - 1] / piv;
+      __syncwarp();
+      for (int c = j + lane; c < pend; c += 32) {
+        const double v = row[c] - l * prow[c - j];
+        row[c] = v;
+        if (c == j) cand = v;
+      }
+      if (lane == 0) row[j - 1] = l;
+    } else if (lane == 0) {
+      cand = row[j];
+    }
+    if (search && lane == 0) {
+      const double v = fabs(cand);
+      if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
   }
-  sv[threadIdx.x] = best;
-  si[threadIdx.x] = bi;
+  if (!search) return;
+  // block candidate (lane 0 of every warp holds one)
+  if (lane == 0) { sv[warp] = best; si[warp] = bi; }
   __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    if (threadIdx.x < s) {
+  if (threadIdx.x == 0) {
+    double b = sv[0];
+    int ix = si[0];
+    for (int w = 1; w < LU_WARPS; ++w)
+      if (sv[w] > b || (sv[w] == b && si[w] < ix)) { b = sv[w]; ix = si[w]; }
+    pval[blockIdx.x] = b;
+    pidx[blockIdx.x] = ix;
+    __threadfence();
+    const int ticket = atomicAdd(counter, 1);
+    s_last = (ticket == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // the last block: reduce the per-block candidates
+  {
+    double b = -1.0;
+    int ix = j;
+    for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) {
+      const double v = __ldcg(pval + q);
+      const int i2 = __ldcg(pidx + q);
+      if (v > b || (v == b && i2 < ix)) { b = v; ix = i2; }
+    }
+    sv[threadIdx.x] = b;
+    si[threadIdx.x] = ix;
+  }
+  __syncthreads();
+  for (int s = (LU_WARPS * 32) >> 1; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
       const double v = sv[threadIdx.x + s];
       const int i2 = si[threadIdx.x + s];
       if (v > sv[threadIdx.x] || (v == sv[threadIdx.x] && i2 < si[threadIdx.x])) {
@@ -320,69 +388,372 @@ __global__ void lu_pivot_partial_kernel(const double* __restrict__ A, long long 
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) { pval[blockIdx.x] = sv[0]; pidx[blockIdx.x] = si[0]; }
-}
-
-// stage 2: pick the pivot, record it, swap rows j <-> p over all N columns
-__global__ void lu_pivot_swap_kernel(double* __restrict__ A, long long lda, int N, int j,
-                                     const double* __restrict__ pval, const int* __restrict__ pidx,
-                                     int nparts, int* __restrict__ ipiv, int* __restrict__ info) {
-  __shared__ int sp;
   if (threadIdx.x == 0) {
-    double best = -1.0;
-    int bi = j;
-    for (int q = 0; q < nparts; ++q)
-      if (pval[q] > best || (pval[q] == best && pidx[q] < bi)) { best = pval[q]; bi = pidx[q]; }
-    ipiv[j] = bi;
-    if (!(best > 0.0) && *info == 0) *info = j + 1;
-    sp = bi;
+    ipiv[j] = si[0];
+    if (!(sv[0] > 0.0) && *info == 0) *info = j + 1;
+    s_piv = si[0];
+    *counter = 0;
   }
   __syncthreads();
-  const int p = sp;
+  const int p = s_piv;
   if (p == j) return;
-  for (int c = threadIdx.x; c < N; c += blockDim.x) {
-    const double a = A[(long long)j * lda + c];
-    const double b = A[(long long)p * lda + c];
+  for (int c = k0 + threadIdx.x; c < pend; c += blockDim.x) {
+    const double a = __ldcg(A + (long long)j * lda + c);
+    const double b = __ldcg(A + (long long)p * lda + c);
     A[(long long)j * lda + c] = b;
     A[(long long)p * lda + c] = a;
   }
 }
 
-// scale column j below the diagonal and update the rest of the panel row-wise (warp per row)
-__global__ void lu_panel_update_kernel(double* __restrict__ A, long long lda, int N, int j,
-                                       int pend) {
-  const int warps_per_block = blockDim.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int i = j + 1 + blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  if (i >= N) return;
-  const double piv = A[(long long)j * lda + j];
-  double* row = A + (long long)i * lda;
-  const double l = row[j] / piv;
-  for (int c = j + 1 + lane; c < pend; c += 32) row[c] -= l * A[(long long)j * lda + c];
-  __syncwarp();
-  if (lane == 0) row[j] = l;
+// Row interchanges ipiv[p_lo..p_hi) applied to the columns [a_lo, a_hi) and [b_lo, b_hi), one after the
+// other by a thread per column (the fallback when the row range does not fit lu_perm_build_kernel).
+__global__ void lu_laswp_kernel(double* __restrict__ A, long long lda, int p_lo, int p_hi,
+                                const int* __restrict__ ipiv, int a_lo, int a_hi, int b_lo, int b_hi) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int na = a_hi - a_lo;
+  if (t >= na + (b_hi - b_lo)) return;
+  const int c = t < na ? a_lo + t : b_lo + (t - na);
+  for (int j = p_lo; j < p_hi; ++j) {
+    const int p = ipiv[j];
+    if (p != j) {
+      const double a = A[(long long)j * lda + c];
+      A[(long long)j * lda + c] = A[(long long)p * lda + c];
+      A[(long long)p * lda + c] = a;
+    }
+  }
 }
 
-// U12 <- inv(L11) A12 with L11 unit lower (pb x pb) : thread per column
-__global__ void lu_trsm_u12_kernel(double* __restrict__ A, long long lda, int k0, int pb, int N) {
-  __shared__ double L11[PB][PB + 1];
-  for (int idx = threadIdx.x; idx < pb * pb; idx += blockDim.x) {
-    const int r = idx / pb, c = idx - r * pb;
-    L11[r][c] = A[(long long)(k0 + r) * lda + k0 + c];
+// The same interchanges as ONE permutation: rows [p_lo, N) tracked in shared memory (perm[t] = the row
+// that ends at position t), the swaps replayed by one thread, then the list of positions that move
+// (at most 2 (p_hi - p_lo)) written out as (target, source) pairs for the gather / scatter pair below.
+constexpr int LU_OB = 256;  // outer block of the factorisation = the most interchanges replayed at once
+constexpr int LU_PERM_MAX_ROWS = 51200;
+
+__global__ void __launch_bounds__(256)
+lu_perm_build_kernel(const int* __restrict__ ipiv, int p_lo, int p_hi, int N, int* __restrict__ list_t,
+                     int* __restrict__ list_src, int* __restrict__ count) {
+  extern __shared__ int lu_perm[];
+  __shared__ int piv[LU_OB];
+  __shared__ int cnt;
+  const int n = N - p_lo, ns = p_hi - p_lo;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) lu_perm[i] = i;
+  for (int q = threadIdx.x; q < ns; q += blockDim.x) piv[q] = ipiv[p_lo + q] - p_lo;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < ns; ++q) {
+      const int p = piv[q];
+      if (p != q) {
+        const int t = lu_perm[q];
+        lu_perm[q] = lu_perm[p];
+        lu_perm[p] = t;
+      }
+    }
   }
   __syncthreads();
-  const int c = k0 + pb + blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= N) return;
-  double x[PB];
-#pragma unroll 1
-  for (int r = 0; r < pb; ++r) {
-    double s = A[(long long)(k0 + r) * lda + c];
-    for (int q = 0; q < r; ++q) s -= L11[r][q] * x[q];
-    x[r] = s;
-    A[(long long)(k0 + r) * lda + c] = s;
+  for (int q = threadIdx.x; q < ns; q += blockDim.x) {
+    if (lu_perm[q] != q) {
+      const int m = atomicAdd(&cnt, 1);
+      list_t[m] = p_lo + q;
+      list_src[m] = p_lo + lu_perm[q];
+    }
+    const int p = piv[q];
+    if (p >= ns && lu_perm[p] != p) {
+      bool first = true;
+      for (int q2 = 0; q2 < q; ++q2) first = first && piv[q2] != p;
+      if (first) {
+        const int m = atomicAdd(&cnt, 1);
+        list_t[m] = p_lo + p;
+        list_src[m] = p_lo + lu_perm[p];
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *count = cnt;
+}
+
+// tmp[m][.] <- A[src_m][cols]   (SCATTER = false)      A[t_m][cols] <- tmp[m][.]   (SCATTER = true)
+template <bool SCATTER>
+__global__ void lu_perm_move_kernel(double* __restrict__ A, long long lda, const int* __restrict__ list_t,
+                                    const int* __restrict__ list_src, const int* __restrict__ count,
+                                    double* __restrict__ tmp, int a_lo, int a_hi, int b_lo, int b_hi) {
+  const int m = blockIdx.y;
+  if (m >= *count) return;
+  const int na = a_hi - a_lo, ncols = na + (b_hi - b_lo);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ncols) return;
+  const int c = t < na ? a_lo + t : b_lo + (t - na);
+  if (SCATTER) A[(long long)list_t[m] * lda + c] = tmp[(long long)m * ncols + t];
+  else tmp[(long long)m * ncols + t] = A[(long long)list_src[m] * lda + c];
+}
+
+// Whole pivot sequence of a factorisation as one row permutation (for the right-hand sides of getrs).
+__global__ void __launch_bounds__(1024)
+lu_perm_full_kernel(const int* __restrict__ ipiv, int N, int* __restrict__ perm_out) {
+  extern __shared__ int lu_perm[];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) lu_perm[i] = i;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < N; ++q) {
+      const int p = ipiv[q];
+      if (p != q) {
+        const int t = lu_perm[q];
+        lu_perm[q] = lu_perm[p];
+        lu_perm[p] = t;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) perm_out[i] = lu_perm[i];
+}
+
+// out[i][c] = B[perm[i]][c]  (perm == nullptr: plain copy back)
+__global__ void lu_permute_rows_kernel(const double* __restrict__ src, long long lds,
+                                       double* __restrict__ dst, long long ldd, int N, int nrhs,
+                                       const int* __restrict__ perm) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (c >= nrhs || i >= N) return;
+  const int r = perm ? perm[i] : i;
+  dst[(long long)i * ldd + c] = src[(long long)r * lds + c];
+}
+
+// ---- inner panel on one thread-block cluster ---------------------------------------------------
+// LUC_W columns of the outer panel, rows [j0, N), factorised by ONE launch: the LUC_CL CTAs of a cluster
+// hold the rows in shared memory (column-major, rpc rows per CTA) and run the LUC_W column steps with a
+// single cluster barrier per column.  Before the barrier every CTA writes its pivot candidate (value,
+// row index and the candidate row's LUC_W entries) into a slot of every CTA of the cluster through
+// distributed shared memory, and CTA 0 writes row j the same way; after it each CTA knows the pivot, has
+// the pivot row for the rank-1 step, and the owners of rows j and p put the other row's entries in place
+// -- no second exchange.  Slots are double-buffered by column parity (a CTA can be at most one barrier
+// ahead).  The interchange of the outer panel's other columns is done in global memory by fixed threads
+// of CTA 0 (one per column, so a column's swaps stay in program order), the stores of column j delayed to
+// column j+1 so the load latency is off the critical path.  The same threads finish with
+// U12 <- inv(L11) A12 for the outer panel's columns right of the inner panel.
+namespace cg = cooperative_groups;
+constexpr int LUC_W = 8;
+constexpr int LUC_CL = 8;
+constexpr int LUC_THREADS = 1024;
+constexpr int LUC_RPC_MAX = 3072;  // rows per CTA: 8 columns x 3072 rows x 8 B = 192 KB
+
+struct LucSlot {
+  double val;
+  int idx;
+  int pad;
+  double row[LUC_W];
+};
+
+__device__ __forceinline__ bool luc_better(double v, int i, double bv, int bi) {
+  return v > bv || (v == bv && i < bi);
+}
+
+__global__ void __cluster_dims__(LUC_CL, 1, 1) __launch_bounds__(LUC_THREADS)
+lu_inner_panel_kernel(double* A, long long lda, int N, int k0, int pend, int j0, int w, int rpc,
+                      int* ipiv, int* info) {
+  extern __shared__ double luc_a[];  // [LUC_W][rpc]
+  __shared__ LucSlot slots[2][LUC_CL];
+  __shared__ double rowj[2][LUC_W];
+  __shared__ double wv[LUC_THREADS / 32];
+  __shared__ int wi[LUC_THREADS / 32];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nrows = N - j0;
+  const int base = rank * rpc;
+  const int myrows = max(0, min(rpc, nrows - base));
+  double* a = luc_a;
+
+  for (int li = tid; li < myrows; li += LUC_THREADS) {
+    const double* src = A + (long long)(j0 + base + li) * lda + j0;
+    for (int c = 0; c < w; ++c) a[c * rpc + li] = src[c];
+  }
+  __syncthreads();
+
+  // the thread of CTA 0 that owns outer-panel column sc (outside the inner panel)
+  const int sc = k0 + tid;
+  const bool swapper = rank == 0 && sc < pend && (sc < j0 || sc >= j0 + w);
+  bool pending = false;
+  double va = 0.0, vb = 0.0;
+  long long pa = 0, pb2 = 0;
+
+  for (int jj = 0; jj < w; ++jj) {
+    const int par = jj & 1;
+    // pivot candidate of this thread, warp, CTA
+    double best = -1.0;
+    int bi = 0x7fffffff;
+    for (int li = tid; li < myrows; li += LUC_THREADS) {
+      const int idx = base + li;
+      if (idx >= jj) {
+        const double v = fabs(a[jj * rpc + li]);
+        if (luc_better(v, idx, best, bi)) { best = v; bi = idx; }
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ov = __shfl_down_sync(0xffffffffu, best, off);
+      const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+      if (luc_better(ov, oi, best, bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) { wv[warp] = best; wi[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+      best = wv[lane];
+      bi = wi[lane];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, best, off);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+        if (luc_better(ov, oi, best, bi)) { best = ov; bi = oi; }
+      }
+      best = __shfl_sync(0xffffffffu, best, 0);
+      bi = __shfl_sync(0xffffffffu, bi, 0);
+      double rv = 0.0, rj = 0.0;
+      if (lane < w && best >= 0.0) rv = a[lane * rpc + (bi - base)];
+      if (rank == 0 && lane < w) rj = a[lane * rpc + jj];
+      for (int d = 0; d < LUC_CL; ++d) {
+        LucSlot* rs = cluster.map_shared_rank(&slots[par][rank], d);
+        if (lane < w) rs->row[lane] = rv;
+        if (lane == 0) { rs->val = best; rs->idx = bi; }
+        if (rank == 0 && lane < w) {
+          double* rr = cluster.map_shared_rank(&rowj[par][0], d);
+          rr[lane] = rj;
+        }
+      }
+    }
+    cluster.sync();
+
+    // the pivot: largest candidate, smallest row index on ties; none valid -> keep row j
+    double pv = -1.0;
+    int pidx = 0x7fffffff, wr = 0;
+#pragma unroll
+    for (int d = 0; d < LUC_CL; ++d) {
+      const double v = slots[par][d].val;
+      const int ix = slots[par][d].idx;
+      if (luc_better(v, ix, pv, pidx)) { pv = v; pidx = ix; wr = d; }
+    }
+    if (!(pv >= 0.0)) pidx = jj;
+    const double* prow = (pidx == jj) ? rowj[par] : slots[par][wr].row;
+    const double piv = prow[jj];
+    if (rank == 0 && tid == 0) {
+      ipiv[j0 + jj] = j0 + pidx;
+      if (!(pv > 0.0) && *info == 0) *info = j0 + jj + 1;
+    }
+    if (pidx != jj && tid < w) {
+      if (pidx >= base && pidx < base + myrows) a[tid * rpc + (pidx - base)] = rowj[par][tid];
+      if (rank == 0) a[tid * rpc + jj] = prow[tid];
+    }
+    if (swapper) {
+      if (pending) { A[pa] = vb; A[pb2] = va; pending = false; }
+      if (pidx != jj) {
+        pa = (long long)(j0 + jj) * lda + sc;
+        pb2 = (long long)(j0 + pidx) * lda + sc;
+        va = A[pa];
+        vb = A[pb2];
+        pending = true;
+      }
+    }
+    __syncthreads();
+    // rank-1 step on the rows below j
+    for (int li = tid; li < myrows; li += LUC_THREADS) {
+      if (base + li > jj) {
+        const double l = a[jj * rpc + li] / piv;
+        a[jj * rpc + li] = l;
+        for (int c = jj + 1; c < w; ++c) a[c * rpc + li] -= l * prow[c];
+      }
+    }
+  }
+  if (swapper && pending) { A[pa] = vb; A[pb2] = va; }
+  __syncthreads();
+  for (int li = tid; li < myrows; li += LUC_THREADS) {
+    double* dst = A + (long long)(j0 + base + li) * lda + j0;
+    for (int c = 0; c < w; ++c) dst[c] = a[c * rpc + li];
+  }
+  if (rank == 0 && sc >= j0 + w && sc < pend) {
+    double x[LUC_W];
+#pragma unroll
+    for (int r = 0; r < LUC_W; ++r) {
+      if (r < w) {
+        double sum = A[(long long)(j0 + r) * lda + sc];
+#pragma unroll
+        for (int q = 0; q < r; ++q) sum -= a[q * rpc + r] * x[q];
+        x[r] = sum;
+        A[(long long)(j0 + r) * lda + sc] = sum;
+      }
+    }
   }
 }
 
+// A[i][c] -= sum_q A[i][j0+q] A[j0+q][c] for rows i >= j0 + w and the outer panel's columns right of the
+// inner panel, c in [j0 + w, pend): a warp per row.
+__global__ void __launch_bounds__(256)
+lu_inner_update_kernel(double* __restrict__ A, long long lda, int N, int j0, int w, int pend) {
+  __shared__ double U[LUC_W][PB];
+  const int c0 = j0 + w, ncols = pend - c0;
+  for (int t = threadIdx.x; t < LUC_W * ncols; t += blockDim.x) {
+    const int q = t / ncols, c = t - q * ncols;
+    U[q][c] = q < w ? A[(long long)(j0 + q) * lda + c0 + c] : 0.0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  for (int i = c0 + blockIdx.x * wpb + warp; i < N; i += gridDim.x * wpb) {
+    double* row = A + (long long)i * lda;
+    const double mine = lane < w ? row[j0 + lane] : 0.0;
+    double l[LUC_W];
+#pragma unroll
+    for (int q = 0; q < LUC_W; ++q) l[q] = __shfl_sync(0xffffffffu, mine, q);
+    for (int c = lane; c < ncols; c += 32) {
+      double v = row[c0 + c];
+#pragma unroll
+      for (int q = 0; q < LUC_W; ++q) v -= l[q] * U[q][c];
+      row[c0 + c] = v;
+    }
+  }
+}
+
+// Triangular solve with one diagonal block (pb <= PB rows at k0) of a factorised matrix, unit lower or
+// upper, for the columns [c_lo, c_hi) of X (rows k0.. of X; X may be the factorised matrix itself: U12 <-
+// inv(L11) A12).  A thread per column with the column's pb entries in registers: one round of loads, the
+// substitution fully unrolled in its right-looking form (independent updates after every x_q), one round
+// of stores.  A short last block is padded with the identity.
+template <bool UPPER>
+__global__ void __launch_bounds__(128)
+lu_diag_solve_reg_kernel(const double* LU, long long lda, int k0, int pb, double* X, long long ldx,
+                         int c_lo, int c_hi) {
+  __shared__ double T[PB][PB + 1];
+  for (int idx = threadIdx.x; idx < PB * PB; idx += blockDim.x) {
+    const int r = idx / PB, c = idx - r * PB;
+    double v = r == c ? 1.0 : 0.0;
+    if (r < pb && c < pb) v = LU[(long long)(k0 + r) * lda + k0 + c];
+    T[r][c] = v;
+  }
+  __syncthreads();
+  const int c = c_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= c_hi) return;
+  double x[PB];
+#pragma unroll
+  for (int r = 0; r < PB; ++r) x[r] = r < pb ? X[(long long)(k0 + r) * ldx + c] : 0.0;
+  if (!UPPER) {
+#pragma unroll
+    for (int q = 0; q < PB; ++q) {
+      const double xq = x[q];
+#pragma unroll
+      for (int r = q + 1; r < PB; ++r) x[r] -= T[r][q] * xq;
+    }
+  } else {
+#pragma unroll
+    for (int q = PB - 1; q >= 0; --q) {
+      x[q] /= T[q][q];
+      const double xq = x[q];
+#pragma unroll
+      for (int r = 0; r < q; ++r) x[r] -= T[r][q] * xq;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < PB; ++r)
+    if (r < pb) X[(long long)(k0 + r) * ldx + c] = x[r];
+}
+
+// sequential row interchanges of the right-hand sides (fallback of getrs for very large N)
 __global__ void lu_apply_pivots_kernel(double* __restrict__ B, long long ldb, int nrhs, int N,
                                        const int* __restrict__ ipiv) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -393,38 +764,6 @@ __global__ void lu_apply_pivots_kernel(double* __restrict__ B, long long ldb, in
       const double a = B[(long long)j * ldb + c];
       B[(long long)j * ldb + c] = B[(long long)p * ldb + c];
       B[(long long)p * ldb + c] = a;
-    }
-  }
-}
-
-// Solve with the pb x pb diagonal block (unit lower, or upper) for every rhs column in place.
-__global__ void lu_diag_solve_kernel(const double* __restrict__ LU, long long lda, int k0, int pb,
-                                     double* __restrict__ B, long long ldb, int nrhs, int upper) {
-  __shared__ double T[PB][PB + 1];
-  for (int idx = threadIdx.x; idx < pb * pb; idx += blockDim.x) {
-    const int r = idx / pb, c = idx - r * pb;
-    T[r][c] = LU[(long long)(k0 + r) * lda + k0 + c];
-  }
-  __syncthreads();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= nrhs) return;
-  double x[PB];
-  if (!upper) {
-#pragma unroll 1
-    for (int r = 0; r < pb; ++r) {
-      double s = B[(long long)(k0 + r) * ldb + c];
-      for (int q = 0; q < r; ++q) s -= T[r][q] * x[q];
-      x[r] = s;
-      B[(long long)(k0 + r) * ldb + c] = s;
-    }
-  } else {
-#pragma unroll 1
-    for (int r = pb - 1; r >= 0; --r) {
-      double s = B[(long long)(k0 + r) * ldb + c];
-      for (int q = r + 1; q < pb; ++q) s -= T[r][q] * x[q];
-      s /= T[r][r];
-      x[r] = s;
-      B[(long long)(k0 + r) * ldb + c] = s;
     }
   }
 }
@@ -1063,42 +1402,158 @@ extern "C" int pmr_shifted_combine(const double* M, const double* W, int N, long
 
 // --------------------------------------------------------------------------------------- LU
 extern "C" long long pmr_getrf_work_doubles(int N) {
-  (void)N;
-  return 2 * 1024;  // pivot-search partials (values + indices packed as doubles)
+  // pivot-search partials and the interchange lists (2048 doubles), then the row buffer of the
+  // block interchanges: at most 2 LU_OB rows of N entries
+  return 2048 + 2LL * LU_OB * std::max(N, 1);
 }
 
+static bool g_lu_cluster = true;
+extern "C" void pmr_set_lu_cluster_panel(int on) { g_lu_cluster = on != 0; }
+
+namespace {
+struct LuScratch {
+  double* pval;
+  int* pidx;
+  int* counter;
+  int* count;
+  int* list_t;
+  int* list_src;
+  double* rows;
+};
+
+// one PB-wide panel [k0, pend), rows [k0, N): pivots, multipliers, interchanges inside the panel
+int lu_factor_panel(double* A, long long lda, int N, int k0, int pend, int* ipiv, int* info,
+                    const LuScratch& w, cudaStream_t st) {
+  using namespace pmr;
+  if (g_lu_cluster && N - k0 <= LUC_CL * LUC_RPC_MAX) {
+    // inner panels of LUC_W columns, each one cluster launch (+ one update of the panel's rest)
+    for (int j0 = k0; j0 < pend; j0 += LUC_W) {
+      const int wd = std::min(LUC_W, pend - j0);
+      const int per = (N - j0 + LUC_CL - 1) / LUC_CL;
+      const int rpc = (per + 31) / 32 * 32;
+      const size_t smem = sizeof(double) * LUC_W * (size_t)rpc;
+      lu_inner_panel_kernel<<<LUC_CL, LUC_THREADS, smem, st>>>(A, lda, N, k0, pend, j0, wd, rpc, ipiv,
+                                                               info);
+      PMR_CHECK_LAUNCH("lu_inner_panel_kernel");
+      if (j0 + wd < pend) {
+        const int rows = N - (j0 + wd);
+        const int blocks = std::max(1, std::min(LU_MAX_PARTS, (rows + 7) / 8));
+        lu_inner_update_kernel<<<blocks, 256, 0, st>>>(A, lda, N, j0, wd, pend);
+        PMR_CHECK_LAUNCH("lu_inner_update_kernel");
+      }
+    }
+  } else {
+    // one launch per column: finish the previous column and pick the next pivot; one more finishes
+    // the panel's last column (nothing to do when the panel reaches the last row)
+    for (int j = k0; j <= pend; ++j) {
+      const int rows = N - j;
+      if (rows <= 0) break;
+      const int nparts = std::max(1, std::min(LU_MAX_PARTS, (rows + LU_WARPS - 1) / LU_WARPS));
+      lu_column_kernel<<<nparts, LU_WARPS * 32, 0, st>>>(A, lda, N, k0, pend, j, w.pval, w.pidx,
+                                                         w.counter, ipiv, info);
+      PMR_CHECK_LAUNCH("lu_column_kernel");
+    }
+  }
+  return 0;
+}
+
+// interchanges ipiv[p_lo..p_hi) applied to the columns [a_lo, a_hi) and [b_lo, b_hi)
+int lu_swap_rows(double* A, long long lda, int N, int p_lo, int p_hi, const int* ipiv, int a_lo,
+                 int a_hi, int b_lo, int b_hi, const LuScratch& w, cudaStream_t st) {
+  using namespace pmr;
+  const int ncols = (a_hi - a_lo) + (b_hi - b_lo);
+  if (ncols <= 0 || p_hi <= p_lo) return 0;
+  if (N - p_lo > LU_PERM_MAX_ROWS) {
+    lu_laswp_kernel<<<(ncols + 127) / 128, 128, 0, st>>>(A, lda, p_lo, p_hi, ipiv, a_lo, a_hi, b_lo,
+                                                         b_hi);
+    PMR_CHECK_LAUNCH("lu_laswp_kernel");
+    return 0;
+  }
+  lu_perm_build_kernel<<<1, 256, sizeof(int) * (size_t)(N - p_lo), st>>>(ipiv, p_lo, p_hi, N, w.list_t,
+                                                                         w.list_src, w.count);
+  PMR_CHECK_LAUNCH("lu_perm_build_kernel");
+  const dim3 grid((ncols + 255) / 256, 2 * (p_hi - p_lo));
+  lu_perm_move_kernel<false><<<grid, 256, 0, st>>>(A, lda, w.list_t, w.list_src, w.count, w.rows, a_lo,
+                                                   a_hi, b_lo, b_hi);
+  PMR_CHECK_LAUNCH("lu_perm_move_kernel");
+  lu_perm_move_kernel<true><<<grid, 256, 0, st>>>(A, lda, w.list_t, w.list_src, w.count, w.rows, a_lo,
+                                                  a_hi, b_lo, b_hi);
+  PMR_CHECK_LAUNCH("lu_perm_move_kernel");
+  return 0;
+}
+
+int lu_set_attributes() {
+  using namespace pmr;
+  static bool done = false;
+  if (done) return 0;
+  PMR_CHECK_CUDA(cudaFuncSetAttribute(lu_inner_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(sizeof(double) * LUC_W * LUC_RPC_MAX)));
+  PMR_CHECK_CUDA(cudaFuncSetAttribute(lu_perm_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(sizeof(int) * LU_PERM_MAX_ROWS)));
+  PMR_CHECK_CUDA(cudaFuncSetAttribute(lu_perm_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(sizeof(int) * LU_PERM_MAX_ROWS)));
+  done = true;
+  return 0;
+}
+}  // namespace
+
+// Two levels of blocking: PB-wide panels are factorised and applied inside an LU_OB-wide block only;
+// the trailing matrix sees one interchange pass, one U12 solve and one rank-LU_OB update per block
+// (a quarter of the traffic of rank-PB updates, and GEMMs deep enough to run at the DMMA rate).
 extern "C" int pmr_getrf(double* A, int N, long long lda, int* ipiv, int* info, double* work,
                          void* stream) {
+  using namespace pmr;
   cudaStream_t st = as_stream(stream);
   PMR_REQUIRE(N >= 0, "getrf: bad N");
   PMR_REQUIRE(A && ipiv && info && work, "getrf: null pointer");
+  PMR_TRY(lu_set_attributes());
   PMR_CHECK_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
   if (N == 0) return 0;
-  double* pval = work;
-  int* pidx = reinterpret_cast<int*>(work + 1024);
-  for (int k0 = 0; k0 < N; k0 += PB) {
-    const int pb = std::min(PB, N - k0);
-    const int pend = k0 + pb;
-    for (int j = k0; j < pend; ++j) {
-      const int rows = N - j;
-      const int nparts = std::max(1, std::min(512, (rows + 1023) / 1024));
-      lu_pivot_partial_kernel<<<nparts, 256, 0, st>>>(A, lda, N, j, pval, pidx);
-      PMR_CHECK_LAUNCH("lu_pivot_partial_kernel");
-      lu_pivot_swap_kernel<<<1, 256, 0, st>>>(A, lda, N, j, pval, pidx, nparts, ipiv, info);
-      PMR_CHECK_LAUNCH("lu_pivot_swap_kernel");
-      if (rows > 1) {
-        const int wpb = 8;
-        lu_panel_update_kernel<<<(rows - 1 + wpb - 1) / wpb, wpb * 32, 0, st>>>(A, lda, N, j, pend);
-        PMR_CHECK_LAUNCH("lu_panel_update_kernel");
+  LuScratch w;
+  w.pval = work;
+  w.pidx = reinterpret_cast<int*>(work + 1024);
+  w.counter = w.pidx + LU_MAX_PARTS;
+  w.count = w.pidx + LU_MAX_PARTS + 1;
+  w.list_t = w.pidx + 1024;
+  w.list_src = w.pidx + 1536;
+  w.rows = work + 2048;
+  PMR_CHECK_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(int), st));
+  for (int K0 = 0; K0 < N; K0 += LU_OB) {
+    const int KEND = std::min(K0 + LU_OB, N);
+    for (int k0 = K0; k0 < KEND; k0 += PB) {
+      const int pend = std::min(k0 + PB, KEND), pb = pend - k0;
+      PMR_TRY(lu_factor_panel(A, lda, N, k0, pend, ipiv, info, w, st));
+      PMR_TRY(lu_swap_rows(A, lda, N, k0, pend, ipiv, K0, k0, pend, KEND, w, st));
+      if (pend < KEND) {
+        const int nc = KEND - pend;
+        lu_diag_solve_reg_kernel<false><<<(nc + 127) / 128, 128, 0, st>>>(A, lda, k0, pb, A, lda, pend,
+                                                                          KEND);
+        PMR_CHECK_LAUNCH("lu_diag_solve_reg_kernel");
+        pmr_gemm_t g = make_gemm(N - pend, nc, pb, -1.0, A + (long long)pend * lda + k0, lda, 1,
+                                 A + (long long)k0 * lda + pend, lda, 1, 1.0,
+                                 A + (long long)pend * lda + pend, lda, 1);
+        PMR_TRY(gemm(g, st));
       }
     }
-    const int rest = N - pend;
+    PMR_TRY(lu_swap_rows(A, lda, N, K0, KEND, ipiv, 0, K0, KEND, N, w, st));
+    const int rest = N - KEND;
     if (rest > 0) {
-      lu_trsm_u12_kernel<<<(rest + 127) / 128, 128, 0, st>>>(A, lda, k0, pb, N);
-      PMR_CHECK_LAUNCH("lu_trsm_u12_kernel");
-      pmr_gemm_t g = make_gemm(rest, rest, pb, -1.0, A + (long long)pend * lda + k0, lda, 1,
-                               A + (long long)k0 * lda + pend, lda, 1, 1.0,
-                               A + (long long)pend * lda + pend, lda, 1);
+      // U12 <- inv(L11) A12 with the block's unit-lower L11, PB rows at a time
+      for (int k0 = K0; k0 < KEND; k0 += PB) {
+        const int pend = std::min(k0 + PB, KEND), pb = pend - k0;
+        lu_diag_solve_reg_kernel<false><<<(rest + 127) / 128, 128, 0, st>>>(A, lda, k0, pb, A, lda, KEND,
+                                                                            N);
+        PMR_CHECK_LAUNCH("lu_diag_solve_reg_kernel");
+        if (pend < KEND) {
+          pmr_gemm_t g = make_gemm(KEND - pend, rest, pb, -1.0, A + (long long)pend * lda + k0, lda, 1,
+                                   A + (long long)k0 * lda + KEND, lda, 1, 1.0,
+                                   A + (long long)pend * lda + KEND, lda, 1);
+          PMR_TRY(gemm(g, st));
+        }
+      }
+      pmr_gemm_t g = make_gemm(rest, rest, KEND - K0, -1.0, A + (long long)KEND * lda + K0, lda, 1,
+                               A + (long long)K0 * lda + KEND, lda, 1, 1.0,
+                               A + (long long)KEND * lda + KEND, lda, 1);
       PMR_TRY(gemm(g, st));
     }
   }
@@ -1107,18 +1562,31 @@ extern "C" int pmr_getrf(double* A, int N, long long lda, int* ipiv, int* info, 
 
 extern "C" int pmr_getrs(const double* LU, int N, long long lda, const int* ipiv, double* B,
                          int nrhs, long long ldb, double* work, void* stream) {
+  using namespace pmr;
   cudaStream_t st = as_stream(stream);
-  (void)work;
   PMR_REQUIRE(N >= 0 && nrhs >= 0, "getrs: bad sizes");
   if (N == 0 || nrhs == 0) return 0;
-  PMR_REQUIRE(LU && ipiv && B, "getrs: null pointer");
-  lu_apply_pivots_kernel<<<(nrhs + 63) / 64, 64, 0, st>>>(B, ldb, nrhs, N, ipiv);
-  PMR_CHECK_LAUNCH("lu_apply_pivots_kernel");
+  PMR_REQUIRE(LU && ipiv && B && work, "getrs: null pointer");
+  PMR_TRY(lu_set_attributes());
+  if (N <= LU_PERM_MAX_ROWS) {
+    // the pivot sequence as one permutation: rows gathered into the work buffer and copied back
+    int* perm = reinterpret_cast<int*>(work + (long long)N * nrhs);
+    lu_perm_full_kernel<<<1, 1024, sizeof(int) * (size_t)N, st>>>(ipiv, N, perm);
+    PMR_CHECK_LAUNCH("lu_perm_full_kernel");
+    const dim3 grid((nrhs + 127) / 128, N);
+    lu_permute_rows_kernel<<<grid, 128, 0, st>>>(B, ldb, work, nrhs, N, nrhs, perm);
+    PMR_CHECK_LAUNCH("lu_permute_rows_kernel");
+    lu_permute_rows_kernel<<<grid, 128, 0, st>>>(work, nrhs, B, ldb, N, nrhs, nullptr);
+    PMR_CHECK_LAUNCH("lu_permute_rows_kernel");
+  } else {
+    lu_apply_pivots_kernel<<<(nrhs + 63) / 64, 64, 0, st>>>(B, ldb, nrhs, N, ipiv);
+    PMR_CHECK_LAUNCH("lu_apply_pivots_kernel");
+  }
   // forward (unit lower), right-looking
   for (int k0 = 0; k0 < N; k0 += PB) {
     const int pb = std::min(PB, N - k0), rest = N - k0 - pb;
-    lu_diag_solve_kernel<<<(nrhs + 63) / 64, 64, 0, st>>>(LU, lda, k0, pb, B, ldb, nrhs, 0);
-    PMR_CHECK_LAUNCH("lu_diag_solve_kernel");
+    lu_diag_solve_reg_kernel<false><<<(nrhs + 127) / 128, 128, 0, st>>>(LU, lda, k0, pb, B, ldb, 0, nrhs);
+    PMR_CHECK_LAUNCH("lu_diag_solve_reg_kernel");
     if (rest > 0) {
       pmr_gemm_t g = make_gemm(rest, nrhs, pb, -1.0, LU + (long long)(k0 + pb) * lda + k0, lda, 1,
                                B + (long long)k0 * ldb, ldb, 1, 1.0,
@@ -1130,8 +1598,8 @@ extern "C" int pmr_getrs(const double* LU, int N, long long lda, const int* ipiv
   const int nblk = (N + PB - 1) / PB;
   for (int kb = nblk - 1; kb >= 0; --kb) {
     const int k0 = kb * PB, pb = std::min(PB, N - k0);
-    lu_diag_solve_kernel<<<(nrhs + 63) / 64, 64, 0, st>>>(LU, lda, k0, pb, B, ldb, nrhs, 1);
-    PMR_CHECK_LAUNCH("lu_diag_solve_kernel");
+    lu_diag_solve_reg_kernel<true><<<(nrhs + 127) / 128, 128, 0, st>>>(LU, lda, k0, pb, B, ldb, 0, nrhs);
+    PMR_CHECK_LAUNCH("lu_diag_solve_reg_kernel");
     if (k0 > 0) {
       pmr_gemm_t g = make_gemm(k0, nrhs, pb, -1.0, LU + k0, lda, 1, B + (long long)k0 * ldb, ldb,
                                1, 1.0, B, ldb, 1);

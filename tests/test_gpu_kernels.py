@@ -319,8 +319,16 @@ def test_shifted_combine_lower_triangle():
 
 
 # ----------------------------------------------------------------------------------- LU
-@pytest.mark.parametrize("n", [1, 7, 64, 65, 200])
-def test_getrf_getrs_with_pivoting(n):
+@pytest.fixture(params=[1, 0], ids=["cluster_panel", "column_launches"])
+def lu_panel_mode(request):
+    nv = _nv()
+    nv.lib().pmr_set_lu_cluster_panel(request.param)
+    yield request.param
+    nv.lib().pmr_set_lu_cluster_panel(1)
+
+
+@pytest.mark.parametrize("n", [1, 7, 64, 65, 200, 256, 257, 333, 700, 1500])
+def test_getrf_getrs_with_pivoting(n, lu_panel_mode):
     from pymolresponse_b200 import _engine as eng
 
     nv = _nv()
@@ -329,7 +337,7 @@ def test_getrf_getrs_with_pivoting(n):
     if n > 2:
         A[0, 0] = 0.0          # forces a row interchange in the first column
         A[2, 2] = 1e-14
-    rhs = r.standard_normal((n, 3))
+    rhs = r.standard_normal((n, 3 if n != 333 else 200))
     Ad = nv.to_dev(A).clone()
     ipiv, info = eng.getrf(Ad)
     assert int(nv.to_host(info)[0]) == 0
@@ -343,6 +351,29 @@ def test_getrf_getrs_with_pivoting(n):
     for j, p in enumerate(nv.to_host(ipiv)[:n]):
         PA[[j, p]] = PA[[p, j]]
     assert np.abs(Lm @ Um - PA).max() <= 1e-12 * max(1, n)
+    # partial pivoting: every multiplier is bounded by one, and the pivots are LAPACK's
+    assert np.abs(np.tril(LU, -1)).max() <= 1.0
+    import scipy.linalg
+
+    _, piv = scipy.linalg.lu_factor(A)
+    assert np.array_equal(nv.to_host(ipiv)[:n], piv)
+
+
+def test_getrf_panel_modes_agree_bitwise():
+    from pymolresponse_b200 import _engine as eng
+
+    nv = _nv()
+    A = _rng(171).standard_normal((777, 777))
+    out = []
+    for mode in (1, 0):
+        nv.lib().pmr_set_lu_cluster_panel(mode)
+        Ad = nv.to_dev(A).clone()
+        ipiv, info = eng.getrf(Ad)
+        out.append((nv.to_host(Ad), nv.to_host(ipiv)[:777].copy(), int(nv.to_host(info)[0])))
+    nv.lib().pmr_set_lu_cluster_panel(1)
+    assert out[0][2] == 0 and out[1][2] == 0
+    assert np.array_equal(out[0][1], out[1][1])
+    assert np.abs(out[0][0] - out[1][0]).max() <= 1e-11
 
 
 def test_getrf_flags_singular_matrix():

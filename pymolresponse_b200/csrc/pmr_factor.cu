@@ -671,15 +671,17 @@ lu_inner_panel_kernel(double* A, long long lda, int N, int k0, int pend, int j0,
   if (rank == 0 && sc >= j0 + w && sc < pend) {
     double x[LUC_W];
 #pragma unroll
-    for (int r = 0; r < LUC_W; ++r) {
-      if (r < w) {
-        double sum = A[(long long)(j0 + r) * lda + sc];
+    for (int r = 0; r < LUC_W; ++r) x[r] = r < w ? A[(long long)(j0 + r) * lda + sc] : 0.0;
 #pragma unroll
-        for (int q = 0; q < r; ++q) sum -= a[q * rpc + r] * x[q];
-        x[r] = sum;
-        A[(long long)(j0 + r) * lda + sc] = sum;
+    for (int r = 1; r < LUC_W; ++r) {
+      if (r < w) {
+#pragma unroll
+        for (int q = 0; q < r; ++q) x[r] -= a[q * rpc + r] * x[q];
       }
     }
+#pragma unroll
+    for (int r = 0; r < LUC_W; ++r)
+      if (r < w) A[(long long)(j0 + r) * lda + sc] = x[r];
   }
 }
 
@@ -712,13 +714,18 @@ lu_inner_update_kernel(double* __restrict__ A, long long lda, int N, int j0, int
 
 // Triangular solve with one diagonal block (pb <= PB rows at k0) of a factorised matrix, unit lower or
 // upper, for the columns [c_lo, c_hi) of X (rows k0.. of X; X may be the factorised matrix itself: U12 <-
-// inv(L11) A12).  A thread per column with the column's pb entries in registers: one round of loads, the
-// substitution fully unrolled in its right-looking form (independent updates after every x_q), one round
-// of stores.  A short last block is padded with the identity.
+// inv(L11) A12).  Four lanes share a column (lane = 8 t + column, rows r = 4 i + t in registers), so a warp
+// covers eight columns: one round of loads, the substitution fully unrolled in its right-looking form
+// (x_q comes from its owner by a shuffle, every lane updates its own rows), one round of stores.  A short
+// last block is padded with the identity.
+constexpr int LU_SOLVE_THREADS = 256;
+constexpr int LU_SOLVE_COLS = LU_SOLVE_THREADS / 4;  // columns per block
+
 template <bool UPPER>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(LU_SOLVE_THREADS)
 lu_diag_solve_reg_kernel(const double* LU, long long lda, int k0, int pb, double* X, long long ldx,
                          int c_lo, int c_hi) {
+  static_assert(PB == 64, "row split below assumes a 64-row diagonal block");
   __shared__ double T[PB][PB + 1];
   for (int idx = threadIdx.x; idx < PB * PB; idx += blockDim.x) {
     const int r = idx / PB, c = idx - r * PB;
@@ -727,30 +734,39 @@ lu_diag_solve_reg_kernel(const double* LU, long long lda, int k0, int pb, double
     T[r][c] = v;
   }
   __syncthreads();
-  const int c = c_lo + blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= c_hi) return;
-  double x[PB];
+  const int lane = threadIdx.x & 31, cl = lane & 7, t = lane >> 3;
+  const int c = c_lo + (blockIdx.x * (LU_SOLVE_THREADS / 32) + (threadIdx.x >> 5)) * 8 + cl;
+  const bool live = c < c_hi;  // no early exit: the shuffles below need every lane
+  double x[16];
 #pragma unroll
-  for (int r = 0; r < PB; ++r) x[r] = r < pb ? X[(long long)(k0 + r) * ldx + c] : 0.0;
+  for (int i = 0; i < 16; ++i) {
+    const int r = 4 * i + t;
+    x[i] = (live && r < pb) ? X[(long long)(k0 + r) * ldx + c] : 0.0;
+  }
   if (!UPPER) {
 #pragma unroll
     for (int q = 0; q < PB; ++q) {
-      const double xq = x[q];
+      const double xq = __shfl_sync(0xffffffffu, x[q >> 2], (q & 3) * 8 + cl);
 #pragma unroll
-      for (int r = q + 1; r < PB; ++r) x[r] -= T[r][q] * xq;
+      for (int i = q >> 2; i < 16; ++i)
+        if (i > (q >> 2) || t > (q & 3)) x[i] -= T[4 * i + t][q] * xq;
     }
   } else {
 #pragma unroll
     for (int q = PB - 1; q >= 0; --q) {
-      x[q] /= T[q][q];
-      const double xq = x[q];
+      const double d = x[q >> 2] / T[q][q];
+      if (t == (q & 3)) x[q >> 2] = d;
+      const double xq = __shfl_sync(0xffffffffu, x[q >> 2], (q & 3) * 8 + cl);
 #pragma unroll
-      for (int r = 0; r < q; ++r) x[r] -= T[r][q] * xq;
+      for (int i = 0; i <= (q >> 2); ++i)
+        if (i < (q >> 2) || t < (q & 3)) x[i] -= T[4 * i + t][q] * xq;
     }
   }
 #pragma unroll
-  for (int r = 0; r < PB; ++r)
-    if (r < pb) X[(long long)(k0 + r) * ldx + c] = x[r];
+  for (int i = 0; i < 16; ++i) {
+    const int r = 4 * i + t;
+    if (live && r < pb) X[(long long)(k0 + r) * ldx + c] = x[i];
+  }
 }
 
 // sequential row interchanges of the right-hand sides (fallback of getrs for very large N)
@@ -1526,7 +1542,7 @@ extern "C" int pmr_getrf(double* A, int N, long long lda, int* ipiv, int* info, 
       PMR_TRY(lu_swap_rows(A, lda, N, k0, pend, ipiv, K0, k0, pend, KEND, w, st));
       if (pend < KEND) {
         const int nc = KEND - pend;
-        lu_diag_solve_reg_kernel<false><<<(nc + 127) / 128, 128, 0, st>>>(A, lda, k0, pb, A, lda, pend,
+        lu_diag_solve_reg_kernel<false><<<(nc + LU_SOLVE_COLS - 1) / LU_SOLVE_COLS, LU_SOLVE_THREADS, 0, st>>>(A, lda, k0, pb, A, lda, pend,
                                                                           KEND);
         PMR_CHECK_LAUNCH("lu_diag_solve_reg_kernel");
         pmr_gemm_t g = make_gemm(N - pend, nc, pb, -1.0, A + (long long)pend * lda + k0, lda, 1,
@@ -1541,7 +1557,7 @@ extern "C" int pmr_getrf(double* A, int N, long long lda, int* ipiv, int* info, 
       // U12 <- inv(L11) A12 with the block's unit-lower L11, PB rows at a time
       for (int k0 = K0; k0 < KEND; k0 += PB) {
         const int pend = std::min(k0 + PB, KEND), pb = pend - k0;
-        lu_diag_solve_reg_kernel<false><<<(rest + 127) / 128, 128, 0, st>>>(A, lda, k0, pb, A, lda, KEND,
+        lu_diag_solve_reg_kernel<false><<<(rest + LU_SOLVE_COLS - 1) / LU_SOLVE_COLS, LU_SOLVE_THREADS, 0, st>>>(A, lda, k0, pb, A, lda, KEND,
                                                                             N);
         PMR_CHECK_LAUNCH("lu_diag_solve_reg_kernel");
         if (pend < KEND) {
@@ -1585,7 +1601,7 @@ extern "C" int pmr_getrs(const double* LU, int N, long long lda, const int* ipiv
   // forward (unit lower), right-looking
   for (int k0 = 0; k0 < N; k0 += PB) {
     const int pb = std::min(PB, N - k0), rest = N - k0 - pb;
-    lu_diag_solve_reg_kernel<false><<<(nrhs + 127) / 128, 128, 0, st>>>(LU, lda, k0, pb, B, ldb, 0, nrhs);
+    lu_diag_solve_reg_kernel<false><<<(nrhs + LU_SOLVE_COLS - 1) / LU_SOLVE_COLS, LU_SOLVE_THREADS, 0, st>>>(LU, lda, k0, pb, B, ldb, 0, nrhs);
     PMR_CHECK_LAUNCH("lu_diag_solve_reg_kernel");
     if (rest > 0) {
       pmr_gemm_t g = make_gemm(rest, nrhs, pb, -1.0, LU + (long long)(k0 + pb) * lda + k0, lda, 1,
@@ -1598,7 +1614,7 @@ extern "C" int pmr_getrs(const double* LU, int N, long long lda, const int* ipiv
   const int nblk = (N + PB - 1) / PB;
   for (int kb = nblk - 1; kb >= 0; --kb) {
     const int k0 = kb * PB, pb = std::min(PB, N - k0);
-    lu_diag_solve_reg_kernel<true><<<(nrhs + 127) / 128, 128, 0, st>>>(LU, lda, k0, pb, B, ldb, 0, nrhs);
+    lu_diag_solve_reg_kernel<true><<<(nrhs + LU_SOLVE_COLS - 1) / LU_SOLVE_COLS, LU_SOLVE_THREADS, 0, st>>>(LU, lda, k0, pb, B, ldb, 0, nrhs);
     PMR_CHECK_LAUNCH("lu_diag_solve_reg_kernel");
     if (k0 > 0) {
       pmr_gemm_t g = make_gemm(k0, nrhs, pb, -1.0, LU + k0, lda, 1, B + (long long)k0 * ldb, ldb,

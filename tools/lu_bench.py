@@ -11,7 +11,8 @@ from pymolresponse_b200 import _engine as eng  # noqa: E402
 from pymolresponse_b200 import _native as nv  # noqa: E402
 
 torch.manual_seed(0)
-for N in (2048, 4096, 8192, 14336):
+SIZES = [int(a) for a in sys.argv[1:]] or [2048, 4096, 8192, 14336]
+for N in SIZES:
     X = torch.randn(N, N, dtype=torch.float64, device="cuda")
     A = X + N ** 0.5 * torch.eye(N, dtype=torch.float64, device="cuda")
     B = torch.randn(N, 6, dtype=torch.float64, device="cuda")

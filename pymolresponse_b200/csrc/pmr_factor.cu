@@ -535,6 +535,8 @@ constexpr int LUC_W = 8;
 constexpr int LUC_CL = 8;
 constexpr int LUC_THREADS = 1024;
 constexpr int LUC_RPC_MAX = 3072;  // rows per CTA: 8 columns x 3072 rows x 8 B = 192 KB
+constexpr int LUC_PAD = 4;         // column stride rpc + 4: the row-wise load / store spreads over the banks
+static_assert(LUC_W == 8, "row-wise load / store below moves 8 columns per row");
 
 struct LucSlot {
   double val;
@@ -547,13 +549,32 @@ __device__ __forceinline__ bool luc_better(double v, int i, double bv, int bi) {
   return v > bv || (v == bv && i < bi);
 }
 
+// Pivot candidates as ordered integers: a non-negative double compares like its bit pattern, +1 keeps
+// zero apart from "no candidate" (key 0).  Warp-wide arg-max with the smallest index on ties in three
+// redux operations (high word, low word, index); every lane gets the result.
+__device__ __forceinline__ unsigned long long luc_key(double v) {
+  return v >= 0.0 ? (unsigned long long)__double_as_longlong(v) + 1ull : 0ull;
+}
+__device__ __forceinline__ double luc_value(unsigned long long key) {
+  return key ? __longlong_as_double((long long)(key - 1ull)) : -1.0;
+}
+__device__ __forceinline__ void luc_warp_argmax(unsigned long long& key, int& idx) {
+  const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  bool cand = hi == mh;
+  const unsigned ml = __reduce_max_sync(0xffffffffu, cand ? lo : 0u);
+  cand = cand && lo == ml;
+  idx = __reduce_min_sync(0xffffffffu, cand ? idx : 0x7fffffff);
+  key = ((unsigned long long)mh << 32) | ml;
+}
+
 __global__ void __cluster_dims__(LUC_CL, 1, 1) __launch_bounds__(LUC_THREADS)
 lu_inner_panel_kernel(double* A, long long lda, int N, int k0, int pend, int j0, int w, int rpc,
                       int* ipiv, int* info) {
-  extern __shared__ double luc_a[];  // [LUC_W][rpc]
+  extern __shared__ double luc_a[];  // [LUC_W][rpc + LUC_PAD]
   __shared__ LucSlot slots[2][LUC_CL];
   __shared__ double rowj[2][LUC_W];
-  __shared__ double wv[LUC_THREADS / 32];
+  __shared__ unsigned long long wk[LUC_THREADS / 32];
   __shared__ int wi[LUC_THREADS / 32];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -561,13 +582,22 @@ lu_inner_panel_kernel(double* A, long long lda, int N, int k0, int pend, int j0,
   const int nrows = N - j0;
   const int base = rank * rpc;
   const int myrows = max(0, min(rpc, nrows - base));
+  const int ld = rpc + LUC_PAD;  // column stride in shared memory
   double* a = luc_a;
+  // development aid (pmr_debug_potf2_timing): phase stamps of the first inner panel of a factorisation
+#define LUC_TICK(slot)                                                                   \
+  do {                                                                                   \
+    if (tid == 0 && rank == 0 && j0 == 0 && g_potf2_clock) g_potf2_clock[slot] = clock64(); \
+  } while (0)
+  LUC_TICK(0);
 
-  for (int li = tid; li < myrows; li += LUC_THREADS) {
-    const double* src = A + (long long)(j0 + base + li) * lda + j0;
-    for (int c = 0; c < w; ++c) a[c * rpc + li] = src[c];
+  // eight lanes move one row (64 contiguous bytes) per step
+  for (int e = tid; e < myrows * LUC_W; e += LUC_THREADS) {
+    const int li = e >> 3, c = e & 7;
+    if (c < w) a[c * ld + li] = A[(long long)(j0 + base + li) * lda + j0 + c];
   }
   __syncthreads();
+  LUC_TICK(1);
 
   // the thread of CTA 0 that owns outer-panel column sc (outside the inner panel)
   const int sc = k0 + tid;
@@ -584,32 +614,23 @@ lu_inner_panel_kernel(double* A, long long lda, int N, int k0, int pend, int j0,
     for (int li = tid; li < myrows; li += LUC_THREADS) {
       const int idx = base + li;
       if (idx >= jj) {
-        const double v = fabs(a[jj * rpc + li]);
+        const double v = fabs(a[jj * ld + li]);
         if (luc_better(v, idx, best, bi)) { best = v; bi = idx; }
       }
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const double ov = __shfl_down_sync(0xffffffffu, best, off);
-      const int oi = __shfl_down_sync(0xffffffffu, bi, off);
-      if (luc_better(ov, oi, best, bi)) { best = ov; bi = oi; }
-    }
-    if (lane == 0) { wv[warp] = best; wi[warp] = bi; }
+    unsigned long long key = luc_key(best);
+    luc_warp_argmax(key, bi);
+    if (lane == 0) { wk[warp] = key; wi[warp] = bi; }
     __syncthreads();
     if (warp == 0) {
-      best = wv[lane];
+      key = wk[lane];
       bi = wi[lane];
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const double ov = __shfl_down_sync(0xffffffffu, best, off);
-        const int oi = __shfl_down_sync(0xffffffffu, bi, off);
-        if (luc_better(ov, oi, best, bi)) { best = ov; bi = oi; }
-      }
-      best = __shfl_sync(0xffffffffu, best, 0);
-      bi = __shfl_sync(0xffffffffu, bi, 0);
+      luc_warp_argmax(key, bi);
+      best = luc_value(key);
+      LUC_TICK(2 + 5 * jj);
       double rv = 0.0, rj = 0.0;
-      if (lane < w && best >= 0.0) rv = a[lane * rpc + (bi - base)];
-      if (rank == 0 && lane < w) rj = a[lane * rpc + jj];
+      if (lane < w && best >= 0.0) rv = a[lane * ld + (bi - base)];
+      if (rank == 0 && lane < w) rj = a[lane * ld + jj];
       for (int d = 0; d < LUC_CL; ++d) {
         LucSlot* rs = cluster.map_shared_rank(&slots[par][rank], d);
         if (lane < w) rs->row[lane] = rv;
@@ -620,7 +641,9 @@ lu_inner_panel_kernel(double* A, long long lda, int N, int k0, int pend, int j0,
         }
       }
     }
+    LUC_TICK(3 + 5 * jj);
     cluster.sync();
+    LUC_TICK(4 + 5 * jj);
 
     // the pivot: largest candidate, smallest row index on ties; none valid -> keep row j
     double pv = -1.0;
@@ -634,13 +657,17 @@ lu_inner_panel_kernel(double* A, long long lda, int N, int k0, int pend, int j0,
     if (!(pv >= 0.0)) pidx = jj;
     const double* prow = (pidx == jj) ? rowj[par] : slots[par][wr].row;
     const double piv = prow[jj];
+    // multipliers by the reciprocal pivot, as LAPACK's dgetf2 / dgetrf2 scale the column (guarded
+    // against a reciprocal that would overflow)
+    const bool use_rpiv = fabs(piv) >= 2.2250738585072014e-308;
+    const double rpiv = 1.0 / piv;
     if (rank == 0 && tid == 0) {
       ipiv[j0 + jj] = j0 + pidx;
       if (!(pv > 0.0) && *info == 0) *info = j0 + jj + 1;
     }
     if (pidx != jj && tid < w) {
-      if (pidx >= base && pidx < base + myrows) a[tid * rpc + (pidx - base)] = rowj[par][tid];
-      if (rank == 0) a[tid * rpc + jj] = prow[tid];
+      if (pidx >= base && pidx < base + myrows) a[tid * ld + (pidx - base)] = rowj[par][tid];
+      if (rank == 0) a[tid * ld + jj] = prow[tid];
     }
     if (swapper) {
       if (pending) { A[pa] = vb; A[pb2] = va; pending = false; }
@@ -653,21 +680,25 @@ lu_inner_panel_kernel(double* A, long long lda, int N, int k0, int pend, int j0,
       }
     }
     __syncthreads();
+    LUC_TICK(5 + 5 * jj);
     // rank-1 step on the rows below j
     for (int li = tid; li < myrows; li += LUC_THREADS) {
       if (base + li > jj) {
-        const double l = a[jj * rpc + li] / piv;
-        a[jj * rpc + li] = l;
-        for (int c = jj + 1; c < w; ++c) a[c * rpc + li] -= l * prow[c];
+        const double l = use_rpiv ? a[jj * ld + li] * rpiv : a[jj * ld + li] / piv;
+        a[jj * ld + li] = l;
+        for (int c = jj + 1; c < w; ++c) a[c * ld + li] -= l * prow[c];
       }
     }
+    LUC_TICK(6 + 5 * jj);
   }
   if (swapper && pending) { A[pa] = vb; A[pb2] = va; }
   __syncthreads();
-  for (int li = tid; li < myrows; li += LUC_THREADS) {
-    double* dst = A + (long long)(j0 + base + li) * lda + j0;
-    for (int c = 0; c < w; ++c) dst[c] = a[c * rpc + li];
+  LUC_TICK(42);
+  for (int e = tid; e < myrows * LUC_W; e += LUC_THREADS) {
+    const int li = e >> 3, c = e & 7;
+    if (c < w) A[(long long)(j0 + base + li) * lda + j0 + c] = a[c * ld + li];
   }
+  LUC_TICK(43);
   if (rank == 0 && sc >= j0 + w && sc < pend) {
     double x[LUC_W];
 #pragma unroll
@@ -676,13 +707,15 @@ lu_inner_panel_kernel(double* A, long long lda, int N, int k0, int pend, int j0,
     for (int r = 1; r < LUC_W; ++r) {
       if (r < w) {
 #pragma unroll
-        for (int q = 0; q < r; ++q) x[r] -= a[q * rpc + r] * x[q];
+        for (int q = 0; q < r; ++q) x[r] -= a[q * ld + r] * x[q];
       }
     }
 #pragma unroll
     for (int r = 0; r < LUC_W; ++r)
       if (r < w) A[(long long)(j0 + r) * lda + sc] = x[r];
   }
+  LUC_TICK(44);
+#undef LUC_TICK
 }
 
 // A[i][c] -= sum_q A[i][j0+q] A[j0+q][c] for rows i >= j0 + w and the outer panel's columns right of the
@@ -1447,7 +1480,7 @@ int lu_factor_panel(double* A, long long lda, int N, int k0, int pend, int* ipiv
       const int wd = std::min(LUC_W, pend - j0);
       const int per = (N - j0 + LUC_CL - 1) / LUC_CL;
       const int rpc = (per + 31) / 32 * 32;
-      const size_t smem = sizeof(double) * LUC_W * (size_t)rpc;
+      const size_t smem = sizeof(double) * LUC_W * (size_t)(rpc + LUC_PAD);
       lu_inner_panel_kernel<<<LUC_CL, LUC_THREADS, smem, st>>>(A, lda, N, k0, pend, j0, wd, rpc, ipiv,
                                                                info);
       PMR_CHECK_LAUNCH("lu_inner_panel_kernel");
@@ -1503,7 +1536,7 @@ int lu_set_attributes() {
   static bool done = false;
   if (done) return 0;
   PMR_CHECK_CUDA(cudaFuncSetAttribute(lu_inner_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(sizeof(double) * LUC_W * LUC_RPC_MAX)));
+                                      (int)(sizeof(double) * LUC_W * (LUC_RPC_MAX + LUC_PAD))));
   PMR_CHECK_CUDA(cudaFuncSetAttribute(lu_perm_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(sizeof(int) * LU_PERM_MAX_ROWS)));
   PMR_CHECK_CUDA(cudaFuncSetAttribute(lu_perm_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

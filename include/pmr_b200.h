@@ -168,8 +168,9 @@ long long pmr_potrf_dinv_doubles(int N);
  * (look-ahead).  Switch it off to get serialised, individually timeable kernels (bench.py's
  * roofline pass does); results are identical either way.  Per calling thread; default on. */
 void pmr_set_lookahead(int on);
-/* Development aid: while a device buffer (>= 19 long long) is set, the diagonal-block kernel of the
- * Cholesky stores clock64() at its phase boundaries (tools/potf2_phases.py); NULL switches it off. */
+/* Development aid: while a device buffer (>= 64 long long) is set, the diagonal-block kernel of the
+ * Cholesky (tools/potf2_phases.py) and the first cluster-resident inner panel of pmr_getrf
+ * (tools/lu_panel_phases.py) store clock64() at their phase boundaries; NULL switches it off. */
 int pmr_debug_potf2_timing(long long* device_buffer);
 int pmr_potrf(double* A, int N, long long lda, int batch, long long stride_a, double* dinv,
               int* info /* device, batch ints */, void* stream);
@@ -235,7 +236,7 @@ int pmr_getrf(double* A, int N, long long lda, int* ipiv /* device, N */, int* i
               double* work /* pmr_getrf_work_doubles(N) */, void* stream);
 long long pmr_getrf_work_doubles(int N);
 /* Panels of the pivoted LU are factorised eight columns per launch by one thread-block cluster (rows in
- * shared memory, one cluster barrier per column) while N - k0 <= 24576 rows remain, and one launch per
+ * registers, one cluster barrier per column) while N - k0 <= 16384 rows remain, and one launch per
  * column otherwise.  Switching the cluster panel off forces the per-column path (the tests run both;
  * the pivots and the factors are the same).  Default on. */
 void pmr_set_lu_cluster_panel(int on);

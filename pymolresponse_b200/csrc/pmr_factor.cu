@@ -520,7 +520,7 @@ __global__ void lu_permute_rows_kernel(const double* __restrict__ src, long long
 
 // ---- inner panel on one thread-block cluster ---------------------------------------------------
 // LUC_W columns of the outer panel, rows [j0, N), factorised by ONE launch: the LUC_CL CTAs of a cluster
-// hold the rows in shared memory (column-major, rpc rows per CTA) and run the LUC_W column steps with a
+// hold the rows in registers (rpc rows per CTA, staged through shared memory) and run the LUC_W column steps with a
 // single cluster barrier per column.  Before the barrier every CTA writes its pivot candidate (value,
 // row index and the candidate row's LUC_W entries) into a slot of every CTA of the cluster through
 // distributed shared memory, and CTA 0 writes row j the same way; after it each CTA knows the pivot, has
@@ -533,13 +533,13 @@ __global__ void lu_permute_rows_kernel(const double* __restrict__ src, long long
 namespace cg = cooperative_groups;
 constexpr int LUC_W = 8;
 constexpr int LUC_CL = 8;
-constexpr int LUC_THREADS = 1024;
-constexpr int LUC_RPC_MAX = 3072;  // rows per CTA: 8 columns x 3072 rows x 8 B = 192 KB
+constexpr int LUC_THREADS = 512;
+constexpr int LUC_RPC_MAX = 2048;  // rows per CTA: four register-resident rows per thread
 constexpr int LUC_PAD = 4;         // column stride rpc + 4: the row-wise load / store spreads over the banks
 static_assert(LUC_W == 8, "row-wise load / store below moves 8 columns per row");
 
 struct LucSlot {
-  double val;
+  unsigned long long key;  // luc_key of the candidate's magnitude
   int idx;
   int pad;
   double row[LUC_W];
@@ -568,21 +568,25 @@ __device__ __forceinline__ void luc_warp_argmax(unsigned long long& key, int& id
   key = ((unsigned long long)mh << 32) | ml;
 }
 
+// Rows live in registers (RPT rows of LUC_W entries per thread: thread tid owns the local rows tid + k *
+// LUC_THREADS), so the rank-1 steps and the candidate scans run at register speed; shared memory only
+// stages the panel in and out (eight lanes per 64-byte row) and carries the pivot exchange.
+template <int RPT>
 __global__ void __cluster_dims__(LUC_CL, 1, 1) __launch_bounds__(LUC_THREADS)
 lu_inner_panel_kernel(double* A, long long lda, int N, int k0, int pend, int j0, int w, int rpc,
                       int* ipiv, int* info) {
-  extern __shared__ double luc_a[];  // [LUC_W][rpc + LUC_PAD]
+  extern __shared__ double luc_a[];  // [LUC_W][rpc + LUC_PAD], staging only
   __shared__ LucSlot slots[2][LUC_CL];
   __shared__ double rowj[2][LUC_W];
-  __shared__ unsigned long long wk[LUC_THREADS / 32];
-  __shared__ int wi[LUC_THREADS / 32];
+  __shared__ unsigned long long wk[32];
+  __shared__ int wi[32];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nrows = N - j0;
   const int base = rank * rpc;
   const int myrows = max(0, min(rpc, nrows - base));
-  const int ld = rpc + LUC_PAD;  // column stride in shared memory
+  const int ld = rpc + LUC_PAD;
   double* a = luc_a;
   // development aid (pmr_debug_potf2_timing): phase stamps of the first inner panel of a factorisation
 #define LUC_TICK(slot)                                                                   \
@@ -591,12 +595,18 @@ lu_inner_panel_kernel(double* A, long long lda, int N, int k0, int pend, int j0,
   } while (0)
   LUC_TICK(0);
 
-  // eight lanes move one row (64 contiguous bytes) per step
   for (int e = tid; e < myrows * LUC_W; e += LUC_THREADS) {
     const int li = e >> 3, c = e & 7;
     if (c < w) a[c * ld + li] = A[(long long)(j0 + base + li) * lda + j0 + c];
   }
   __syncthreads();
+  double x[RPT][LUC_W];
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int li = tid + k * LUC_THREADS;
+#pragma unroll
+    for (int c = 0; c < LUC_W; ++c) x[k][c] = (li < myrows && c < w) ? a[c * ld + li] : 0.0;
+  }
   LUC_TICK(1);
 
   // the thread of CTA 0 that owns outer-panel column sc (outside the inner panel)
@@ -606,92 +616,143 @@ lu_inner_panel_kernel(double* A, long long lda, int N, int k0, int pend, int j0,
   double va = 0.0, vb = 0.0;
   long long pa = 0, pb2 = 0;
 
-  for (int jj = 0; jj < w; ++jj) {
-    const int par = jj & 1;
-    // pivot candidate of this thread, warp, CTA
-    double best = -1.0;
-    int bi = 0x7fffffff;
-    for (int li = tid; li < myrows; li += LUC_THREADS) {
-      const int idx = base + li;
-      if (idx >= jj) {
-        const double v = fabs(a[jj * ld + li]);
-        if (luc_better(v, idx, best, bi)) { best = v; bi = idx; }
-      }
-    }
-    unsigned long long key = luc_key(best);
-    luc_warp_argmax(key, bi);
-    if (lane == 0) { wk[warp] = key; wi[warp] = bi; }
-    __syncthreads();
-    if (warp == 0) {
-      key = wk[lane];
-      bi = wi[lane];
-      luc_warp_argmax(key, bi);
-      best = luc_value(key);
-      LUC_TICK(2 + 5 * jj);
-      double rv = 0.0, rj = 0.0;
-      if (lane < w && best >= 0.0) rv = a[lane * ld + (bi - base)];
-      if (rank == 0 && lane < w) rj = a[lane * ld + jj];
-      for (int d = 0; d < LUC_CL; ++d) {
-        LucSlot* rs = cluster.map_shared_rank(&slots[par][rank], d);
-        if (lane < w) rs->row[lane] = rv;
-        if (lane == 0) { rs->val = best; rs->idx = bi; }
-        if (rank == 0 && lane < w) {
-          double* rr = cluster.map_shared_rank(&rowj[par][0], d);
-          rr[lane] = rj;
+#pragma unroll
+  for (int jj = 0; jj < LUC_W; ++jj) {
+    if (jj < w) {  // uniform over the cluster
+      const int par = jj & 1;
+      // pivot candidate of this thread, warp, CTA
+      double best = -1.0;
+      int bi = 0x7fffffff;
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        const int li = tid + k * LUC_THREADS;
+        if (li < myrows && base + li >= jj) {
+          const double v = fabs(x[k][jj]);
+          if (luc_better(v, base + li, best, bi)) { best = v; bi = base + li; }
         }
       }
-    }
-    LUC_TICK(3 + 5 * jj);
-    cluster.sync();
-    LUC_TICK(4 + 5 * jj);
-
-    // the pivot: largest candidate, smallest row index on ties; none valid -> keep row j
-    double pv = -1.0;
-    int pidx = 0x7fffffff, wr = 0;
+      unsigned long long key = luc_key(best);
+      luc_warp_argmax(key, bi);
+      if (lane == 0) { wk[warp] = key; wi[warp] = bi; }
+      __syncthreads();
+      // every warp finishes the CTA-level reduction for itself (no second block barrier)
+      key = lane < LUC_THREADS / 32 ? wk[lane] : 0ull;
+      bi = lane < LUC_THREADS / 32 ? wi[lane] : 0x7fffffff;
+      luc_warp_argmax(key, bi);
+      LUC_TICK(2 + 5 * jj);
+      // the owner of the CTA's candidate row writes it into this CTA's slot of every CTA
+      if (key != 0ull) {
+        const int lo = bi - base;
+        if ((lo & (LUC_THREADS - 1)) == tid) {
+          const int kk = lo / LUC_THREADS;
+          double rv[LUC_W];
 #pragma unroll
-    for (int d = 0; d < LUC_CL; ++d) {
-      const double v = slots[par][d].val;
-      const int ix = slots[par][d].idx;
-      if (luc_better(v, ix, pv, pidx)) { pv = v; pidx = ix; wr = d; }
-    }
-    if (!(pv >= 0.0)) pidx = jj;
-    const double* prow = (pidx == jj) ? rowj[par] : slots[par][wr].row;
-    const double piv = prow[jj];
-    // multipliers by the reciprocal pivot, as LAPACK's dgetf2 / dgetrf2 scale the column (guarded
-    // against a reciprocal that would overflow)
-    const bool use_rpiv = fabs(piv) >= 2.2250738585072014e-308;
-    const double rpiv = 1.0 / piv;
-    if (rank == 0 && tid == 0) {
-      ipiv[j0 + jj] = j0 + pidx;
-      if (!(pv > 0.0) && *info == 0) *info = j0 + jj + 1;
-    }
-    if (pidx != jj && tid < w) {
-      if (pidx >= base && pidx < base + myrows) a[tid * ld + (pidx - base)] = rowj[par][tid];
-      if (rank == 0) a[tid * ld + jj] = prow[tid];
-    }
-    if (swapper) {
-      if (pending) { A[pa] = vb; A[pb2] = va; pending = false; }
+          for (int c = 0; c < LUC_W; ++c) {
+            rv[c] = x[0][c];
+#pragma unroll
+            for (int k = 1; k < RPT; ++k)
+              if (kk == k) rv[c] = x[k][c];
+          }
+          for (int d = 0; d < LUC_CL; ++d) {
+            LucSlot* rs = cluster.map_shared_rank(&slots[par][rank], d);
+#pragma unroll
+            for (int c = 0; c < LUC_W; ++c) rs->row[c] = rv[c];
+            rs->key = key;
+            rs->idx = bi;
+          }
+        }
+      } else if (tid == 0) {
+        for (int d = 0; d < LUC_CL; ++d) {
+          LucSlot* rs = cluster.map_shared_rank(&slots[par][rank], d);
+          rs->key = 0ull;
+          rs->idx = 0x7fffffff;
+        }
+      }
+      if (rank == 0 && tid == jj) {  // row j is local row jj of CTA 0: thread jj, k = 0
+        for (int d = 0; d < LUC_CL; ++d) {
+          double* rr = cluster.map_shared_rank(&rowj[par][0], d);
+#pragma unroll
+          for (int c = 0; c < LUC_W; ++c) rr[c] = x[0][c];
+        }
+      }
+      LUC_TICK(3 + 5 * jj);
+      cluster.sync();
+      LUC_TICK(4 + 5 * jj);
+
+      // the pivot: largest candidate, smallest row index on ties; none valid -> keep row j
+      unsigned long long pk = 0ull;
+      int pidx = 0x7fffffff, wr = 0;
+#pragma unroll
+      for (int d = 0; d < LUC_CL; ++d) {
+        const unsigned long long kd = slots[par][d].key;
+        const int ix = slots[par][d].idx;
+        if (kd > pk || (kd == pk && ix < pidx)) { pk = kd; pidx = ix; wr = d; }
+      }
+      if (pk == 0ull) pidx = jj;
+      const double* prow_s = (pidx == jj) ? rowj[par] : slots[par][wr].row;
+      double prow[LUC_W];
+#pragma unroll
+      for (int c = 0; c < LUC_W; ++c) prow[c] = prow_s[c];
+      const double piv = prow[jj];
+      // multipliers by the reciprocal pivot, as LAPACK's dgetf2 / dgetrf2 scale the column (guarded
+      // against a reciprocal that would overflow)
+      const bool use_rpiv = fabs(piv) >= 2.2250738585072014e-308;
+      const double rpiv = 1.0 / piv;
+      if (rank == 0 && tid == 0) {
+        ipiv[j0 + jj] = j0 + pidx;
+        if (pk <= 1ull && *info == 0) *info = j0 + jj + 1;  // key 1 is the value 0.0
+      }
       if (pidx != jj) {
-        pa = (long long)(j0 + jj) * lda + sc;
-        pb2 = (long long)(j0 + pidx) * lda + sc;
-        va = A[pa];
-        vb = A[pb2];
-        pending = true;
+        // row j's entries go to the pivot row's position, the pivot row to position j
+        const int lo = pidx - base;
+        if (lo >= 0 && lo < myrows && (lo & (LUC_THREADS - 1)) == tid) {
+          const int kk = lo / LUC_THREADS;
+#pragma unroll
+          for (int c = 0; c < LUC_W; ++c) {
+            const double v = rowj[par][c];
+#pragma unroll
+            for (int k = 0; k < RPT; ++k)
+              if (kk == k) x[k][c] = v;
+          }
+        }
+        if (rank == 0 && tid == jj) {
+#pragma unroll
+          for (int c = 0; c < LUC_W; ++c) x[0][c] = prow[c];
+        }
       }
-    }
-    __syncthreads();
-    LUC_TICK(5 + 5 * jj);
-    // rank-1 step on the rows below j
-    for (int li = tid; li < myrows; li += LUC_THREADS) {
-      if (base + li > jj) {
-        const double l = use_rpiv ? a[jj * ld + li] * rpiv : a[jj * ld + li] / piv;
-        a[jj * ld + li] = l;
-        for (int c = jj + 1; c < w; ++c) a[c * ld + li] -= l * prow[c];
+      if (swapper) {
+        if (pending) { A[pa] = vb; A[pb2] = va; pending = false; }
+        if (pidx != jj) {
+          pa = (long long)(j0 + jj) * lda + sc;
+          pb2 = (long long)(j0 + pidx) * lda + sc;
+          va = A[pa];
+          vb = A[pb2];
+          pending = true;
+        }
       }
+      LUC_TICK(5 + 5 * jj);
+      // rank-1 step on the rows below j
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        const int li = tid + k * LUC_THREADS;
+        if (li < myrows && base + li > jj) {
+          const double l = use_rpiv ? x[k][jj] * rpiv : x[k][jj] / piv;
+          x[k][jj] = l;
+#pragma unroll
+          for (int c = jj + 1; c < LUC_W; ++c) x[k][c] -= l * prow[c];
+        }
+      }
+      LUC_TICK(6 + 5 * jj);
     }
-    LUC_TICK(6 + 5 * jj);
   }
   if (swapper && pending) { A[pa] = vb; A[pb2] = va; }
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int li = tid + k * LUC_THREADS;
+#pragma unroll
+    for (int c = 0; c < LUC_W; ++c)
+      if (li < myrows && c < w) a[c * ld + li] = x[k][c];
+  }
   __syncthreads();
   LUC_TICK(42);
   for (int e = tid; e < myrows * LUC_W; e += LUC_THREADS) {
@@ -700,19 +761,19 @@ lu_inner_panel_kernel(double* A, long long lda, int N, int k0, int pend, int j0,
   }
   LUC_TICK(43);
   if (rank == 0 && sc >= j0 + w && sc < pend) {
-    double x[LUC_W];
+    double u[LUC_W];
 #pragma unroll
-    for (int r = 0; r < LUC_W; ++r) x[r] = r < w ? A[(long long)(j0 + r) * lda + sc] : 0.0;
+    for (int r = 0; r < LUC_W; ++r) u[r] = r < w ? A[(long long)(j0 + r) * lda + sc] : 0.0;
 #pragma unroll
     for (int r = 1; r < LUC_W; ++r) {
       if (r < w) {
 #pragma unroll
-        for (int q = 0; q < r; ++q) x[r] -= a[q * ld + r] * x[q];
+        for (int q = 0; q < r; ++q) u[r] -= a[q * ld + r] * u[q];
       }
     }
 #pragma unroll
     for (int r = 0; r < LUC_W; ++r)
-      if (r < w) A[(long long)(j0 + r) * lda + sc] = x[r];
+      if (r < w) A[(long long)(j0 + r) * lda + sc] = u[r];
   }
   LUC_TICK(44);
 #undef LUC_TICK
@@ -1481,8 +1542,15 @@ int lu_factor_panel(double* A, long long lda, int N, int k0, int pend, int* ipiv
       const int per = (N - j0 + LUC_CL - 1) / LUC_CL;
       const int rpc = (per + 31) / 32 * 32;
       const size_t smem = sizeof(double) * LUC_W * (size_t)(rpc + LUC_PAD);
-      lu_inner_panel_kernel<<<LUC_CL, LUC_THREADS, smem, st>>>(A, lda, N, k0, pend, j0, wd, rpc, ipiv,
-                                                               info);
+      if (rpc <= LUC_THREADS)
+        lu_inner_panel_kernel<1><<<LUC_CL, LUC_THREADS, smem, st>>>(A, lda, N, k0, pend, j0, wd, rpc,
+                                                                    ipiv, info);
+      else if (rpc <= 2 * LUC_THREADS)
+        lu_inner_panel_kernel<2><<<LUC_CL, LUC_THREADS, smem, st>>>(A, lda, N, k0, pend, j0, wd, rpc,
+                                                                    ipiv, info);
+      else
+        lu_inner_panel_kernel<4><<<LUC_CL, LUC_THREADS, smem, st>>>(A, lda, N, k0, pend, j0, wd, rpc,
+                                                                    ipiv, info);
       PMR_CHECK_LAUNCH("lu_inner_panel_kernel");
       if (j0 + wd < pend) {
         const int rows = N - (j0 + wd);
@@ -1535,8 +1603,13 @@ int lu_set_attributes() {
   using namespace pmr;
   static bool done = false;
   if (done) return 0;
-  PMR_CHECK_CUDA(cudaFuncSetAttribute(lu_inner_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(sizeof(double) * LUC_W * (LUC_RPC_MAX + LUC_PAD))));
+  const int luc_smem = (int)(sizeof(double) * LUC_W * (LUC_RPC_MAX + LUC_PAD));
+  PMR_CHECK_CUDA(cudaFuncSetAttribute(lu_inner_panel_kernel<1>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, luc_smem));
+  PMR_CHECK_CUDA(cudaFuncSetAttribute(lu_inner_panel_kernel<2>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, luc_smem));
+  PMR_CHECK_CUDA(cudaFuncSetAttribute(lu_inner_panel_kernel<4>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, luc_smem));
   PMR_CHECK_CUDA(cudaFuncSetAttribute(lu_perm_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(sizeof(int) * LU_PERM_MAX_ROWS)));
   PMR_CHECK_CUDA(cudaFuncSetAttribute(lu_perm_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

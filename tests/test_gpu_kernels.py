@@ -376,6 +376,32 @@ def test_getrf_panel_modes_agree_bitwise():
     assert np.abs(out[0][0] - out[1][0]).max() <= 1e-11
 
 
+def test_getrf_cluster_panel_with_several_rows_per_thread():
+    """n = 9000: the cluster-resident panels start with four register-resident rows per thread, then
+    two, then one; the per-column path is the yardstick (same pivots, same factors)."""
+    from pymolresponse_b200 import _engine as eng
+
+    nv = _nv()
+    torch = nv.torch_mod()
+    n = 9000
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn(n, n, dtype=torch.float64, device="cuda", generator=g)
+    xt = torch.randn(n, 2, dtype=torch.float64, device="cuda", generator=g)
+    b = A @ xt
+    out = []
+    for mode in (1, 0):
+        nv.lib().pmr_set_lu_cluster_panel(mode)
+        Ad = A.clone()
+        ipiv, info = eng.getrf(Ad)
+        assert int(info.item()) == 0
+        out.append((Ad, ipiv.clone()))
+    nv.lib().pmr_set_lu_cluster_panel(1)
+    assert bool((out[0][1] == out[1][1]).all())
+    assert float((out[0][0] - out[1][0]).abs().max()) <= 1e-9
+    X = eng.getrs(out[0][0], out[0][1], b.clone())
+    assert float((A @ X - b).abs().max()) <= 1e-7 * float(b.abs().max())
+
+
 def test_getrf_flags_singular_matrix():
     from pymolresponse_b200 import _engine as eng
 

@@ -12,7 +12,7 @@ from pymolresponse_b200 import _native as nv  # noqa: E402
 N = 7168
 X = torch.randn(N, 256, dtype=torch.float64, device="cuda")
 A = X @ X.t() / 256 + 2.0 * torch.eye(N, dtype=torch.float64, device="cuda")
-buf = torch.zeros(32, dtype=torch.int64, device="cuda")
+buf = torch.zeros(64, dtype=torch.int64, device="cuda")
 for rep in range(2):
     K = A[:128, :128].clone()  # a single 128-block: exactly one diagonal-block launch
     Kp = torch.zeros(128, N, dtype=torch.float64, device="cuda")

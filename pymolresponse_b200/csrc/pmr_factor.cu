@@ -536,7 +536,7 @@ constexpr int LUC_CL = 8;
 constexpr int LUC_THREADS = 512;
 constexpr int LUC_RPC_MAX = 2048;  // rows per CTA: four register-resident rows per thread
 constexpr int LUC_PAD = 4;         // column stride rpc + 4: the row-wise load / store spreads over the banks
-static_assert(LUC_W == 8, "row-wise load / store below moves 8 columns per row");
+static_assert(LUC_W == 8 && LUC_CL == 8, "row-wise staging and the slot writes assume 8 columns, 8 CTAs");
 
 struct LucSlot {
   unsigned long long key;  // luc_key of the candidate's magnitude
@@ -640,39 +640,48 @@ lu_inner_panel_kernel(double* A, long long lda, int N, int k0, int pend, int j0,
       bi = lane < LUC_THREADS / 32 ? wi[lane] : 0x7fffffff;
       luc_warp_argmax(key, bi);
       LUC_TICK(2 + 5 * jj);
-      // the owner of the CTA's candidate row writes it into this CTA's slot of every CTA
-      if (key != 0ull) {
-        const int lo = bi - base;
-        if ((lo & (LUC_THREADS - 1)) == tid) {
-          const int kk = lo / LUC_THREADS;
-          double rv[LUC_W];
+      // the warp that owns the CTA's candidate row writes it into this CTA's slot of every CTA: the
+      // owner lane hands entry c to lane c, then lane 8 dd + c stores entry c at destination 4 r + dd
+      const int lo = bi - base;
+      const int owner_tid = lo & (LUC_THREADS - 1);
+      if (key != 0ull && (owner_tid >> 5) == warp) {  // uniform over the warp
+        const int kk = lo / LUC_THREADS;
+        double mine = 0.0;
 #pragma unroll
-          for (int c = 0; c < LUC_W; ++c) {
-            rv[c] = x[0][c];
+        for (int c = 0; c < LUC_W; ++c) {
+          double v = x[0][c];
 #pragma unroll
-            for (int k = 1; k < RPT; ++k)
-              if (kk == k) rv[c] = x[k][c];
-          }
-          for (int d = 0; d < LUC_CL; ++d) {
-            LucSlot* rs = cluster.map_shared_rank(&slots[par][rank], d);
-#pragma unroll
-            for (int c = 0; c < LUC_W; ++c) rs->row[c] = rv[c];
-            rs->key = key;
-            rs->idx = bi;
-          }
+          for (int k = 1; k < RPT; ++k)
+            if (kk == k) v = x[k][c];
+          v = __shfl_sync(0xffffffffu, v, owner_tid & 31);
+          if (lane == c) mine = v;
         }
-      } else if (tid == 0) {
-        for (int d = 0; d < LUC_CL; ++d) {
-          LucSlot* rs = cluster.map_shared_rank(&slots[par][rank], d);
-          rs->key = 0ull;
-          rs->idx = 0x7fffffff;
+        const int c = lane & 7;
+        const double val = __shfl_sync(0xffffffffu, mine, c);
+#pragma unroll
+        for (int r = 0; r < LUC_CL / 4; ++r) {
+          LucSlot* rs = cluster.map_shared_rank(&slots[par][rank], r * 4 + (lane >> 3));
+          rs->row[c] = val;
+          if (c == 0) { rs->key = key; rs->idx = bi; }
         }
+      } else if (key == 0ull && tid < LUC_CL) {
+        LucSlot* rs = cluster.map_shared_rank(&slots[par][rank], tid);
+        rs->key = 0ull;
+        rs->idx = 0x7fffffff;
       }
-      if (rank == 0 && tid == jj) {  // row j is local row jj of CTA 0: thread jj, k = 0
-        for (int d = 0; d < LUC_CL; ++d) {
-          double* rr = cluster.map_shared_rank(&rowj[par][0], d);
+      if (rank == 0 && warp == 0) {  // row j is local row jj of CTA 0: lane jj of warp 0, k = 0
+        double mine = 0.0;
 #pragma unroll
-          for (int c = 0; c < LUC_W; ++c) rr[c] = x[0][c];
+        for (int c = 0; c < LUC_W; ++c) {
+          const double v = __shfl_sync(0xffffffffu, x[0][c], jj);
+          if (lane == c) mine = v;
+        }
+        const int c = lane & 7;
+        const double val = __shfl_sync(0xffffffffu, mine, c);
+#pragma unroll
+        for (int r = 0; r < LUC_CL / 4; ++r) {
+          double* rr = cluster.map_shared_rank(&rowj[par][0], r * 4 + (lane >> 3));
+          rr[c] = val;
         }
       }
       LUC_TICK(3 + 5 * jj);
